@@ -1,0 +1,61 @@
+"""Import the UNMODIFIED reference modules from /root/reference  --  TEST INFRASTRUCTURE ONLY.
+
+Used by oracle/make_golden.py (and by tests that are skipped when the reference tree is
+absent, i.e. on the GPU box) to pin oracle/vitpose_oracle.py against the reference's own
+arithmetic.  Nothing on the product path imports this.
+
+The reference cannot be imported as-is in this image: vit_utils/__init__.py:4 pulls in
+vit_utils/visualization.py, which imports matplotlib.pyplot and ffmpeg (both absent).
+Empty module stubs for those names are enough (probed).
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("EASY_VITPOSE_REF", "/root/reference")
+REF_PKG = os.path.join(REF_ROOT, "easy_ViTPose")
+
+
+def available() -> bool:
+    return os.path.isdir(REF_PKG)
+
+
+def load():
+    """Returns a namespace with ViTPose, dyn_model_import, keypoints_from_heatmaps,
+    transform_preds from the reference tree."""
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REF_ROOT}")
+    sys.dont_write_bytecode = True            # the reference mount is read-only
+    for name in ("matplotlib", "matplotlib.pyplot", "ffmpeg"):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    if REF_PKG not in sys.path:
+        sys.path.insert(0, REF_PKG)
+    ns = types.SimpleNamespace()
+    ns.ViTPose = importlib.import_module("vit_models.model").ViTPose
+    ns.dyn_model_import = importlib.import_module("vit_utils.util").dyn_model_import
+    tde = importlib.import_module("vit_utils.top_down_eval")
+    ns.keypoints_from_heatmaps = tde.keypoints_from_heatmaps
+    ns.transform_preds = importlib.import_module("vit_utils.post_processing.post_transforms").transform_preds
+    return ns
+
+
+def postprocess(ns, heatmaps, org_w, org_h):
+    """What VitInference.postprocess does (easy_ViTPose/inference.py:187-205), calling the
+    reference's keypoints_from_heatmaps.  VitInference itself is not importable here
+    (top-level `from ultralytics import YOLO`, inference.py:10)."""
+    import warnings
+
+    import numpy as np
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)
+        points, prob = ns.keypoints_from_heatmaps(
+            heatmaps=heatmaps, center=np.array([[org_w // 2, org_h // 2]]),
+            scale=np.array([[org_w, org_h]]), unbiased=True, use_udp=True)
+    return np.concatenate([points[:, :, ::-1], prob], axis=2)

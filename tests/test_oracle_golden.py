@@ -1,0 +1,64 @@
+"""CPU: oracle/vitpose_oracle.py against the reference outputs committed in tests/golden/
+(made by oracle/make_golden.py from the unmodified reference).  This is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_import, vitpose_oracle as O
+
+FWD = ["s_coco", "b_coco", "l_coco_25", "h_wholebody"]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+@pytest.mark.parametrize("name", FWD)
+def test_forward_matches_reference_heatmaps(golden_dir, name):
+    g = _load(golden_dir, "fwd_" + name)
+    D, depth, heads, K, B, wseed, xseed = (int(v) for v in g["meta"])
+    sd = O.make_state_dict(D, depth, K, wseed, peaky=float(g["peaky"]))
+    hm = O.forward_heatmaps(O.make_crops(B, xseed), sd, depth, heads)
+    ref = g["heatmaps"]
+    assert hm.shape == ref.shape == (B, K, O.HM_H, O.HM_W)
+    # fp32 on both sides, different GEMM blocking: 1e-4 of a +-13 range
+    assert np.abs(hm - ref).max() < 2e-4 * np.abs(ref).max()
+    assert np.array_equal(hm.reshape(B, K, -1).argmax(-1), ref.reshape(B, K, -1).argmax(-1))
+
+
+@pytest.mark.parametrize("name", FWD)
+def test_decode_of_reference_heatmaps(golden_dir, name):
+    g = _load(golden_dir, "fwd_" + name)
+    kp, idx = O.decode_maps(g["heatmaps"], g["org_wh"], wrap="crop")
+    assert np.array_equal(kp[..., 2], g["kpts"][..., 2])          # score = raw max, exact
+    # the blur is bit-exact vs cv2; only np.log's SIMD path can differ between hosts
+    assert np.abs(kp[..., :2] - g["kpts"][..., :2]).max() < 2e-3
+
+
+@pytest.mark.parametrize("name,wrap", [("decode_crop", "crop"), ("decode_batch", "batch")])
+def test_decode_edge_cases(golden_dir, name, wrap):
+    g = _load(golden_dir, name)
+    N, K, seed = (int(v) for v in g["meta"])
+    maps = O.make_decode_maps(N, K, seed)
+    kp, idx = O.decode_maps(maps, g["org_wh"], wrap=wrap)
+    assert np.array_equal(idx, g["idx"])                            # integer argmax: bit-exact
+    assert np.array_equal(kp[..., 2], g["kpts"][..., 2])
+    ref = g["kpts"][..., :2]
+    err = np.abs(kp[..., :2] - ref)
+    kinds = (np.arange(N * K) % 10).reshape(N, K)
+    well = np.isin(kinds, [0, 1, 2, 3, 5, 7])                       # real peaks: tight
+    assert err[well].max() < 1e-3
+    # sentinel / flat / noise maps have (near-)singular Hessians: relative agreement
+    assert np.all(err[~well] <= 1e-3 + 1e-3 * np.abs(ref[~well]))
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree only exists in the build container")
+def test_live_reference_decode_matches_oracle():
+    ns = ref_import.load()
+    maps = O.make_decode_maps(2, 17, 999)
+    for i in range(2):
+        ref = ref_import.postprocess(ns, maps[i:i + 1], 200 + i, 300 + i)
+        kp, _ = O.decode_maps(maps[i:i + 1], np.array([[200 + i, 300 + i]]), wrap="crop")
+        assert np.array_equal(kp[..., 2], ref[..., 2])
+        assert np.abs(kp - ref).max() < 1e-3 + 1e-3 * np.abs(ref).max()
