@@ -1,0 +1,63 @@
+"""ctypes binding of libvitpose_b200.so (C ABI declared in include/vitpose_b200.h).
+
+The library is the product; this module only declares argument types and turns non-zero return codes
+into RuntimeError.  A missing library is a hard error: there is no Python / CPU fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB
+
+_lib = None
+
+
+class VpbConfig(C.Structure):
+    _fields_ = [("embed_dim", C.c_int32), ("depth", C.c_int32), ("num_heads", C.c_int32),
+                ("num_keypoints", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "vpb_last_error": (C.c_char_p, []),
+    "vpb_create": (C.c_int, [C.POINTER(VpbConfig), C.POINTER(C.c_void_p)]),
+    "vpb_destroy": (None, [C.c_void_p]),
+    "vpb_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "vpb_finalize": (C.c_int, [C.c_void_p]),
+    "vpb_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vpb_forward_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "vpb_decode": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vpb_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vpb_infer_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vpb_host_alloc": (C.c_void_p, [C.c_int64]),
+    "vpb_host_free": (None, [C.c_void_p]),
+    "vpb_kernel_launches": (C.c_int, [C.c_void_p, C.c_int32]),
+    "vpb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
+    "vpb_read_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "vpb_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                           C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "vpb_attention": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vpb_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+}
+
+
+def lib():
+    """Loads the shared library once.  Raises if it has not been built (python -m easy_vitpose_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise RuntimeError(f"{LIB} is missing: build it with `python -m easy_vitpose_b200.build` "
+                               "(or __graft_entry__.build()); there is no fallback implementation")
+        handle = C.CDLL(LIB)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(handle, name)          # AttributeError here = header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise RuntimeError(f"vitpose_b200 error {code}: {lib().vpb_last_error().decode()}")

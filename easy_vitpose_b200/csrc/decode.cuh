@@ -1,0 +1,166 @@
+// Heatmap decode: [N,K,64,48] f32 -> keypoints [N,K,3] (y, x, score) + flat argmax [N,K] i32.
+// HBM-bound (12 288 B read per map, 16 B written); one warp per map, 128-bit coalesced loads.
+//
+// Restates the branch VitInference takes (unbiased=True, use_udp=True, GaussianHeatmap):
+//   _get_max_preds            vit_utils/top_down_eval.py:82-114   first-index argmax, (-1,-1) if max <= 0
+//   post_dark_udp(kernel=11)  vit_utils/top_down_eval.py:354-415  cv2.GaussianBlur 11x11 -> clip -> log ->
+//                                                                 7-point Taylor step with a float64 2x2 inverse
+//   transform_preds(use_udp)  vit_utils/post_processing/post_transforms.py:183-192
+//   VitInference.postprocess  easy_ViTPose/inference.py:187-205   centre = org // 2, output order (y, x, score)
+// The blur is only evaluated at the (at most) 7 stencil points the Taylor step reads, with cv2's exact
+// float32 accumulation order (row pass: sequential fmaf left to right; column pass: centre tap then
+// fmaf of symmetric pairs), so blurred values are bit-identical to cv2 4.13 (oracle/make_golden.py).
+#pragma once
+#include "ptx.cuh"
+
+namespace vpb {
+
+constexpr int HM_H = 64, HM_W = 48, HM_PIX = HM_H * HM_W;
+
+// float32(cv2.getGaussianKernel(11, 0)) taps 0..5 (symmetric), sigma = 0.3*((11-1)*0.5-1)+0.8 = 2.0
+__device__ __constant__ float c_gauss11[6] = {0x1.20c256p-7f, 0x1.bcb86ap-6f, 0x1.0ab50ap-4f,
+                                              0x1.f2464cp-4f, 0x1.6a7e1ep-3f, 0x1.9ac20ap-3f};
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  i = i < 0 ? -i : i;
+  return i >= n ? 2 * (n - 1) - i : i;
+}
+__device__ __forceinline__ bool arg_better(float v, int i, float bv, int bi) {
+  // np.argmax order: NaN beats everything, first index wins among equals
+  const bool vn = v != v, bn = bv != bv;
+  if (vn != bn) return vn;
+  if (!vn && v != bv) return v > bv;
+  return i < bi;
+}
+
+struct DecodeParams {
+  const float* heatmaps;   // [N,K,64,48]
+  const int* org_wh;       // [N,2] crop (width, height)
+  float* kpts;             // [N,K,3]
+  int* idx;                // [N,K] (may be nullptr)
+  int n, k;
+  int wrap_batch;          // sentinel quirk: 0 = previous map wraps inside the crop, 1 = inside the whole call
+};
+
+__global__ void __launch_bounds__(256) decode_heatmaps(const DecodeParams p) {
+  __shared__ float s_rowpass[8][7][11];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * 8 + wib;                       // map index n*K + k
+  const int total = p.n * p.k;
+  if (g >= total) return;
+  const float* hm = p.heatmaps + static_cast<size_t>(g) * HM_PIX;
+
+  // ---- first-index argmax over 3072 values
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  {
+    const float4* h4 = reinterpret_cast<const float4*>(hm);
+    bool have = false;
+#pragma unroll 6
+    for (int j = 0; j < HM_PIX / 128; ++j) {
+      const float4 v = __ldg(h4 + j * 32 + lane);
+      const int base = (j * 32 + lane) * 4;
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (!have || arg_better(vv[e], base + e, bv, bi)) { bv = vv[e]; bi = base + e; have = true; }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  const float mx = bv;
+  const int amax = bi;
+  const bool positive = mx > 0.0f;
+
+  // ---- stencil points (map, x, y), order: c, x+1, y+1, x+1y+1, x-1, y-1, x-1y-1
+  int x = -1, y = -1;
+  const float* pmap[7];
+  int ptx[7], pty[7];
+  if (positive) {
+    x = amax % HM_W;
+    y = amax / HM_W;
+    const int xm = max(x - 1, 0), xp = min(x + 1, HM_W - 1), ym = max(y - 1, 0), yp = min(y + 1, HM_H - 1);
+    const int xs[7] = {x, xp, x, xp, xm, x, xm};
+    const int ys[7] = {y, y, yp, yp, y, ym, ym};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { pmap[i] = hm; ptx[i] = xs[i]; pty[i] = ys[i]; }
+  } else {
+    // (-1,-1): four reads land on this map's top-left pad corner (= l(0,0)); the three "minus" reads
+    // underflow into the previous map's padded slab: l_prev(W-1,H-1) twice and l_prev(0,H-1).
+    const int n_i = g / p.k, k_i = g % p.k;
+    const int prev = p.wrap_batch ? (g + total - 1) % total : n_i * p.k + (k_i + p.k - 1) % p.k;
+    const float* hp = p.heatmaps + static_cast<size_t>(prev) * HM_PIX;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pmap[i] = hm; ptx[i] = 0; pty[i] = 0; }
+    pmap[4] = hp; ptx[4] = HM_W - 1; pty[4] = HM_H - 1;     // ix1_   (index - 1)
+    pmap[5] = hp; ptx[5] = 0;        pty[5] = HM_H - 1;     // iy1_   (index - W - 2)
+    pmap[6] = hp; ptx[6] = HM_W - 1; pty[6] = HM_H - 1;     // ix1_y1_(index - W - 3)
+  }
+
+  // ---- row pass of the separable blur: 7 points x 11 rows, one (point,row) per lane per round
+  for (int tsk = lane; tsk < 77; tsk += 32) {
+    const int pt = tsk / 11, r = tsk % 11;
+    const float* m = pmap[0];
+    int cx = ptx[0], cy = pty[0];
+#pragma unroll
+    for (int i = 1; i < 7; ++i)
+      if (pt == i) { m = pmap[i]; cx = ptx[i]; cy = pty[i]; }
+    const float* rowp = m + reflect101(cy - 5 + r, HM_H) * HM_W;
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 11; ++j) acc = __fmaf_rn(c_gauss11[j < 6 ? j : 10 - j], __ldg(rowp + reflect101(cx - 5 + j, HM_W)), acc);
+    s_rowpass[wib][pt][r] = acc;
+  }
+  __syncwarp();
+  // ---- column pass + clip + log on lanes 0..6
+  float l = 0.0f;
+  if (lane < 7) {
+    const float* rp = s_rowpass[wib][lane];
+    float acc = __fmul_rn(c_gauss11[5], rp[5]);
+#pragma unroll
+    for (int d = 1; d <= 5; ++d) acc = __fmaf_rn(c_gauss11[5 - d], __fadd_rn(rp[5 + d], rp[5 - d]), acc);
+    l = logf(fminf(fmaxf(acc, 1e-3f), 50.0f));
+  }
+  const float i_ = __shfl_sync(0xffffffffu, l, 0), ix1 = __shfl_sync(0xffffffffu, l, 1);
+  const float iy1 = __shfl_sync(0xffffffffu, l, 2), ix1y1 = __shfl_sync(0xffffffffu, l, 3);
+  const float ix1_ = __shfl_sync(0xffffffffu, l, 4), iy1_ = __shfl_sync(0xffffffffu, l, 5);
+  const float ix1_y1_ = __shfl_sync(0xffffffffu, l, 6);
+
+  if (lane == 0) {
+    const float dx = __fmul_rn(0.5f, __fsub_rn(ix1, ix1_));
+    const float dy = __fmul_rn(0.5f, __fsub_rn(iy1, iy1_));
+    const float two_i = __fmul_rn(2.0f, i_);
+    const float dxx = __fadd_rn(__fsub_rn(ix1, two_i), ix1_);
+    const float dyy = __fadd_rn(__fsub_rn(iy1, two_i), iy1_);
+    float t = __fsub_rn(ix1y1, ix1);
+    t = __fsub_rn(t, iy1);
+    t = __fadd_rn(t, i_);
+    t = __fadd_rn(t, i_);
+    t = __fsub_rn(t, ix1_);
+    t = __fsub_rn(t, iy1_);
+    t = __fadd_rn(t, ix1_y1_);
+    const float dxy = __fmul_rn(0.5f, t);
+    // float64 2x2 inverse of H + eps*I (top_down_eval.py:413), then coords -= H^-1 g (:414)
+    const double eps = 1.1920928955078125e-07;
+    const double a = static_cast<double>(dxx) + eps, b = static_cast<double>(dxy), d = static_cast<double>(dyy) + eps;
+    const double det = a * d - b * b;
+    const double offx = (d * static_cast<double>(dx) - b * static_cast<double>(dy)) / det;
+    const double offy = (a * static_cast<double>(dy) - b * static_cast<double>(dx)) / det;
+    const float xr = static_cast<float>(static_cast<double>(x) - offx);
+    const float yr = static_cast<float>(static_cast<double>(y) - offy);
+    const int n_i = g / p.k;
+    const int ow = p.org_wh[2 * n_i], oh = p.org_wh[2 * n_i + 1];
+    const float X = static_cast<float>(static_cast<double>(xr) * (ow / (HM_W - 1.0)) + static_cast<double>(ow / 2) - ow * 0.5);
+    const float Y = static_cast<float>(static_cast<double>(yr) * (oh / (HM_H - 1.0)) + static_cast<double>(oh / 2) - oh * 0.5);
+    float* o = p.kpts + static_cast<size_t>(g) * 3;
+    o[0] = Y; o[1] = X; o[2] = mx;
+    if (p.idx != nullptr) p.idx[g] = amax;
+  }
+}
+
+}  // namespace vpb

@@ -1,0 +1,609 @@
+// libvitpose_b200.so: the engine object behind include/vitpose_b200.h.
+// Owns the packed weights, the activation workspace and the TMA tensor maps; enqueues the kernel chain
+//   patch_im2col -> GEMM(+pos) -> depth x [LN -> GEMM qkv -> attention -> GEMM proj(+res) -> LN -> GEMM fc1(GELU)
+//   -> GEMM fc2(+res)] -> LN -> 2 x [phase im2col -> 4 GEMM(BN+ReLU)] -> GEMM 1x1 (NCHW heatmaps) -> decode
+// on the caller's stream.  No host synchronisation on the hot path, no CPU fallback.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vitpose_b200.h"
+#include "attention.cuh"
+#include "decode.cuh"
+#include "gemm.cuh"
+#include "pointwise.cuh"
+
+using namespace vpb;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU_TRY(expr)                                                                                  \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) return fail(VPB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+#define VPB_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != VPB_OK) return _r; \
+  } while (0)
+
+extern "C" const char* vpb_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------------ TMA maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int load_driver_api() {
+  if (g_encode) return VPB_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return fail(VPB_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return VPB_OK;
+}
+// bf16 row-major [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols] (128 B) 128B-swizzled.
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  VPB_TRY(load_driver_api());
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VPB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%u", (int)r,
+                                     (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+  return VPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM dispatch
+static int g_num_sms = 0;
+static bool g_attr_done = false;
+
+template <int BN, int EPI>
+static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_tcgen05<BN, EPI>;
+  static bool attr = false;
+  if (!attr) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr = true;
+  }
+  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tw, p);
+  CU_TRY(cudaGetLastError());
+  return VPB_OK;
+}
+static int gemm_launch(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
+  if (p.K % GEMM_BK != 0 || p.K <= 0) return fail(VPB_ERR_ARG, "gemm: K=%d must be a positive multiple of 64", p.K);
+#define VPB_CASE(BN_, EPI_) \
+  if (bn == BN_ && epi == EPI_) return gemm_launch_t<BN_, EPI_>(ta, tw, p, st);
+  VPB_CASE(256, EPI_BF16) VPB_CASE(128, EPI_BF16)
+  VPB_CASE(256, EPI_BF16_GELU) VPB_CASE(128, EPI_BF16_GELU)
+  VPB_CASE(256, EPI_F32_RESID) VPB_CASE(128, EPI_F32_RESID)
+  VPB_CASE(256, EPI_BF16_RELU_UP)
+  VPB_CASE(32, EPI_F32_NCHW) VPB_CASE(144, EPI_F32_NCHW)
+#undef VPB_CASE
+  return fail(VPB_ERR_ARG, "gemm: no kernel for BN=%d epilogue=%d", bn, epi);
+}
+static int bn_for(int n) { return (n % 256 == 0) ? 256 : 128; }
+
+static int device_check(int device) {
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(VPB_ERR_ARG, "device %d is sm_%d%d; this library only runs on sm_100 (B200), no fallback", device,
+                                    prop.major, prop.minor);
+  g_num_sms = prop.multiProcessorCount;
+  if (!g_attr_done) {
+    CU_TRY(cudaFuncSetAttribute(attention_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    g_attr_done = true;
+  }
+  return VPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ engine
+struct LinearW {
+  __nv_bfloat16* w = nullptr;   // [N,K] bf16
+  float* b = nullptr;           // [N padded]
+  int n = 0, k = 0, bn = 0;
+  CUtensorMap map;
+};
+struct BlockW {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  LinearW qkv, proj, fc1, fc2;
+};
+struct vpb_engine {
+  vpb_config cfg;
+  int D, depth, heads, K, maxB, n_final;   // n_final = padded channel count of the 1x1 conv GEMM
+  bool finalized = false;
+  int stop_after = 0, attn_v_manual = 0;
+  std::map<std::string, std::pair<float*, int64_t>> staged;   // fp32 state_dict tensors on device until finalize
+  std::vector<void*> allocs;
+  // packed weights
+  LinearW patch;            // bias unused (folded into pos_bias)
+  float* pos_bias = nullptr;   // [192, D]
+  std::vector<BlockW> blocks;
+  float *lnf_g = nullptr, *lnf_b = nullptr;
+  LinearW dc1[4], dc2[4], fin;
+  // workspace
+  __nv_bfloat16 *patch_rows, *xn, *qkv, *attn, *hid, *col1, *d1, *col2, *d2;
+  float *x, *heat, *kpts;
+  int32_t *idx, *org_wh;
+  CUtensorMap m_patch_rows, m_xn, m_attn, m_hid, m_col1[4], m_col2[4], m_d2, m_qkv_att;
+};
+
+template <typename T>
+static int dev_alloc(vpb_engine* e, T** p, size_t count) {
+  void* q = nullptr;
+  CU_TRY(cudaMalloc(&q, count * sizeof(T) + 256));
+  e->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return VPB_OK;
+}
+
+static std::vector<std::pair<std::string, int64_t>> expected_keys(const vpb_engine* e) {
+  const int64_t D = e->D, K = e->K;
+  std::vector<std::pair<std::string, int64_t>> v;
+  v.push_back({"backbone.pos_embed", 193 * D});
+  v.push_back({"backbone.patch_embed.proj.weight", D * 768});
+  v.push_back({"backbone.patch_embed.proj.bias", D});
+  for (int i = 0; i < e->depth; ++i) {
+    const std::string p = "backbone.blocks." + std::to_string(i) + ".";
+    v.push_back({p + "norm1.weight", D}); v.push_back({p + "norm1.bias", D});
+    v.push_back({p + "attn.qkv.weight", 3 * D * D}); v.push_back({p + "attn.qkv.bias", 3 * D});
+    v.push_back({p + "attn.proj.weight", D * D}); v.push_back({p + "attn.proj.bias", D});
+    v.push_back({p + "norm2.weight", D}); v.push_back({p + "norm2.bias", D});
+    v.push_back({p + "mlp.fc1.weight", 4 * D * D}); v.push_back({p + "mlp.fc1.bias", 4 * D});
+    v.push_back({p + "mlp.fc2.weight", 4 * D * D}); v.push_back({p + "mlp.fc2.bias", D});
+  }
+  v.push_back({"backbone.last_norm.weight", D}); v.push_back({"backbone.last_norm.bias", D});
+  int64_t cin = D;
+  for (int li : {0, 3}) {
+    const std::string p = "keypoint_head.deconv_layers.";
+    v.push_back({p + std::to_string(li) + ".weight", cin * 256 * 16});
+    for (const char* s : {".weight", ".bias", ".running_mean", ".running_var"}) v.push_back({p + std::to_string(li + 1) + s, 256});
+    cin = 256;
+  }
+  v.push_back({"keypoint_head.final_layer.weight", K * 256});
+  v.push_back({"keypoint_head.final_layer.bias", K});
+  return v;
+}
+
+extern "C" int vpb_create(const vpb_config* cfg, vpb_engine** out) {
+  if (!cfg || !out) return fail(VPB_ERR_ARG, "vpb_create: null argument");
+  *out = nullptr;
+  if (cfg->embed_dim % 128 != 0 || cfg->num_heads <= 0 || cfg->embed_dim % cfg->num_heads != 0)
+    return fail(VPB_ERR_ARG, "embed_dim=%d / num_heads=%d unsupported", cfg->embed_dim, cfg->num_heads);
+  if (cfg->embed_dim / cfg->num_heads != 64)
+    return fail(VPB_ERR_ARG, "head_dim=%d: the attention kernel currently covers head_dim 64 (ViT-B, ViT-L)",
+                cfg->embed_dim / cfg->num_heads);
+  if (cfg->embed_dim != 384 && cfg->embed_dim != 768 && cfg->embed_dim != 1024 && cfg->embed_dim != 1280)
+    return fail(VPB_ERR_ARG, "embed_dim=%d has no LayerNorm instantiation", cfg->embed_dim);
+  if (cfg->num_keypoints < 1 || cfg->num_keypoints > 144) return fail(VPB_ERR_ARG, "num_keypoints=%d out of range 1..144", cfg->num_keypoints);
+  if (cfg->max_batch < 1 || cfg->depth < 1) return fail(VPB_ERR_ARG, "max_batch/depth must be >= 1");
+  CU_TRY(cudaSetDevice(cfg->device));
+  VPB_TRY(device_check(cfg->device));
+  vpb_engine* e = new vpb_engine();
+  e->cfg = *cfg;
+  e->D = cfg->embed_dim; e->depth = cfg->depth; e->heads = cfg->num_heads; e->K = cfg->num_keypoints; e->maxB = cfg->max_batch;
+  e->n_final = e->K <= 32 ? 32 : 144;
+  *out = e;
+  return VPB_OK;
+}
+
+extern "C" void vpb_destroy(vpb_engine* e) {
+  if (!e) return;
+  for (auto& kv : e->staged) cudaFree(kv.second.first);
+  for (void* p : e->allocs) cudaFree(p);
+  delete e;
+}
+
+extern "C" int vpb_load_tensor(vpb_engine* e, const char* key, const float* data, int64_t numel) {
+  if (!e || !key || (!data && numel > 0)) return fail(VPB_ERR_ARG, "vpb_load_tensor: null argument");
+  if (e->finalized) return fail(VPB_ERR_STATE, "vpb_load_tensor after vpb_finalize");
+  const std::string k(key);
+  if (k.size() > 19 && k.compare(k.size() - 19, 19, "num_batches_tracked") == 0) return VPB_OK;
+  bool known = false;
+  for (auto& kv : expected_keys(e))
+    if (kv.first == k) {
+      known = true;
+      if (kv.second != numel) return fail(VPB_ERR_ARG, "size mismatch for %s: got %lld elements, expected %lld", key, (long long)numel, (long long)kv.second);
+    }
+  if (!known) return fail(VPB_ERR_ARG, "unexpected key in state_dict: %s", key);
+  if (e->staged.count(k)) return fail(VPB_ERR_ARG, "duplicate key: %s", key);
+  CU_TRY(cudaSetDevice(e->cfg.device));
+  float* d = nullptr;
+  CU_TRY(cudaMalloc(&d, numel * sizeof(float)));
+  CU_TRY(cudaMemcpy(d, data, numel * sizeof(float), cudaMemcpyHostToDevice));
+  e->staged[k] = {d, numel};
+  return VPB_OK;
+}
+
+static inline int cdiv(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+static int pack_linear(vpb_engine* e, LinearW& L, const std::string& wkey, const std::string& bkey, int n, int k, int bn,
+                       int scaled_rows, float scale) {
+  L.n = n; L.k = k; L.bn = bn;
+  const int n_pad = cdiv(n, bn) * bn;
+  VPB_TRY(dev_alloc(e, &L.w, static_cast<size_t>(n_pad) * k));
+  CU_TRY(cudaMemset(L.w, 0, static_cast<size_t>(n_pad) * k * 2));
+  const long long ne = static_cast<long long>(n) * k;
+  pack_linear_bf16<<<cdiv(ne, 256), 256>>>(e->staged[wkey].first, L.w, ne, k, scaled_rows, scale);
+  VPB_TRY(dev_alloc(e, &L.b, n_pad));
+  if (!bkey.empty()) pack_bias<<<cdiv(n_pad, 256), 256>>>(e->staged[bkey].first, L.b, n, n_pad, scaled_rows, scale);
+  else CU_TRY(cudaMemset(L.b, 0, n_pad * sizeof(float)));
+  CU_TRY(cudaGetLastError());
+  return make_map(&L.map, L.w, n_pad, k, k, bn);
+}
+
+static int copy_vec(vpb_engine* e, float** dst, const std::string& key) {
+  auto& s = e->staged[key];
+  VPB_TRY(dev_alloc(e, dst, s.second));
+  CU_TRY(cudaMemcpy(*dst, s.first, s.second * sizeof(float), cudaMemcpyDeviceToDevice));
+  return VPB_OK;
+}
+
+extern "C" int vpb_finalize(vpb_engine* e) {
+  if (!e) return fail(VPB_ERR_ARG, "vpb_finalize: null engine");
+  if (e->finalized) return fail(VPB_ERR_STATE, "vpb_finalize called twice");
+  for (auto& kv : expected_keys(e))
+    if (!e->staged.count(kv.first)) return fail(VPB_ERR_ARG, "missing key in state_dict: %s", kv.first.c_str());
+  CU_TRY(cudaSetDevice(e->cfg.device));
+  const int D = e->D;
+  const float qscale = 1.0f / sqrtf(static_cast<float>(D / e->heads));
+
+  VPB_TRY(pack_linear(e, e->patch, "backbone.patch_embed.proj.weight", "", D, 768, bn_for(D), 0, 1.f));
+  VPB_TRY(dev_alloc(e, &e->pos_bias, 192 * D));
+  pack_pos_bias<<<cdiv(192 * D, 256), 256>>>(e->staged["backbone.pos_embed"].first, e->staged["backbone.patch_embed.proj.bias"].first,
+                                              e->pos_bias, 192, D);
+  e->blocks.resize(e->depth);
+  for (int i = 0; i < e->depth; ++i) {
+    const std::string p = "backbone.blocks." + std::to_string(i) + ".";
+    BlockW& b = e->blocks[i];
+    VPB_TRY(copy_vec(e, &b.ln1_g, p + "norm1.weight")); VPB_TRY(copy_vec(e, &b.ln1_b, p + "norm1.bias"));
+    VPB_TRY(copy_vec(e, &b.ln2_g, p + "norm2.weight")); VPB_TRY(copy_vec(e, &b.ln2_b, p + "norm2.bias"));
+    // q rows (first D) carry head_dim^-0.5: vit.py:170 scales q before QK^T; fp32 multiply, then bf16 rounding
+    VPB_TRY(pack_linear(e, b.qkv, p + "attn.qkv.weight", p + "attn.qkv.bias", 3 * D, D, bn_for(3 * D), D, qscale));
+    VPB_TRY(pack_linear(e, b.proj, p + "attn.proj.weight", p + "attn.proj.bias", D, D, bn_for(D), 0, 1.f));
+    VPB_TRY(pack_linear(e, b.fc1, p + "mlp.fc1.weight", p + "mlp.fc1.bias", 4 * D, D, bn_for(4 * D), 0, 1.f));
+    VPB_TRY(pack_linear(e, b.fc2, p + "mlp.fc2.weight", p + "mlp.fc2.bias", D, 4 * D, bn_for(D), 0, 1.f));
+  }
+  VPB_TRY(copy_vec(e, &e->lnf_g, "backbone.last_norm.weight"));
+  VPB_TRY(copy_vec(e, &e->lnf_b, "backbone.last_norm.bias"));
+  // deconv layers: 4 phase matrices [256, 4*Cin] each, BN folded (eps 1e-5 = nn.BatchNorm2d default)
+  int cin = D;
+  for (int layer = 0; layer < 2; ++layer) {
+    LinearW* dc = layer == 0 ? e->dc1 : e->dc2;
+    const std::string wk = "keypoint_head.deconv_layers." + std::to_string(layer * 3) + ".weight";
+    const std::string bnp = "keypoint_head.deconv_layers." + std::to_string(layer * 3 + 1) + ".";
+    __nv_bfloat16* wp; float* shift;
+    VPB_TRY(dev_alloc(e, &wp, static_cast<size_t>(4) * 256 * 4 * cin));
+    VPB_TRY(dev_alloc(e, &shift, 256));
+    const long long tot = 4LL * 256 * 4 * cin;
+    pack_deconv<<<cdiv(tot, 256), 256>>>(e->staged[wk].first, e->staged[bnp + "weight"].first, e->staged[bnp + "bias"].first,
+                                         e->staged[bnp + "running_mean"].first, e->staged[bnp + "running_var"].first, wp, shift,
+                                         cin, 256, 1e-5f);
+    CU_TRY(cudaGetLastError());
+    for (int ph = 0; ph < 4; ++ph) {
+      dc[ph].w = wp + static_cast<size_t>(ph) * 256 * 4 * cin; dc[ph].b = shift; dc[ph].n = 256; dc[ph].k = 4 * cin; dc[ph].bn = 256;
+      VPB_TRY(make_map(&dc[ph].map, dc[ph].w, 256, 4 * cin, 4 * cin, 256));
+    }
+    cin = 256;
+  }
+  {  // final 1x1 conv: [K,256] zero-padded to the N tile
+    LinearW& L = e->fin;
+    VPB_TRY(pack_linear(e, L, "keypoint_head.final_layer.weight", "keypoint_head.final_layer.bias", e->K, 256, e->n_final, 0, 1.f));
+  }
+  // ---- workspace for max_batch crops
+  const size_t B = e->maxB, M = B * 192;
+  VPB_TRY(dev_alloc(e, &e->patch_rows, M * 768));
+  VPB_TRY(dev_alloc(e, &e->x, M * D));
+  VPB_TRY(dev_alloc(e, &e->xn, M * D));
+  VPB_TRY(dev_alloc(e, &e->qkv, M * 3 * D));
+  VPB_TRY(dev_alloc(e, &e->attn, M * D));
+  VPB_TRY(dev_alloc(e, &e->hid, M * 4 * D));
+  VPB_TRY(dev_alloc(e, &e->col1, 4 * M * 4 * D));
+  VPB_TRY(dev_alloc(e, &e->d1, B * 768 * 256));
+  VPB_TRY(dev_alloc(e, &e->col2, 4 * B * 768 * 1024));
+  VPB_TRY(dev_alloc(e, &e->d2, B * 3072 * 256));
+  VPB_TRY(dev_alloc(e, &e->heat, B * e->K * 3072));
+  VPB_TRY(dev_alloc(e, &e->kpts, B * e->K * 3));
+  VPB_TRY(dev_alloc(e, &e->idx, B * e->K));
+  VPB_TRY(dev_alloc(e, &e->org_wh, B * 2));
+  VPB_TRY(make_map(&e->m_patch_rows, e->patch_rows, M, 768, 768, 128));
+  VPB_TRY(make_map(&e->m_xn, e->xn, M, D, D, 128));
+  VPB_TRY(make_map(&e->m_attn, e->attn, M, D, D, 128));
+  VPB_TRY(make_map(&e->m_hid, e->hid, M, 4 * D, 4 * D, 128));
+  for (int ph = 0; ph < 4; ++ph) {
+    VPB_TRY(make_map(&e->m_col1[ph], e->col1 + ph * M * 4 * D, M, 4 * D, 4 * D, 128));
+    VPB_TRY(make_map(&e->m_col2[ph], e->col2 + ph * B * 768 * 1024, B * 768, 1024, 1024, 128));
+  }
+  VPB_TRY(make_map(&e->m_d2, e->d2, B * 3072, 256, 256, 128));
+  VPB_TRY(make_map(&e->m_qkv_att, e->qkv, M, 3 * D, 3 * D, 192));
+  CU_TRY(cudaDeviceSynchronize());
+  for (auto& kv : e->staged) cudaFree(kv.second.first);
+  e->staged.clear();
+  e->finalized = true;
+  return VPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int D>
+static void ln_launch(const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, float eps, cudaStream_t st) {
+  layernorm_f32_to_bf16<D><<<cdiv(rows, 8), 256, 0, st>>>(x, g, b, y, rows, eps);
+}
+static int layernorm(const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, int D, float eps, cudaStream_t st) {
+  switch (D) {
+    case 384: ln_launch<384>(x, g, b, y, rows, eps, st); break;
+    case 768: ln_launch<768>(x, g, b, y, rows, eps, st); break;
+    case 1024: ln_launch<1024>(x, g, b, y, rows, eps, st); break;
+    case 1280: ln_launch<1280>(x, g, b, y, rows, eps, st); break;
+    default: return fail(VPB_ERR_ARG, "layernorm: dim %d not instantiated", D);
+  }
+  CU_TRY(cudaGetLastError());
+  return VPB_OK;
+}
+
+static GemmParams gp(int M, int N, int K, const float* bias, void* out, int ldc) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldc = ldc;
+  return p;
+}
+
+// stop_after stages (debug): 1 patch rows, 2 patch embed, 3 first LN, 4 first qkv, 5 first attention, 6 first proj,
+// 7 first fc1, 8 first block, 9 all blocks, 10 last norm, 11 deconv1, 12 deconv2
+static int backbone(vpb_engine* e, const float* d_crops, int B, cudaStream_t st) {
+  const int D = e->D, M = B * 192;
+  const int stop = e->stop_after;
+  patch_im2col<<<cdiv(static_cast<long long>(B) * 3 * 256 * 24, 256), 256, 0, st>>>(d_crops, e->patch_rows, B);
+  CU_TRY(cudaGetLastError());
+  if (stop == 1) return VPB_OK;
+  {  // tokens = rows * Wpatch^T + (pos_embed[1+t] + pos_embed[0] + conv bias)
+    GemmParams p = gp(M, D, 768, nullptr, e->x, D);
+    p.resid = e->pos_bias; p.resid_mod = 192;
+    VPB_TRY(gemm_launch(e->patch.bn, EPI_F32_RESID, e->m_patch_rows, e->patch.map, p, st));
+  }
+  if (stop == 2) return VPB_OK;
+  for (int i = 0; i < e->depth; ++i) {
+    BlockW& b = e->blocks[i];
+    VPB_TRY(layernorm(e->x, b.ln1_g, b.ln1_b, e->xn, M, D, 1e-6f, st));
+    if (stop == 3) return VPB_OK;
+    VPB_TRY(gemm_launch(b.qkv.bn, EPI_BF16, e->m_xn, b.qkv.map, gp(M, 3 * D, D, b.qkv.b, e->qkv, 3 * D), st));
+    if (stop == 4) return VPB_OK;
+    {
+      AttnParams ap;
+      ap.batch = B; ap.heads = e->heads; ap.dim = D; ap.out = e->attn; ap.qkv = e->qkv; ap.v_manual = e->attn_v_manual;
+      const int items = B * e->heads;
+      attention_tcgen05<<<items < g_num_sms ? items : g_num_sms, ATT_THREADS, ATT_SMEM, st>>>(e->m_qkv_att, ap);
+      CU_TRY(cudaGetLastError());
+    }
+    if (stop == 5) return VPB_OK;
+    {
+      GemmParams p = gp(M, D, D, b.proj.b, e->x, D);
+      p.resid = e->x;
+      VPB_TRY(gemm_launch(b.proj.bn, EPI_F32_RESID, e->m_attn, b.proj.map, p, st));
+    }
+    if (stop == 6) return VPB_OK;
+    VPB_TRY(layernorm(e->x, b.ln2_g, b.ln2_b, e->xn, M, D, 1e-6f, st));
+    VPB_TRY(gemm_launch(b.fc1.bn, EPI_BF16_GELU, e->m_xn, b.fc1.map, gp(M, 4 * D, D, b.fc1.b, e->hid, 4 * D), st));
+    if (stop == 7) return VPB_OK;
+    {
+      GemmParams p = gp(M, D, 4 * D, b.fc2.b, e->x, D);
+      p.resid = e->x;
+      VPB_TRY(gemm_launch(b.fc2.bn, EPI_F32_RESID, e->m_hid, b.fc2.map, p, st));
+    }
+    if (stop == 8) return VPB_OK;
+  }
+  if (stop == 9) return VPB_OK;
+  return layernorm(e->x, e->lnf_g, e->lnf_b, e->xn, M, D, 1e-6f, st);
+}
+
+static int head(vpb_engine* e, int B, float* d_heat, cudaStream_t st) {
+  const int D = e->D;
+  const int stop = e->stop_after;
+  // deconv 1: tokens (NHWC 16x12xD) -> d1 (NHWC 32x24x256)
+  {
+    const int M = B * 192;
+    const long long tot = static_cast<long long>(M) * 4 * (D / 8);
+    deconv_phase_im2col<<<dim3(cdiv(tot, 256), 4), 256, 0, st>>>(e->xn, e->col1, B, 16, 12, D, static_cast<size_t>(e->maxB) * 192 * 4 * D);
+    CU_TRY(cudaGetLastError());
+    for (int ph = 0; ph < 4; ++ph) {
+      GemmParams p = gp(M, 256, 4 * D, e->dc1[ph].b, e->d1, 256);
+      p.up_h = 16; p.up_w = 12; p.up_py = ph >> 1; p.up_px = ph & 1;
+      VPB_TRY(gemm_launch(256, EPI_BF16_RELU_UP, e->m_col1[ph], e->dc1[ph].map, p, st));
+    }
+  }
+  if (stop == 11) return VPB_OK;
+  {
+    const int M = B * 768;
+    const long long tot = static_cast<long long>(M) * 4 * (256 / 8);
+    deconv_phase_im2col<<<dim3(cdiv(tot, 256), 4), 256, 0, st>>>(e->d1, e->col2, B, 32, 24, 256, static_cast<size_t>(e->maxB) * 768 * 1024);
+    CU_TRY(cudaGetLastError());
+    for (int ph = 0; ph < 4; ++ph) {
+      GemmParams p = gp(M, 256, 1024, e->dc2[ph].b, e->d2, 256);
+      p.up_h = 32; p.up_w = 24; p.up_py = ph >> 1; p.up_px = ph & 1;
+      VPB_TRY(gemm_launch(256, EPI_BF16_RELU_UP, e->m_col2[ph], e->dc2[ph].map, p, st));
+    }
+  }
+  if (stop == 12) return VPB_OK;
+  {
+    GemmParams p = gp(B * 3072, e->n_final, 256, e->fin.b, d_heat, 0);
+    p.n_valid = e->K; p.pix = 3072;
+    VPB_TRY(gemm_launch(e->n_final, EPI_F32_NCHW, e->m_d2, e->fin.map, p, st));
+  }
+  return VPB_OK;
+}
+
+static int check_ready(vpb_engine* e, int batch) {
+  if (!e) return fail(VPB_ERR_ARG, "null engine");
+  if (!e->finalized) return fail(VPB_ERR_STATE, "weights not finalized: call vpb_finalize first");
+  if (batch < 1 || batch > e->maxB) return fail(VPB_ERR_ARG, "batch %d outside 1..max_batch=%d", batch, e->maxB);
+  return VPB_OK;
+}
+
+extern "C" int vpb_forward(vpb_engine* e, const float* d_crops, int32_t batch, float* d_heatmaps, void* stream) {
+  VPB_TRY(check_ready(e, batch));
+  if (!d_crops || !d_heatmaps) return fail(VPB_ERR_ARG, "vpb_forward: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VPB_TRY(backbone(e, d_crops, batch, st));
+  if (e->stop_after && e->stop_after <= 10) return VPB_OK;
+  return head(e, batch, d_heatmaps, st);
+}
+
+extern "C" int vpb_forward_features(vpb_engine* e, const float* d_crops, int32_t batch, float* d_features, void* stream) {
+  VPB_TRY(check_ready(e, batch));
+  if (!d_crops || !d_features) return fail(VPB_ERR_ARG, "vpb_forward_features: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VPB_TRY(backbone(e, d_crops, batch, st));
+  const long long tot = static_cast<long long>(batch) * e->D * 192;
+  tokens_to_nchw<<<cdiv(tot, 256), 256, 0, st>>>(e->xn, d_features, batch, e->D);
+  CU_TRY(cudaGetLastError());
+  return VPB_OK;
+}
+
+extern "C" int vpb_decode(const float* d_heatmaps, int32_t n, int32_t k, const int32_t* d_org_wh, float* d_kpts, int32_t* d_idx,
+                          int32_t wrap_batch, void* stream) {
+  if (!d_heatmaps || !d_org_wh || !d_kpts) return fail(VPB_ERR_ARG, "vpb_decode: null pointer");
+  if (n < 0 || k < 1) return fail(VPB_ERR_ARG, "vpb_decode: n=%d k=%d", n, k);
+  if (n == 0) return VPB_OK;
+  DecodeParams p;
+  p.heatmaps = d_heatmaps; p.org_wh = d_org_wh; p.kpts = d_kpts; p.idx = d_idx; p.n = n; p.k = k; p.wrap_batch = wrap_batch;
+  decode_heatmaps<<<cdiv(static_cast<long long>(n) * k, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  CU_TRY(cudaGetLastError());
+  return VPB_OK;
+}
+
+extern "C" int vpb_infer(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, int32_t batch, float* d_kpts, int32_t* d_idx,
+                         float* d_heatmaps, void* stream) {
+  VPB_TRY(check_ready(e, batch));
+  if (!d_crops || !d_org_wh || !d_kpts) return fail(VPB_ERR_ARG, "vpb_infer: null pointer");
+  float* heat = d_heatmaps ? d_heatmaps : e->heat;
+  VPB_TRY(vpb_forward(e, d_crops, batch, heat, stream));
+  if (e->stop_after) return VPB_OK;
+  return vpb_decode(heat, batch, e->K, d_org_wh, d_kpts, d_idx, 0, stream);
+}
+
+extern "C" int vpb_infer_host(vpb_engine* e, const float* h_crops, const int32_t* h_org_wh, int32_t batch, float* h_kpts,
+                              int32_t* h_idx, void* stream) {
+  VPB_TRY(check_ready(e, batch));
+  if (!h_crops || !h_org_wh || !h_kpts) return fail(VPB_ERR_ARG, "vpb_infer_host: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the crop staging buffer aliases the im2col scratch of deconv 2 (unused until the head runs, and the
+  // patch gather has consumed the crops long before): [B,3,256,192] f32 = 589 824 B/crop <= 4*768*1024*2 B/crop
+  float* d_crops = reinterpret_cast<float*>(e->col2);
+  CU_TRY(cudaMemcpyAsync(d_crops, h_crops, static_cast<size_t>(batch) * 3 * 256 * 192 * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(e->org_wh, h_org_wh, static_cast<size_t>(batch) * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  VPB_TRY(vpb_infer(e, d_crops, e->org_wh, batch, e->kpts, e->idx, nullptr, st));
+  CU_TRY(cudaMemcpyAsync(h_kpts, e->kpts, static_cast<size_t>(batch) * e->K * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (h_idx) CU_TRY(cudaMemcpyAsync(h_idx, e->idx, static_cast<size_t>(batch) * e->K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VPB_OK;
+}
+
+extern "C" void* vpb_host_alloc(int64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, static_cast<size_t>(bytes), cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+extern "C" void vpb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+extern "C" int vpb_kernel_launches(const vpb_engine* e, int32_t) {
+  if (!e) return -1;
+  // patch im2col + patch GEMM + depth*(LN, qkv, attention, proj, LN, fc1, fc2) + LN + 2*(im2col + 4 GEMM) + 1x1 GEMM + decode
+  return 2 + e->depth * 7 + 1 + 2 * 5 + 1 + 1;
+}
+
+extern "C" int vpb_set_option(vpb_engine* e, const char* name, int32_t value) {
+  if (!e || !name) return fail(VPB_ERR_ARG, "vpb_set_option: null argument");
+  if (!strcmp(name, "stop_after")) e->stop_after = value;
+  else if (!strcmp(name, "attn_v_manual")) e->attn_v_manual = value;
+  else return fail(VPB_ERR_ARG, "unknown option %s", name);
+  return VPB_OK;
+}
+
+extern "C" int vpb_read_buffer(vpb_engine* e, const char* name, void* host_dst, int64_t bytes) {
+  if (!e || !name || !host_dst) return fail(VPB_ERR_ARG, "vpb_read_buffer: null argument");
+  if (!e->finalized) return fail(VPB_ERR_STATE, "not finalized");
+  const void* src = nullptr;
+  const std::string n(name);
+  if (n == "patch_rows") src = e->patch_rows;
+  else if (n == "x") src = e->x;
+  else if (n == "xn") src = e->xn;
+  else if (n == "qkv") src = e->qkv;
+  else if (n == "attn") src = e->attn;
+  else if (n == "hid") src = e->hid;
+  else if (n == "d1") src = e->d1;
+  else if (n == "d2") src = e->d2;
+  else if (n == "heat") src = e->heat;
+  else return fail(VPB_ERR_ARG, "unknown buffer %s", name);
+  CU_TRY(cudaDeviceSynchronize());
+  CU_TRY(cudaMemcpy(host_dst, src, bytes, cudaMemcpyDeviceToHost));
+  return VPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel-level entry points
+extern "C" int vpb_gemm(const void* d_a, const void* d_w, const float* d_bias, void* d_out, int32_t m, int32_t n, int32_t k,
+                        int32_t epilogue, const float* d_resid, int32_t resid_mod, int32_t aux0, int32_t aux1, int32_t aux2,
+                        int32_t aux3, void* stream) {
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  VPB_TRY(device_check(dev));
+  if (!d_a || !d_w || !d_out) return fail(VPB_ERR_ARG, "vpb_gemm: null pointer");
+  int bn;
+  if (epilogue == EPI_F32_NCHW) bn = n <= 32 ? 32 : 144;
+  else if (epilogue == EPI_BF16_RELU_UP) bn = 256;
+  else bn = bn_for(n);
+  if (epilogue != EPI_F32_NCHW && n % bn != 0) return fail(VPB_ERR_ARG, "vpb_gemm: N=%d must be a multiple of %d", n, bn);
+  if (epilogue == EPI_F32_NCHW && n != bn) return fail(VPB_ERR_ARG, "vpb_gemm: NCHW epilogue wants W padded to %d rows", bn);
+  CUtensorMap ta, tw;
+  VPB_TRY(make_map(&ta, d_a, m, k, k, 128));
+  VPB_TRY(make_map(&tw, d_w, n, k, k, bn));
+  GemmParams p = gp(m, n, k, d_bias, d_out, n);
+  p.resid = d_resid; p.resid_mod = resid_mod;
+  if (epilogue == EPI_F32_NCHW) { p.n_valid = aux0; p.pix = aux1; }
+  if (epilogue == EPI_BF16_RELU_UP) { p.up_h = aux0; p.up_w = aux1; p.up_py = aux2; p.up_px = aux3; }
+  return gemm_launch(bn, epilogue, ta, tw, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int vpb_attention(const void* d_qkv, int32_t batch, int32_t heads, void* d_out, int32_t v_manual, void* stream) {
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  VPB_TRY(device_check(dev));
+  if (!d_qkv || !d_out || batch < 1 || heads < 1) return fail(VPB_ERR_ARG, "vpb_attention: bad argument");
+  const int D = heads * 64;
+  CUtensorMap tq;
+  VPB_TRY(make_map(&tq, d_qkv, static_cast<uint64_t>(batch) * 192, 3 * D, 3 * D, 192));
+  AttnParams ap;
+  ap.batch = batch; ap.heads = heads; ap.dim = D; ap.out = reinterpret_cast<__nv_bfloat16*>(d_out);
+  ap.qkv = reinterpret_cast<const __nv_bfloat16*>(d_qkv); ap.v_manual = v_manual;
+  const int items = batch * heads;
+  attention_tcgen05<<<items < g_num_sms ? items : g_num_sms, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, ap);
+  CU_TRY(cudaGetLastError());
+  return VPB_OK;
+}
+
+extern "C" int vpb_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_y, int32_t rows, int32_t dim, float eps,
+                             void* stream) {
+  if (!d_x || !d_gamma || !d_beta || !d_y) return fail(VPB_ERR_ARG, "vpb_layernorm: null pointer");
+  return layernorm(d_x, d_gamma, d_beta, reinterpret_cast<__nv_bfloat16*>(d_y), rows, dim, eps, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,176 @@
+// HBM/L2-bound helper kernels around the tensor-core GEMMs: LayerNorm, the two im2col gathers
+// (patch embedding, deconv sub-pixel phases) and the one-time weight packing.  All of them move
+// 16 bytes per thread per access and keep a warp on consecutive addresses.
+#pragma once
+#include "ptx.cuh"
+
+namespace vpb {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm(eps) over the last dim of x f32 [rows, D] -> bf16 [rows, D].  One warp per row, the row
+// lives in registers (D/128 float4 per lane), mean and biased variance by warp shuffles in fp32.
+// Reference: nn.LayerNorm(eps=1e-6) at backbone/vit.py:190,198,304.
+template <int D>
+__global__ void __launch_bounds__(256) layernorm_f32_to_bf16(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                             int rows, float eps) {
+  static_assert(D % 128 == 0, "row must split into float4 per lane");
+  constexpr int V = D / 128;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = xr[i * 32 + lane];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.0f / D) + eps);
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+    uint2 o;
+    o.x = pack_bf16(v[i].x * rstd * g.x + b.x, v[i].y * rstd * g.y + b.y);
+    o.y = pack_bf16(v[i].z * rstd * g.z + b.z, v[i].w * rstd * g.w + b.w);
+    yr[i * 32 + lane] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Patch-embedding im2col: crops f32 [B,3,256,192] -> rows bf16 [B*192, 768],
+//   row (b, py, px), col c*256 + ky*16 + kx  =  x[b, c, 16py-2+ky, 16px-2+kx]   (0 outside the image)
+// Conv2d(k16,s16,p2) geometry from backbone/vit.py:222.  One thread = 8 consecutive kx of one patch
+// row: reads 32 B of the image (8-byte aligned: columns start at -2), writes 16 B.
+__global__ void __launch_bounds__(256) patch_im2col(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int batch) {
+  const int total = batch * 3 * 256 * 24;                  // (b, c, y', xchunk)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int xc = i % 24;
+  const int yp = (i / 24) % 256;                           // y' = 16*py + ky
+  const int c = (i / (24 * 256)) % 3;
+  const int b = i / (24 * 256 * 3);
+  const int y = yp - 2, x0 = xc * 8 - 2;
+  float v[8];
+  if (y >= 0) {                                            // y' < 256 -> y <= 253 < 256 always
+    const float* src = x + ((static_cast<size_t>(b) * 3 + c) * 256 + y) * 192;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const int xx = x0 + j;                               // even offset from -2: pairs never straddle the border
+      if (xx >= 0 && xx < 192) {
+        const float2 f = *reinterpret_cast<const float2*>(src + xx);
+        v[j] = f.x; v[j + 1] = f.y;
+      } else {
+        v[j] = 0.f; v[j + 1] = 0.f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  }
+  const int py = yp >> 4, ky = yp & 15, px = xc >> 1, kx0 = (xc & 1) * 8;
+  const size_t row = (static_cast<size_t>(b) * 16 + py) * 12 + px;
+  uint4 o;
+  o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(a + row * 768 + c * 256 + ky * 16 + kx0) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deconv sub-pixel im2col.  ConvTranspose2d(k4,s2,p1) = 4 phases (py,px); output (2m+py, 2n+px) sums
+// 2x2 taps of the input (head/topdown_heatmap_simple_head.py:305-313):
+//   T(0) = {(ky=1,dy=0),(ky=3,dy=-1)}   T(1) = {(ky=0,dy=+1),(ky=2,dy=0)}        (same along x)
+// in  bf16 NHWC [B,H,W,C];  out[phase] bf16 [B*H*W, 4C], col = (iy*2+ix)*C + ci  =  in[b, m+dy, n+dx, ci]
+// blockIdx.y = phase (matrices `phase_stride` elements apart).  One thread = 8 channels (16 B).
+__global__ void __launch_bounds__(256) deconv_phase_im2col(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                           int batch, int H, int W, int C, size_t phase_stride) {
+  const int phase = blockIdx.y, py = phase >> 1, px = phase & 1;
+  const int cv = C / 8;
+  const long long total = static_cast<long long>(batch) * H * W * 4 * cv;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = static_cast<int>(i % cv);
+  const int tap = static_cast<int>((i / cv) % 4);
+  const long long pos = i / (4 * cv);                       // (b, m, n)
+  const int n = static_cast<int>(pos % W);
+  const int m = static_cast<int>((pos / W) % H);
+  const int b = static_cast<int>(pos / (static_cast<long long>(W) * H));
+  const int iy = tap >> 1, ix = tap & 1;
+  const int dy = py ? (iy ? 0 : 1) : (iy ? -1 : 0);
+  const int dx = px ? (ix ? 0 : 1) : (ix ? -1 : 0);
+  const int yy = m + dy, xx = n + dx;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+    v = *reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * H + yy) * W + xx) * C + c8 * 8);
+  __nv_bfloat16* dst = out + static_cast<size_t>(phase) * phase_stride;   // elements between phase matrices
+  *reinterpret_cast<uint4*>(dst + static_cast<size_t>(pos) * 4 * C + tap * C + c8 * 8) = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One-time weight packing (fp32 state_dict tensors already on the device -> bf16 / folded fp32).
+// Linear weight [N,K] f32 -> bf16, rows < scaled_rows multiplied by `scale` in fp32 first
+// (the q rows of attn.qkv get head_dim^-0.5: vit.py:170 scales q before QK^T).
+__global__ void pack_linear_bf16(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, long long n_elem, int K,
+                                 int scaled_rows, float scale) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_elem) return;
+  const int row = static_cast<int>(i / K);
+  const float v = w[i] * (row < scaled_rows ? scale : 1.0f);
+  out[i] = __float2bfloat16_rn(v);
+}
+__global__ void pack_bias(const float* __restrict__ b, float* __restrict__ out, int n, int n_padded, int scaled, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_padded) return;
+  out[i] = i < n ? b[i] * (i < scaled ? scale : 1.0f) : 0.0f;
+}
+// pos_bias[t, d] = pos_embed[1+t, d] + pos_embed[0, d] + patch_bias[d]     (vit.py:382 + conv bias)
+__global__ void pack_pos_bias(const float* __restrict__ pos, const float* __restrict__ pbias, float* __restrict__ out, int T, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * D) return;
+  const int t = i / D, d = i % D;
+  out[i] = pos[(1 + t) * D + d] + pos[d] + pbias[d];
+}
+// ConvTranspose2d weight [Cin,Cout,4,4] + eval BatchNorm -> 4 phase matrices bf16 [Cout, 4*Cin] with the
+// BN scale folded into the rows, and the BN shift as bias.
+//   Wp[phase][co][(iy*2+ix)*Cin + ci] = W[ci][co][ky(py,iy)][kx(px,ix)] * gamma[co]/sqrt(var[co]+eps)
+__global__ void pack_deconv(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                            const float* __restrict__ mean, const float* __restrict__ var, __nv_bfloat16* __restrict__ wp,
+                            float* __restrict__ shift, int Cin, int Cout, float eps) {
+  const long long total = 4LL * Cout * 4 * Cin;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ci = static_cast<int>(i % Cin);
+  const int tap = static_cast<int>((i / Cin) % 4);
+  const int co = static_cast<int>((i / (4LL * Cin)) % Cout);
+  const int phase = static_cast<int>(i / (4LL * Cin * Cout));
+  const int py = phase >> 1, px = phase & 1, iy = tap >> 1, ix = tap & 1;
+  const int ky = py ? (iy ? 2 : 0) : (iy ? 3 : 1);
+  const int kx = px ? (ix ? 2 : 0) : (ix ? 3 : 1);
+  const float s = gamma[co] / sqrtf(var[co] + eps);
+  wp[i] = __float2bfloat16_rn(w[((static_cast<size_t>(ci) * Cout + co) * 4 + ky) * 4 + kx] * s);
+  if (phase == 0 && tap == 0 && ci == 0) shift[co] = beta[co] - mean[co] * s;
+}
+// token-major bf16 [B*192, D] -> f32 NCHW [B, D, 16, 12]   (ViT.forward's final permute, vit.py:388)
+__global__ void tokens_to_nchw(const __nv_bfloat16* __restrict__ tok, float* __restrict__ out, int batch, int D) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(batch) * D * 192) return;
+  const int t = static_cast<int>(i % 192);
+  const int d = static_cast<int>((i / 192) % D);
+  const int b = static_cast<int>(i / (192LL * D));
+  out[i] = __bfloat162float(tok[(static_cast<size_t>(b) * 192 + t) * D + d]);
+}
+
+}  // namespace vpb

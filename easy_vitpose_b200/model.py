@@ -1,0 +1,258 @@
+"""ViTPose(cfg): the reference's model object (easy_ViTPose/vit_models/model.py:10-24) backed by the
+sm_100a engine.  Same constructor argument, same state_dict key contract, same forward signature;
+the arithmetic runs in libvitpose_b200.so (bf16 tensor-core GEMMs, fp32 residual stream/softmax/LN).
+
+torch is used for what it is good at here: owning device memory and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = ["ViTPose"]
+
+IMG_H, IMG_W, HM_H, HM_W = 256, 192, 64, 48
+
+
+def _expected_shapes(D: int, depth: int, K: int) -> "OrderedDict[str, tuple]":
+    """state_dict contract of the reference ViTPose."""
+    s: "OrderedDict[str, tuple]" = OrderedDict()
+    s["backbone.pos_embed"] = (1, 193, D)
+    s["backbone.patch_embed.proj.weight"] = (D, 3, 16, 16)
+    s["backbone.patch_embed.proj.bias"] = (D,)
+    for i in range(depth):
+        p = f"backbone.blocks.{i}."
+        s[p + "norm1.weight"] = (D,); s[p + "norm1.bias"] = (D,)
+        s[p + "attn.qkv.weight"] = (3 * D, D); s[p + "attn.qkv.bias"] = (3 * D,)
+        s[p + "attn.proj.weight"] = (D, D); s[p + "attn.proj.bias"] = (D,)
+        s[p + "norm2.weight"] = (D,); s[p + "norm2.bias"] = (D,)
+        s[p + "mlp.fc1.weight"] = (4 * D, D); s[p + "mlp.fc1.bias"] = (4 * D,)
+        s[p + "mlp.fc2.weight"] = (D, 4 * D); s[p + "mlp.fc2.bias"] = (D,)
+    s["backbone.last_norm.weight"] = (D,); s["backbone.last_norm.bias"] = (D,)
+    cin = D
+    for li in (0, 3):
+        s[f"keypoint_head.deconv_layers.{li}.weight"] = (cin, 256, 4, 4)
+        for n in ("weight", "bias", "running_mean", "running_var"):
+            s[f"keypoint_head.deconv_layers.{li + 1}.{n}"] = (256,)
+        s[f"keypoint_head.deconv_layers.{li + 1}.num_batches_tracked"] = ()
+        cin = 256
+    s["keypoint_head.final_layer.weight"] = (K, 256, 1, 1)
+    s["keypoint_head.final_layer.bias"] = (K,)
+    return s
+
+
+class ViTPose:
+    """Drop-in for the reference `ViTPose(cfg)` on the inference path.
+
+    cfg is the reference's model dict (cfg['backbone'], cfg['keypoint_head']; 'type' keys ignored,
+    model.py:14-15).  Only the configurations the reference ships are accepted: patch 16, 256x192,
+    mlp_ratio 4, qkv_bias, two 4x4 deconvs of 256 filters and a 1x1 final conv.
+    """
+
+    def __init__(self, cfg: dict, max_batch: int = 64, device: "int | str | torch.device | None" = None) -> None:
+        bb = {k: v for k, v in cfg["backbone"].items() if k != "type"}
+        hd = {k: v for k, v in cfg["keypoint_head"].items() if k != "type"}
+        if tuple(bb.get("img_size", (256, 192))) != (256, 192) or bb.get("patch_size", 16) != 16 or bb.get("ratio", 1) != 1:
+            raise ValueError("only img_size=(256,192), patch_size=16, ratio=1 (the reference's configs) are built")
+        if bb.get("mlp_ratio", 4) != 4 or not bb.get("qkv_bias", False):
+            raise ValueError("only mlp_ratio=4, qkv_bias=True (the reference's configs) are built")
+        if hd.get("num_deconv_layers", 3) != 2 or tuple(hd.get("num_deconv_filters", ())) != (256, 256) \
+                or tuple(hd.get("num_deconv_kernels", ())) != (4, 4) or (hd.get("extra") or {}).get("final_conv_kernel", 1) != 1:
+            raise ValueError("only the 2x deconv(256,4x4) + 1x1 conv head of the reference's configs is built")
+        self.embed_dim = int(bb["embed_dim"]); self.depth = int(bb["depth"]); self.num_heads = int(bb["num_heads"])
+        self.num_keypoints = int(hd["out_channels"])
+        if int(hd["in_channels"]) != self.embed_dim:
+            raise ValueError("keypoint_head.in_channels must equal backbone.embed_dim")
+        self.max_batch = int(max_batch)
+        self.training = False
+        self._cfg = cfg
+        self._handle = C.c_void_p()
+        self._loaded = False
+        self._state: "OrderedDict[str, torch.Tensor] | None" = None
+        self._device = None
+        if device is not None:
+            self.to(device)
+
+    # ---------------------------------------------------------------- nn.Module-like surface
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise RuntimeError("the B200 engine is inference-only (eval mode); training stays with the reference")
+        return self
+
+    def to(self, device):
+        dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        if dev.type != "cuda":
+            raise RuntimeError(f"ViTPose(B200) has no {dev.type} path: it needs a CUDA sm_100 device")
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        if self._device is not None and self._device != index and self._handle:
+            raise RuntimeError("engine already lives on another device")
+        self._device = index
+        if self._state is not None and not self._loaded:
+            self._upload()
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", device if device is not None else torch.cuda.current_device()))
+
+    def state_dict(self):
+        if self._state is None:
+            raise RuntimeError("no weights loaded")
+        return OrderedDict((k, v.clone()) for k, v in self._state.items())
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        """Same contract as nn.Module.load_state_dict(strict=True): missing / unexpected keys and
+        shape mismatches raise (easy_ViTPose/inference.py:162-166 calls it exactly like this)."""
+        if "state_dict" in state_dict and not any(k.startswith("backbone.") for k in state_dict):
+            state_dict = state_dict["state_dict"]
+        exp = _expected_shapes(self.embed_dim, self.depth, self.num_keypoints)
+        missing = [k for k in exp if k not in state_dict and not k.endswith("num_batches_tracked")]
+        unexpected = [k for k in state_dict if k not in exp]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict for ViTPose: missing keys {missing[:5]}"
+                               f"{'...' if len(missing) > 5 else ''}, unexpected keys {unexpected[:5]}")
+        st: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        for k, shape in exp.items():
+            if k not in state_dict:
+                if k.endswith("num_batches_tracked"):
+                    st[k] = torch.zeros((), dtype=torch.int64)
+                    continue
+                raise RuntimeError(f"missing key {k}")
+            v = state_dict[k]
+            v = torch.as_tensor(np.asarray(v)) if not isinstance(v, torch.Tensor) else v
+            if tuple(v.shape) != tuple(shape):
+                raise RuntimeError(f"size mismatch for {k}: copying a param with shape {tuple(v.shape)}, expected {tuple(shape)}")
+            st[k] = v.detach().to("cpu").contiguous()
+        if self._loaded:
+            raise RuntimeError("weights already packed on the device; create a new ViTPose to load another checkpoint")
+        self._state = st
+        if self._device is not None:
+            self._upload()
+        return self
+
+    # ---------------------------------------------------------------- engine plumbing
+    def _ensure(self):
+        if not self._loaded:
+            if self._state is None:
+                raise RuntimeError("load_state_dict() before forward()")
+            if self._device is None:
+                self.to("cuda")
+            else:
+                self._upload()
+
+    def _upload(self):
+        L = _lib.lib()
+        cfg = _lib.VpbConfig(self.embed_dim, self.depth, self.num_heads, self.num_keypoints, self.max_batch, self._device)
+        with torch.cuda.device(self._device):
+            _lib.check(L.vpb_create(C.byref(cfg), C.byref(self._handle)))
+            for k, v in self._state.items():
+                if k.endswith("num_batches_tracked"):
+                    continue
+                a = v.to(torch.float32).contiguous().numpy()
+                _lib.check(L.vpb_load_tensor(self._handle, k.encode(), a.ctypes.data_as(C.c_void_p), a.size))
+            _lib.check(L.vpb_finalize(self._handle))
+        self._loaded = True
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+
+    def _check_input(self, x: torch.Tensor) -> torch.Tensor:
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("expected a torch.Tensor [B,3,256,192]")
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, IMG_H, IMG_W):
+            raise ValueError(f"expected [B,3,256,192], got {tuple(x.shape)}")
+        if x.shape[0] < 1 or x.shape[0] > self.max_batch:
+            raise ValueError(f"batch {x.shape[0]} outside 1..max_batch={self.max_batch}")
+        self._ensure()
+        if not x.is_cuda:
+            x = x.to(torch.device("cuda", self._device), non_blocking=True)
+        if x.device.index != self._device:
+            raise ValueError("input lives on another GPU than the engine")
+        return x.to(torch.float32).contiguous()
+
+    # ---------------------------------------------------------------- forward paths
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """[B,3,256,192] float32 -> heatmaps [B,K,64,48] float32 (model.py:23-24)."""
+        x = self._check_input(x)
+        out = torch.empty((x.shape[0], self.num_keypoints, HM_H, HM_W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().vpb_forward(self._handle, C.c_void_p(x.data_ptr()), x.shape[0], C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    __call__ = forward
+
+    @torch.no_grad()
+    def forward_features(self, x: torch.Tensor) -> torch.Tensor:
+        """[B,3,256,192] -> backbone features [B,D,16,12] (model.py:20-21, vit.py:375-389)."""
+        x = self._check_input(x)
+        out = torch.empty((x.shape[0], self.embed_dim, 16, 12), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().vpb_forward_features(self._handle, C.c_void_p(x.data_ptr()), x.shape[0], C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    @torch.no_grad()
+    def infer_crops(self, x: torch.Tensor, org_wh: torch.Tensor, return_heatmaps: bool = False):
+        """Batched crops -> keypoints [B,K,3] (y, x, score) in crop pixels + flat argmax [B,K].
+        org_wh int32 [B,2] = each crop's (width, height) before the resize to 192x256."""
+        x = self._check_input(x)
+        B = x.shape[0]
+        org = torch.as_tensor(org_wh).to(device=x.device, dtype=torch.int32).contiguous()
+        if tuple(org.shape) != (B, 2):
+            raise ValueError(f"org_wh must be [B,2], got {tuple(org.shape)}")
+        kp = torch.empty((B, self.num_keypoints, 3), dtype=torch.float32, device=x.device)
+        idx = torch.empty((B, self.num_keypoints), dtype=torch.int32, device=x.device)
+        hm = torch.empty((B, self.num_keypoints, HM_H, HM_W), dtype=torch.float32, device=x.device) if return_heatmaps else None
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().vpb_infer(self._handle, C.c_void_p(x.data_ptr()), C.c_void_p(org.data_ptr()), B,
+                                            C.c_void_p(kp.data_ptr()), C.c_void_p(idx.data_ptr()),
+                                            C.c_void_p(hm.data_ptr()) if hm is not None else None, self._stream()))
+        return (kp, idx, hm) if return_heatmaps else (kp, idx)
+
+    def infer_host(self, crops: np.ndarray, org_wh: np.ndarray, kpts_out: np.ndarray | None = None,
+                   idx_out: np.ndarray | None = None):
+        """HOST buffers in, HOST keypoints out through the C ABI (vpb_infer_host): H2D + path + D2H + sync."""
+        self._ensure()
+        crops = np.ascontiguousarray(crops, np.float32)
+        org = np.ascontiguousarray(org_wh, np.int32)
+        B = crops.shape[0]
+        if crops.shape[1:] != (3, IMG_H, IMG_W) or org.shape != (B, 2):
+            raise ValueError("crops [B,3,256,192] float32 and org_wh [B,2] int32 expected")
+        kp = kpts_out if kpts_out is not None else np.empty((B, self.num_keypoints, 3), np.float32)
+        idx = idx_out if idx_out is not None else np.empty((B, self.num_keypoints), np.int32)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().vpb_infer_host(self._handle, crops.ctypes.data_as(C.c_void_p), org.ctypes.data_as(C.c_void_p), B,
+                                                 kp.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p), self._stream()))
+        return kp, idx
+
+    def kernel_launches(self, batch: int) -> int:
+        self._ensure()
+        return int(_lib.lib().vpb_kernel_launches(self._handle, batch))
+
+    def set_option(self, name: str, value: int) -> None:
+        self._ensure()
+        _lib.check(_lib.lib().vpb_set_option(self._handle, name.encode(), int(value)))
+
+    def read_buffer(self, name: str, shape, dtype) -> np.ndarray:
+        """Debug: synchronous copy of an internal activation buffer (see vpb_read_buffer)."""
+        self._ensure()
+        tdtype = torch.bfloat16 if dtype == "bf16" else torch.float32
+        out = torch.empty(tuple(shape), dtype=tdtype)
+        _lib.check(_lib.lib().vpb_read_buffer(self._handle, name.encode(), C.c_void_p(out.data_ptr()), out.numel() * out.element_size()))
+        return out
+
+    def __del__(self):
+        try:
+            if self._handle:
+                _lib.lib().vpb_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:
+            pass

@@ -1,0 +1,100 @@
+/* vitpose_b200.h -- C ABI of the B200-native ViTPose crop engine (libvitpose_b200.so).
+ *
+ * One data-parallel hot path of JunkyByte/easy_ViTPose, rebuilt for sm_100a:
+ *     crops f32 [B,3,256,192] -> ViT backbone -> TopdownHeatmapSimpleHead -> heatmaps f32 [B,K,64,48]
+ *     -> argmax + DARK/UDP refine -> keypoints f32 [B,K,3] rows (y, x, score)
+ * Plain pointers and sizes only; no torch types.  Device pointers are CUDA device addresses on the
+ * engine's device, `stream` is a cudaStream_t passed as void* (NULL = default stream).  All calls are
+ * asynchronous on `stream` unless stated; none of them frees or keeps caller memory.
+ * There is no CPU fallback: every entry point fails (non-zero + vpb_last_error()) without an sm_100 GPU.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference repo).
+ */
+#ifndef VITPOSE_B200_H
+#define VITPOSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPB_OK 0
+#define VPB_ERR_ARG 1      /* bad argument / unsupported configuration / missing weights */
+#define VPB_ERR_CUDA 2     /* CUDA runtime or driver error (message in vpb_last_error) */
+#define VPB_ERR_STATE 3    /* call order violated (e.g. forward before finalize) */
+
+typedef struct vpb_engine vpb_engine;
+
+/* Model hyper-parameters: easy_ViTPose/configs/ViTPose_common.py:65-195 (embed_dim, depth, num_heads;
+ * mlp_ratio 4, qkv_bias, patch 16, img 256x192, 2 deconv layers of 256 filters, 1x1 final conv are fixed
+ * on this path) and the per-dataset out_channels (e.g. configs/ViTPose_coco.py:16-18). */
+typedef struct vpb_config {
+  int32_t embed_dim;      /* 384 / 768 / 1024 / 1280 */
+  int32_t depth;          /* 12 / 12 / 24 / 32 */
+  int32_t num_heads;      /* 12 / 12 / 16 / 16 */
+  int32_t num_keypoints;  /* K = keypoint_head.out_channels, 1..144 */
+  int32_t max_batch;      /* workspace is sized for this many crops per call */
+  int32_t device;         /* CUDA device ordinal */
+} vpb_config;
+
+/* Thread-local description of the last failure in this thread ("" if none). */
+const char* vpb_last_error(void);
+
+/* Replaces ViTPose(cfg) construction (easy_ViTPose/vit_models/model.py:10-18; VitInference.__init__,
+ * easy_ViTPose/inference.py:156-157): allocates weights arena + workspace on cfg->device. */
+int vpb_create(const vpb_config* cfg, vpb_engine** out);
+void vpb_destroy(vpb_engine* e);
+
+/* Replaces nn.Module.load_state_dict (easy_ViTPose/inference.py:162-166), one tensor at a time, under the
+ * reference's own key names ("backbone.blocks.3.attn.qkv.weight", ...).  `data` is HOST
+ * float32, C-contiguous, `numel` elements; "...num_batches_tracked" keys are accepted and ignored. */
+int vpb_load_tensor(vpb_engine* e, const char* key, const float* data, int64_t numel);
+/* Strict check (every key of the contract loaded exactly once) + one-time packing on the GPU: bf16
+ * conversion, q-scale fold into attn.qkv, pos_embed+conv-bias fold, BatchNorm fold into the deconv phases. */
+int vpb_finalize(vpb_engine* e);
+
+/* Replaces ViTPose.forward (vit_models/model.py:23-24): d_crops f32 [batch,3,256,192] ->
+ * d_heatmaps f32 [batch,K,64,48]. */
+int vpb_forward(vpb_engine* e, const float* d_crops, int32_t batch, float* d_heatmaps, void* stream);
+/* Replaces ViTPose.forward_features (vit_models/model.py:20-21): -> d_features f32 [batch,D,16,12]. */
+int vpb_forward_features(vpb_engine* e, const float* d_crops, int32_t batch, float* d_features, void* stream);
+
+/* Replaces keypoints_from_heatmaps(unbiased=True, use_udp=True) + the (y,x,score) packing of
+ * VitInference.postprocess (vit_utils/top_down_eval.py:493-641 branch :586-589; easy_ViTPose/inference.py:187-205).
+ * d_heatmaps f32 [n,k,64,48]; d_org_wh i32 [n,2] crop (width,height); d_kpts f32 [n,k,3]; d_idx i32 [n,k] flat
+ * argmax or NULL.  wrap_batch selects the reference's "previous map" for max<=0 maps: 0 = one reference call per
+ * crop (VitInference), 1 = one reference call on the whole [n,k,H,W] array.  Does not modify d_heatmaps. */
+int vpb_decode(const float* d_heatmaps, int32_t n, int32_t k, const int32_t* d_org_wh, float* d_kpts, int32_t* d_idx,
+               int32_t wrap_batch, void* stream);
+
+/* Replaces the model + postprocess part of VitInference._inference_torch (easy_ViTPose/inference.py:320-328)
+ * for a whole batch of crops resident on the device.  d_heatmaps may be NULL. */
+int vpb_infer(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, int32_t batch, float* d_kpts,
+              int32_t* d_idx, float* d_heatmaps, void* stream);
+/* Same with HOST buffers: H2D of crops/org_wh, the path, D2H of keypoints (+idx), then a stream sync --
+ * the reference's `.to(device)` ... `.cpu().numpy()` bracket (inference.py:324,327).  Pinned host memory
+ * (vpb_host_alloc) makes the copies asynchronous DMA. */
+int vpb_infer_host(vpb_engine* e, const float* h_crops, const int32_t* h_org_wh, int32_t batch, float* h_kpts,
+                   int32_t* h_idx, void* stream);
+void* vpb_host_alloc(int64_t bytes);   /* cudaHostAlloc; NULL on failure */
+void vpb_host_free(void* p);
+
+/* Introspection used by bench.py / tests. */
+int vpb_kernel_launches(const vpb_engine* e, int32_t batch);          /* kernels one vpb_infer enqueues */
+int vpb_set_option(vpb_engine* e, const char* name, int32_t value);   /* "stop_after", "attn_v_manual" */
+int vpb_read_buffer(vpb_engine* e, const char* name, void* host_dst, int64_t bytes);  /* synchronous debug read */
+
+/* Kernel-level entry points (unit tests / profiling).  All pointers are device pointers.
+ * vpb_gemm: out = epilogue(A[M,K] bf16 * W[N,K]^T bf16 + bias);  epilogue ids as in csrc/gemm.cuh. */
+int vpb_gemm(const void* d_a, const void* d_w, const float* d_bias, void* d_out, int32_t m, int32_t n, int32_t k,
+             int32_t epilogue, const float* d_resid, int32_t resid_mod, int32_t aux0, int32_t aux1, int32_t aux2,
+             int32_t aux3, void* stream);
+int vpb_attention(const void* d_qkv, int32_t batch, int32_t heads, void* d_out, int32_t v_manual, void* stream);
+int vpb_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_y, int32_t rows, int32_t dim,
+                  float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITPOSE_B200_H */

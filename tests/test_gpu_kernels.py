@@ -1,0 +1,178 @@
+"""-m gpu: each hand-written kernel through the C ABI against a plain fp32 torch restatement of the same op
+(floating-point kernels) or the oracle / golden vectors (decode: integer argmax bit-exact)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vitpose_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    assert torch.cuda.is_available(), "-m gpu tests need a B200"
+    return torch.device("cuda", 0)
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+# ------------------------------------------------------------------------------------------------ decode
+@pytest.mark.parametrize("name,wrap", [("decode_crop", False), ("decode_batch", True)])
+def test_decode_matches_reference_golden(golden_dir, name, wrap):
+    from easy_vitpose_b200 import decode_heatmaps
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    N, K, seed = (int(v) for v in g["meta"])
+    maps = O.make_decode_maps(N, K, seed)
+    kp, idx = decode_heatmaps(torch.from_numpy(maps).to(_dev()), torch.from_numpy(g["org_wh"]), wrap_batch=wrap)
+    kp, idx = kp.cpu().numpy(), idx.cpu().numpy()
+    assert np.array_equal(idx, g["idx"])                              # integer argmax indices: bit-exact
+    assert np.array_equal(kp[..., 2], g["kpts"][..., 2])              # score = raw max: bit-exact
+    ref = g["kpts"][..., :2]
+    err = np.abs(kp[..., :2] - ref)
+    kinds = (np.arange(N * K) % 10).reshape(N, K)
+    well = np.isin(kinds, [0, 1, 2, 3, 5, 7])
+    print("decode err well-conditioned max", err[well].max(), "other max", err[~well].max())
+    assert err[well].max() < 2e-3                                    # px; blur bit-exact, logf vs np.log differ by ulps
+    assert np.all(err[~well] <= 2e-3 + 2e-3 * np.abs(ref[~well]))
+
+
+def test_decode_matches_oracle_random_maps():
+    from easy_vitpose_b200 import decode_heatmaps
+    maps = O.make_decode_maps(8, 17, 4242)
+    org = np.stack([np.arange(8) * 37 + 64, np.arange(8) * 29 + 80], 1).astype(np.int32)
+    kp, idx = decode_heatmaps(torch.from_numpy(maps).to(_dev()), torch.from_numpy(org), wrap_batch=False)
+    okp, oidx = O.decode_maps(maps, org, wrap="crop")
+    assert np.array_equal(idx.cpu().numpy(), oidx)
+    kp = kp.cpu().numpy()
+    assert np.array_equal(kp[..., 2], okp[..., 2])
+    kinds = (np.arange(8 * 17) % 10).reshape(8, 17)
+    well = np.isin(kinds, [0, 1, 2, 3, 5, 7])
+    assert np.abs(kp[..., :2] - okp[..., :2])[well].max() < 2e-3
+
+
+def test_decode_nan_and_ties_first_index():
+    from easy_vitpose_b200 import decode_heatmaps
+    m = np.zeros((1, 3, 64, 48), np.float32)
+    m[0, 0].reshape(-1)[[100, 2000]] = 1.0                 # tie -> 100
+    m[0, 1].reshape(-1)[[77, 78]] = [np.nan, 5.0]          # np.argmax: first NaN wins
+    m[0, 2] = -1.0                                         # all equal negative -> index 0, sentinel
+    _, idx = decode_heatmaps(torch.from_numpy(m).to(_dev()), torch.tensor([[192, 256]], dtype=torch.int32))
+    assert idx.cpu().numpy().tolist() == [[100, 77, 0]]
+    assert np.argmax(m.reshape(3, -1), -1).tolist() == [100, 77, 0]
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("D", [384, 768, 1024, 1280])
+def test_layernorm(D):
+    from tests.gpu_util import layernorm
+    torch.manual_seed(D)
+    x = torch.randn(1000, D, device=_dev()) * 3 + 0.5
+    g = torch.randn(D, device=_dev()) * 0.1 + 1
+    b = torch.randn(D, device=_dev()) * 0.1
+    y = layernorm(x, g, b).float()
+    ref = torch.nn.functional.layer_norm(x, (D,), g, b, 1e-6)
+    assert (y - ref).abs().max() < 0.03                    # bf16 output rounding of values up to ~|5|
+    assert (y - ref.bfloat16().float()).abs().max() < 0.035
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (384, 768, 768), (1000, 2304, 768), (12288, 768, 3072), (200, 384, 384)])
+def test_gemm_bias_bf16(M, N, K):
+    from tests.gpu_util import EPI_BF16, gemm
+    torch.manual_seed(M + N + K)
+    a = (torch.randn(M, K, device=_dev()) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=_dev()) * 0.05).bfloat16()
+    bias = torch.randn(N, device=_dev())
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device=_dev())
+    gemm(a, w, bias, out, EPI_BF16)
+    ref = a.float() @ w.float().T + bias
+    r = _rel(out.float(), ref)
+    print("gemm bf16 rel err", r)
+    assert r < 1e-2
+
+
+def test_gemm_gelu():
+    from tests.gpu_util import EPI_BF16_GELU, gemm
+    torch.manual_seed(1)
+    M, N, K = 640, 3072, 768
+    a = (torch.randn(M, K, device=_dev()) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=_dev()) * 0.05).bfloat16()
+    bias = torch.randn(N, device=_dev()) * 0.1
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device=_dev())
+    gemm(a, w, bias, out, EPI_BF16_GELU)
+    ref = torch.nn.functional.gelu(a.float() @ w.float().T + bias)
+    assert _rel(out.float(), ref) < 1e-2
+
+
+def test_gemm_residual_inplace_and_posmod():
+    from tests.gpu_util import EPI_F32_RESID, gemm
+    torch.manual_seed(2)
+    M, N, K = 576, 768, 768
+    a = (torch.randn(M, K, device=_dev()) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=_dev()) * 0.05).bfloat16()
+    bias = torch.randn(N, device=_dev())
+    x = torch.randn(M, N, device=_dev())
+    ref = x + a.float() @ w.float().T + bias
+    gemm(a, w, bias, x, EPI_F32_RESID, resid=x)                      # in place, like proj / fc2
+    assert _rel(x, ref) < 2e-3
+    pos = torch.randn(192, N, device=_dev())
+    out = torch.zeros(M, N, device=_dev())
+    gemm(a, w, None, out, EPI_F32_RESID, resid=pos, resid_mod=192)   # patch embed + pos_embed
+    ref2 = a.float() @ w.float().T + pos.repeat(M // 192, 1)
+    assert _rel(out, ref2) < 2e-3
+
+
+def test_gemm_deconv_phase_scatter_relu():
+    from tests.gpu_util import EPI_BF16_RELU_UP, gemm
+    torch.manual_seed(3)
+    B, H, W, K = 3, 16, 12, 1024
+    M = B * H * W
+    a = (torch.randn(M, K, device=_dev()) * 0.5).bfloat16()
+    w = (torch.randn(256, K, device=_dev()) * 0.05).bfloat16()
+    bias = torch.randn(256, device=_dev())
+    out = torch.full((B, 2 * H, 2 * W, 256), -7.0, dtype=torch.bfloat16, device=_dev())
+    gemm(a, w, bias, out, EPI_BF16_RELU_UP, aux=(H, W, 1, 0))
+    ref = torch.relu(a.float() @ w.float().T + bias).reshape(B, H, W, 256)
+    got = out[:, 1::2, 0::2].float()
+    assert _rel(got, ref) < 1e-2
+    assert float(out[:, 0::2].float().max()) == -7.0                 # other phases untouched
+
+
+@pytest.mark.parametrize("Kk,Npad", [(17, 32), (25, 32), (133, 144)])
+def test_gemm_heatmap_nchw(Kk, Npad):
+    from tests.gpu_util import EPI_F32_NCHW, gemm
+    torch.manual_seed(4)
+    B, pix, K = 2, 3072, 256
+    a = (torch.randn(B * pix, K, device=_dev()) * 0.5).bfloat16()
+    w = torch.zeros(Npad, K, device=_dev())
+    w[:Kk] = torch.randn(Kk, K, device=_dev()) * 0.05
+    w = w.bfloat16()
+    bias = torch.zeros(Npad, device=_dev())
+    bias[:Kk] = torch.randn(Kk, device=_dev())
+    out = torch.zeros(B, Kk, pix, device=_dev())
+    gemm(a, w, bias, out, EPI_F32_NCHW, aux=(Kk, pix, 0, 0))
+    ref = (a.float() @ w.float().T + bias)[:, :Kk].reshape(B, pix, Kk).permute(0, 2, 1)
+    assert _rel(out, ref) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("v_manual", [0, 1])
+@pytest.mark.parametrize("B,heads", [(1, 1), (3, 12), (40, 16)])
+def test_attention(B, heads, v_manual):
+    from tests.gpu_util import attention
+    torch.manual_seed(B * 100 + heads)
+    D = heads * 64
+    qkv = torch.randn(B * 192, 3 * D, device=_dev())
+    qkv[:, :D] *= 0.125 * 2.0                                        # q arrives pre-scaled; keep logits O(few)
+    qkv = qkv.bfloat16()
+    out = attention(qkv, B, heads, v_manual).float()
+    q, k, v = (qkv.float().reshape(B, 192, 3, heads, 64)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    p = torch.softmax(q @ k.transpose(-1, -2), -1)
+    ref = (p @ v).permute(0, 2, 1, 3).reshape(B * 192, D)
+    r = _rel(out, ref)
+    print("attention rel err", r, "v_manual", v_manual)
+    assert r < 2e-2
