@@ -118,6 +118,32 @@ static int device_check(int device) {
   return VPB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ per-kernel timing
+// Optional ("profile" option): a CUDA-event pair around every launch, on the launch stream, summed per kernel
+// class by vpb_profile_collect.  bench.py uses it to report the dominant kernel's achieved FLOP/s live.
+enum KClass : int { KC_PATCH_IM2COL, KC_GEMM_PATCH, KC_LN, KC_GEMM_QKV, KC_ATTN, KC_GEMM_PROJ, KC_GEMM_FC1, KC_GEMM_FC2,
+                    KC_DECONV_IM2COL, KC_GEMM_DECONV, KC_GEMM_FINAL, KC_DECODE, KC_COUNT };
+static const char* kclass_names[KC_COUNT] = {"patch_im2col", "gemm_patch_embed", "layernorm", "gemm_qkv", "attention", "gemm_proj",
+                                             "gemm_fc1_gelu", "gemm_fc2", "deconv_im2col", "gemm_deconv", "gemm_final_conv", "decode"};
+struct ProfRec { int cls; cudaEvent_t a, b; };
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+  void begin(int cls, cudaStream_t st) {
+    if (!on) return;
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!pool.empty()) { ev = pool.back(); pool.pop_back(); }
+    else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
+    cudaEventRecord(ev.first, st);
+    recs.push_back({cls, ev.first, ev.second});
+  }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(recs.back().b, st);
+  }
+};
+
 // ------------------------------------------------------------------------------------------------ engine
 struct LinearW {
   __nv_bfloat16* w = nullptr;   // [N,K] bf16
@@ -134,6 +160,7 @@ struct vpb_engine {
   int D, depth, heads, K, maxB, n_final;   // n_final = padded channel count of the 1x1 conv GEMM
   bool finalized = false;
   int stop_after = 0, attn_v_manual = 0;
+  Profiler prof;
   std::map<std::string, std::pair<float*, int64_t>> staged;   // fp32 state_dict tensors on device until finalize
   std::vector<void*> allocs;
   // packed weights
@@ -373,47 +400,68 @@ static GemmParams gp(int M, int N, int K, const float* bias, void* out, int ldc)
 static int backbone(vpb_engine* e, const float* d_crops, int B, cudaStream_t st) {
   const int D = e->D, M = B * 192;
   const int stop = e->stop_after;
+  e->prof.begin(KC_PATCH_IM2COL, st);
   patch_im2col<<<cdiv(static_cast<long long>(B) * 3 * 256 * 24, 256), 256, 0, st>>>(d_crops, e->patch_rows, B);
+  e->prof.end(st);
   CU_TRY(cudaGetLastError());
   if (stop == 1) return VPB_OK;
   {  // tokens = rows * Wpatch^T + (pos_embed[1+t] + pos_embed[0] + conv bias)
     GemmParams p = gp(M, D, 768, nullptr, e->x, D);
     p.resid = e->pos_bias; p.resid_mod = 192;
+    e->prof.begin(KC_GEMM_PATCH, st);
     VPB_TRY(gemm_launch(e->patch.bn, EPI_F32_RESID, e->m_patch_rows, e->patch.map, p, st));
+    e->prof.end(st);
   }
   if (stop == 2) return VPB_OK;
   for (int i = 0; i < e->depth; ++i) {
     BlockW& b = e->blocks[i];
+    e->prof.begin(KC_LN, st);
     VPB_TRY(layernorm(e->x, b.ln1_g, b.ln1_b, e->xn, M, D, 1e-6f, st));
+    e->prof.end(st);
     if (stop == 3) return VPB_OK;
+    e->prof.begin(KC_GEMM_QKV, st);
     VPB_TRY(gemm_launch(b.qkv.bn, EPI_BF16, e->m_xn, b.qkv.map, gp(M, 3 * D, D, b.qkv.b, e->qkv, 3 * D), st));
+    e->prof.end(st);
     if (stop == 4) return VPB_OK;
     {
       AttnParams ap;
       ap.batch = B; ap.heads = e->heads; ap.dim = D; ap.out = e->attn; ap.qkv = e->qkv; ap.v_manual = e->attn_v_manual;
       const int items = B * e->heads;
+      e->prof.begin(KC_ATTN, st);
       attention_tcgen05<<<items < g_num_sms ? items : g_num_sms, ATT_THREADS, ATT_SMEM, st>>>(e->m_qkv_att, ap);
+      e->prof.end(st);
       CU_TRY(cudaGetLastError());
     }
     if (stop == 5) return VPB_OK;
     {
       GemmParams p = gp(M, D, D, b.proj.b, e->x, D);
       p.resid = e->x;
+      e->prof.begin(KC_GEMM_PROJ, st);
       VPB_TRY(gemm_launch(b.proj.bn, EPI_F32_RESID, e->m_attn, b.proj.map, p, st));
+      e->prof.end(st);
     }
     if (stop == 6) return VPB_OK;
+    e->prof.begin(KC_LN, st);
     VPB_TRY(layernorm(e->x, b.ln2_g, b.ln2_b, e->xn, M, D, 1e-6f, st));
+    e->prof.end(st);
+    e->prof.begin(KC_GEMM_FC1, st);
     VPB_TRY(gemm_launch(b.fc1.bn, EPI_BF16_GELU, e->m_xn, b.fc1.map, gp(M, 4 * D, D, b.fc1.b, e->hid, 4 * D), st));
+    e->prof.end(st);
     if (stop == 7) return VPB_OK;
     {
       GemmParams p = gp(M, D, 4 * D, b.fc2.b, e->x, D);
       p.resid = e->x;
+      e->prof.begin(KC_GEMM_FC2, st);
       VPB_TRY(gemm_launch(b.fc2.bn, EPI_F32_RESID, e->m_hid, b.fc2.map, p, st));
+      e->prof.end(st);
     }
     if (stop == 8) return VPB_OK;
   }
   if (stop == 9) return VPB_OK;
-  return layernorm(e->x, e->lnf_g, e->lnf_b, e->xn, M, D, 1e-6f, st);
+  e->prof.begin(KC_LN, st);
+  VPB_TRY(layernorm(e->x, e->lnf_g, e->lnf_b, e->xn, M, D, 1e-6f, st));
+  e->prof.end(st);
+  return VPB_OK;
 }
 
 static int head(vpb_engine* e, int B, float* d_heat, cudaStream_t st) {
@@ -423,31 +471,41 @@ static int head(vpb_engine* e, int B, float* d_heat, cudaStream_t st) {
   {
     const int M = B * 192;
     const long long tot = static_cast<long long>(M) * 4 * (D / 8);
+    e->prof.begin(KC_DECONV_IM2COL, st);
     deconv_phase_im2col<<<dim3(cdiv(tot, 256), 4), 256, 0, st>>>(e->xn, e->col1, B, 16, 12, D, static_cast<size_t>(e->maxB) * 192 * 4 * D);
+    e->prof.end(st);
     CU_TRY(cudaGetLastError());
     for (int ph = 0; ph < 4; ++ph) {
       GemmParams p = gp(M, 256, 4 * D, e->dc1[ph].b, e->d1, 256);
       p.up_h = 16; p.up_w = 12; p.up_py = ph >> 1; p.up_px = ph & 1;
+      e->prof.begin(KC_GEMM_DECONV, st);
       VPB_TRY(gemm_launch(256, EPI_BF16_RELU_UP, e->m_col1[ph], e->dc1[ph].map, p, st));
+      e->prof.end(st);
     }
   }
   if (stop == 11) return VPB_OK;
   {
     const int M = B * 768;
     const long long tot = static_cast<long long>(M) * 4 * (256 / 8);
+    e->prof.begin(KC_DECONV_IM2COL, st);
     deconv_phase_im2col<<<dim3(cdiv(tot, 256), 4), 256, 0, st>>>(e->d1, e->col2, B, 32, 24, 256, static_cast<size_t>(e->maxB) * 768 * 1024);
+    e->prof.end(st);
     CU_TRY(cudaGetLastError());
     for (int ph = 0; ph < 4; ++ph) {
       GemmParams p = gp(M, 256, 1024, e->dc2[ph].b, e->d2, 256);
       p.up_h = 32; p.up_w = 24; p.up_py = ph >> 1; p.up_px = ph & 1;
+      e->prof.begin(KC_GEMM_DECONV, st);
       VPB_TRY(gemm_launch(256, EPI_BF16_RELU_UP, e->m_col2[ph], e->dc2[ph].map, p, st));
+      e->prof.end(st);
     }
   }
   if (stop == 12) return VPB_OK;
   {
     GemmParams p = gp(B * 3072, e->n_final, 256, e->fin.b, d_heat, 0);
     p.n_valid = e->K; p.pix = 3072;
+    e->prof.begin(KC_GEMM_FINAL, st);
     VPB_TRY(gemm_launch(e->n_final, EPI_F32_NCHW, e->m_d2, e->fin.map, p, st));
+    e->prof.end(st);
   }
   return VPB_OK;
 }
@@ -498,7 +556,10 @@ extern "C" int vpb_infer(vpb_engine* e, const float* d_crops, const int32_t* d_o
   float* heat = d_heatmaps ? d_heatmaps : e->heat;
   VPB_TRY(vpb_forward(e, d_crops, batch, heat, stream));
   if (e->stop_after) return VPB_OK;
-  return vpb_decode(heat, batch, e->K, d_org_wh, d_kpts, d_idx, 0, stream);
+  e->prof.begin(KC_DECODE, static_cast<cudaStream_t>(stream));
+  VPB_TRY(vpb_decode(heat, batch, e->K, d_org_wh, d_kpts, d_idx, 0, stream));
+  e->prof.end(static_cast<cudaStream_t>(stream));
+  return VPB_OK;
 }
 
 extern "C" int vpb_infer_host(vpb_engine* e, const float* h_crops, const int32_t* h_org_wh, int32_t batch, float* h_kpts,
@@ -537,7 +598,25 @@ extern "C" int vpb_set_option(vpb_engine* e, const char* name, int32_t value) {
   if (!e || !name) return fail(VPB_ERR_ARG, "vpb_set_option: null argument");
   if (!strcmp(name, "stop_after")) e->stop_after = value;
   else if (!strcmp(name, "attn_v_manual")) e->attn_v_manual = value;
+  else if (!strcmp(name, "profile")) e->prof.on = value != 0;
   else return fail(VPB_ERR_ARG, "unknown option %s", name);
+  return VPB_OK;
+}
+
+extern "C" int vpb_profile_classes(void) { return KC_COUNT; }
+extern "C" const char* vpb_profile_class_name(int32_t cls) { return (cls >= 0 && cls < KC_COUNT) ? kclass_names[cls] : ""; }
+extern "C" int vpb_profile_collect(vpb_engine* e, float* ms_per_class, int32_t* launches_per_class) {
+  if (!e || !ms_per_class || !launches_per_class) return fail(VPB_ERR_ARG, "vpb_profile_collect: null argument");
+  CU_TRY(cudaDeviceSynchronize());
+  for (int i = 0; i < KC_COUNT; ++i) { ms_per_class[i] = 0.f; launches_per_class[i] = 0; }
+  for (auto& r : e->prof.recs) {
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+    ms_per_class[r.cls] += ms;
+    launches_per_class[r.cls] += 1;
+    e->prof.pool.push_back({r.a, r.b});
+  }
+  e->prof.recs.clear();
   return VPB_OK;
 }
 

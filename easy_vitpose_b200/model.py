@@ -241,6 +241,16 @@ class ViTPose:
         self._ensure()
         _lib.check(_lib.lib().vpb_set_option(self._handle, name.encode(), int(value)))
 
+    def profile_collect(self) -> dict:
+        """{kernel class: (total ms, launches)} since the last call; needs set_option('profile', 1)."""
+        self._ensure()
+        L = _lib.lib()
+        n = L.vpb_profile_classes()
+        ms = (C.c_float * n)()
+        cnt = (C.c_int32 * n)()
+        _lib.check(L.vpb_profile_collect(self._handle, ms, cnt))
+        return {L.vpb_profile_class_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
     def read_buffer(self, name: str, shape, dtype) -> np.ndarray:
         """Debug: synchronous copy of an internal activation buffer (see vpb_read_buffer)."""
         self._ensure()

@@ -82,7 +82,12 @@ void vpb_host_free(void* p);
 
 /* Introspection used by bench.py / tests. */
 int vpb_kernel_launches(const vpb_engine* e, int32_t batch);          /* kernels one vpb_infer enqueues */
-int vpb_set_option(vpb_engine* e, const char* name, int32_t value);   /* "stop_after", "attn_v_manual" */
+int vpb_set_option(vpb_engine* e, const char* name, int32_t value);   /* "stop_after", "attn_v_manual", "profile" */
+/* With option "profile"=1 every launch is bracketed by a CUDA-event pair on its stream; collect() synchronises,
+ * sums elapsed ms and launch counts per kernel class (arrays of vpb_profile_classes() entries) and resets. */
+int vpb_profile_classes(void);
+const char* vpb_profile_class_name(int32_t cls);
+int vpb_profile_collect(vpb_engine* e, float* ms_per_class, int32_t* launches_per_class);
 int vpb_read_buffer(vpb_engine* e, const char* name, void* host_dst, int64_t bytes);  /* synchronous debug read */
 
 /* Kernel-level entry points (unit tests / profiling).  All pointers are device pointers.

@@ -51,14 +51,14 @@ MODEL_DIMS = {
 # seeded weights that every side (reference, oracle, CUDA engine) can regenerate
 # --------------------------------------------------------------------------------------
 def make_state_dict(embed_dim: int, depth: int, num_keypoints: int, seed: int,
-                    deconv_filters: int = 256, peaky: float = 1.0) -> dict[str, np.ndarray]:
+                    deconv_filters: int = 256, peaky: float = 1.0, bumps: bool = False) -> dict[str, np.ndarray]:
     """Deterministic float32 weights under the reference's state_dict key names.
 
     Key/shape contract: SURVEY.md section 8b (probed from ViTPose(cfg).state_dict()).
     np.random.RandomState is a frozen stream, so the GPU box regenerates the same
     numbers without the reference being present.  BN running stats are randomised
-    so the eval-mode fold is exercised; `peaky` scales the final 1x1 conv so that
-    heatmaps have clearly positive maxima.
+    so the eval-mode fold is exercised; `peaky` scales the random part of the final 1x1 conv;
+    `bumps=True` adds the signal pathway of _add_bump_pathway (one clear peak per keypoint).
     """
     rs = np.random.RandomState(seed)
     D, F = embed_dim, deconv_filters
@@ -88,7 +88,7 @@ def make_state_dict(embed_dim: int, depth: int, num_keypoints: int, seed: int,
     sd["backbone.last_norm.bias"] = nrm(D, std=0.02)
     cin = D
     for li in (0, 3):
-        sd[f"keypoint_head.deconv_layers.{li}.weight"] = nrm(cin, F, 4, 4, std=1.0 / math.sqrt(cin))
+        sd[f"keypoint_head.deconv_layers.{li}.weight"] = nrm(cin, F, 4, 4, std=(0.15 if bumps else 1.0) / math.sqrt(cin))
         b = f"keypoint_head.deconv_layers.{li + 1}."
         sd[b + "weight"] = nrm(F, std=0.1, mean=1.0)
         sd[b + "bias"] = nrm(F, std=0.1)
@@ -98,7 +98,29 @@ def make_state_dict(embed_dim: int, depth: int, num_keypoints: int, seed: int,
         cin = F
     sd["keypoint_head.final_layer.weight"] = nrm(num_keypoints, F, 1, 1, std=0.02 * peaky)
     sd["keypoint_head.final_layer.bias"] = nrm(num_keypoints, std=0.01)
+    if bumps:
+        _add_bump_pathway(sd, rs, D, F, num_keypoints)
     return sd
+
+
+def _add_bump_pathway(sd: dict, rs, D: int, F: int, K: int) -> None:
+    """Superimpose a 'trained-like' signal path on the random weights so heatmaps carry one clear
+    peak per keypoint (random weights alone give noise fields whose argmax / Taylor step are
+    ill-conditioned, which makes keypoint-pixel error meaningless):
+      keypoint k owns token t_k and channel c_k = k % min(D, F).  pos_embed makes channel c_k hot at
+      token t_k; both deconvs carry channel c_k -> c_k through a positive 4x4 bump kernel; the 1x1
+      conv reads channel c_k into heatmap k.  Every other weight stays random, so all the arithmetic
+      of the path still contributes (as noise) to the result.
+    """
+    kern = np.outer([1.0, 2.0, 2.0, 1.0], [1.0, 2.0, 2.0, 1.0]).astype(np.float32) / 4.0
+    nch = min(D, F)
+    for k in range(K):
+        c = k % nch
+        t = int(rs.randint(0, TOKENS))
+        sd["backbone.pos_embed"][0, 1 + t, c] += np.float32(12.0)
+        sd["keypoint_head.deconv_layers.0.weight"][c, c] += kern * np.float32(1.5)
+        sd["keypoint_head.deconv_layers.3.weight"][c, c] += kern * np.float32(1.0)
+        sd["keypoint_head.final_layer.weight"][k, c, 0, 0] += np.float32(0.03)
 
 
 def make_crops(batch: int, seed: int) -> np.ndarray:

@@ -21,7 +21,7 @@ def _engine(g, max_batch=8):
     D, depth, heads, K, B, wseed, xseed = (int(v) for v in g["meta"])
     size = {384: "s", 768: "b", 1024: "l", 1280: "h"}[D]
     m = ViTPose(model_cfg(size, K), max_batch=max_batch)
-    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in O.make_state_dict(D, depth, K, wseed, peaky=float(g["peaky"])).items()})
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in O.make_state_dict(D, depth, K, wseed, peaky=float(g["peaky"]), bumps=True).items()})
     m.to("cuda:0")
     return m, O.make_crops(B, xseed)
 
@@ -42,15 +42,27 @@ def test_forward_heatmaps_vs_reference(golden_dir, name):
     assert np.array_equal(hm2, hm)                                   # deterministic
     B, K = hm.shape[:2]
     assert np.array_equal(idx.cpu().numpy(), hm.reshape(B, K, -1).argmax(-1).astype(np.int32))
-    # keypoints vs the reference pipeline (fp32 forward + reference decode)
-    dev = np.linalg.norm(kp.cpu().numpy()[..., :2] - g["kpts"][..., :2], axis=-1)
-    # heatmap units -> crop pixels differ per crop; report in heatmap cells as well
-    print(name, "keypoint deviation px mean", dev.mean(), "max", dev.max())
-    assert dev.mean() < KPT_MEAN_PX_TOL * max(1.0, float(g["org_wh"].max()) / 48.0)
+    # keypoints vs the reference pipeline (fp32 forward + reference decode), over the keypoints the
+    # reference itself would report (score above VitInference.draw's default confidence_threshold 0.5 is
+    # the user-visible set; 0.3 keeps a margin).  Deviation in pixels of the 256x192 model input.
+    kpn = kp.cpu().numpy()
+    to_model_px = np.stack([256.0 / g["org_wh"][:, 1], 192.0 / g["org_wh"][:, 0]], -1)[:, None, :]   # (y, x) scale
+    dev = np.linalg.norm((kpn[..., :2] - g["kpts"][..., :2]) * to_model_px, axis=-1)
+    vis = g["kpts"][..., 2] > 0.3
+    print(name, "visible keypoints", int(vis.sum()), "/", vis.size, "deviation px mean", dev[vis].mean(), "max", dev[vis].max(),
+          "| score Linf", np.abs(kpn[..., 2] - g["kpts"][..., 2]).max())
+    assert vis.sum() >= 0.8 * vis.size
+    assert dev[vis].mean() < KPT_MEAN_PX_TOL
+    ridx = ref.reshape(B, K, -1).argmax(-1)
+    eidx = idx.cpu().numpy()
+    cell = np.maximum(np.abs(eidx % 48 - ridx % 48), np.abs(eidx // 48 - ridx // 48))
+    print(name, "argmax cell identical to fp32 reference:", float((eidx == ridx)[vis].mean()))
+    assert cell[vis].max() <= 1                                      # a peak lying between two cells may flip to its neighbour
     # and the engine's decode of its own heatmaps equals the oracle's decode of the same heatmaps
     okp, oidx = O.decode_maps(hm, g["org_wh"], wrap="crop")
-    assert np.array_equal(oidx, idx.cpu().numpy())
-    assert np.abs(okp - kp.cpu().numpy()).max() < 5e-3
+    assert np.array_equal(oidx, eidx)
+    assert np.array_equal(okp[..., 2], kpn[..., 2])
+    assert np.abs(okp - kpn)[vis].max() < 5e-3                       # px; same heatmaps, same algorithm, logf vs np.log ulps
 
 
 def test_host_api_matches_device_api(golden_dir):

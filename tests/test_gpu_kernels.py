@@ -68,7 +68,7 @@ def test_decode_nan_and_ties_first_index():
 # ------------------------------------------------------------------------------------------------ LayerNorm
 @pytest.mark.parametrize("D", [384, 768, 1024, 1280])
 def test_layernorm(D):
-    from tests.gpu_util import layernorm
+    from gpu_util import layernorm
     torch.manual_seed(D)
     x = torch.randn(1000, D, device=_dev()) * 3 + 0.5
     g = torch.randn(D, device=_dev()) * 0.1 + 1
@@ -82,7 +82,7 @@ def test_layernorm(D):
 # ------------------------------------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (384, 768, 768), (1000, 2304, 768), (12288, 768, 3072), (200, 384, 384)])
 def test_gemm_bias_bf16(M, N, K):
-    from tests.gpu_util import EPI_BF16, gemm
+    from gpu_util import EPI_BF16, gemm
     torch.manual_seed(M + N + K)
     a = (torch.randn(M, K, device=_dev()) * 0.5).bfloat16()
     w = (torch.randn(N, K, device=_dev()) * 0.05).bfloat16()
@@ -96,7 +96,7 @@ def test_gemm_bias_bf16(M, N, K):
 
 
 def test_gemm_gelu():
-    from tests.gpu_util import EPI_BF16_GELU, gemm
+    from gpu_util import EPI_BF16_GELU, gemm
     torch.manual_seed(1)
     M, N, K = 640, 3072, 768
     a = (torch.randn(M, K, device=_dev()) * 0.5).bfloat16()
@@ -109,7 +109,7 @@ def test_gemm_gelu():
 
 
 def test_gemm_residual_inplace_and_posmod():
-    from tests.gpu_util import EPI_F32_RESID, gemm
+    from gpu_util import EPI_F32_RESID, gemm
     torch.manual_seed(2)
     M, N, K = 576, 768, 768
     a = (torch.randn(M, K, device=_dev()) * 0.5).bfloat16()
@@ -127,7 +127,7 @@ def test_gemm_residual_inplace_and_posmod():
 
 
 def test_gemm_deconv_phase_scatter_relu():
-    from tests.gpu_util import EPI_BF16_RELU_UP, gemm
+    from gpu_util import EPI_BF16_RELU_UP, gemm
     torch.manual_seed(3)
     B, H, W, K = 3, 16, 12, 1024
     M = B * H * W
@@ -144,7 +144,7 @@ def test_gemm_deconv_phase_scatter_relu():
 
 @pytest.mark.parametrize("Kk,Npad", [(17, 32), (25, 32), (133, 144)])
 def test_gemm_heatmap_nchw(Kk, Npad):
-    from tests.gpu_util import EPI_F32_NCHW, gemm
+    from gpu_util import EPI_F32_NCHW, gemm
     torch.manual_seed(4)
     B, pix, K = 2, 3072, 256
     a = (torch.randn(B * pix, K, device=_dev()) * 0.5).bfloat16()
@@ -163,7 +163,7 @@ def test_gemm_heatmap_nchw(Kk, Npad):
 @pytest.mark.parametrize("v_manual", [0, 1])
 @pytest.mark.parametrize("B,heads", [(1, 1), (3, 12), (40, 16)])
 def test_attention(B, heads, v_manual):
-    from tests.gpu_util import attention
+    from gpu_util import attention
     torch.manual_seed(B * 100 + heads)
     D = heads * 64
     qkv = torch.randn(B * 192, 3 * D, device=_dev())

@@ -18,7 +18,7 @@ def _load(golden_dir, name):
 def test_forward_matches_reference_heatmaps(golden_dir, name):
     g = _load(golden_dir, "fwd_" + name)
     D, depth, heads, K, B, wseed, xseed = (int(v) for v in g["meta"])
-    sd = O.make_state_dict(D, depth, K, wseed, peaky=float(g["peaky"]))
+    sd = O.make_state_dict(D, depth, K, wseed, peaky=float(g["peaky"]), bumps=True)
     hm = O.forward_heatmaps(O.make_crops(B, xseed), sd, depth, heads)
     ref = g["heatmaps"]
     assert hm.shape == ref.shape == (B, K, O.HM_H, O.HM_W)
