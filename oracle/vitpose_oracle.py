@@ -114,10 +114,12 @@ def _add_bump_pathway(sd: dict, rs, D: int, F: int, K: int) -> None:
     """
     kern = np.outer([1.0, 2.0, 2.0, 1.0], [1.0, 2.0, 2.0, 1.0]).astype(np.float32) / 4.0
     nch = min(D, F)
+    depth = sum(1 for k in sd if k.endswith(".norm1.weight"))
+    amp = 12.0 * depth / 12.0          # the residual stream's random part grows with depth; keep the bump on top
     for k in range(K):
         c = k % nch
         t = int(rs.randint(0, TOKENS))
-        sd["backbone.pos_embed"][0, 1 + t, c] += np.float32(12.0)
+        sd["backbone.pos_embed"][0, 1 + t, c] += np.float32(amp)
         sd["keypoint_head.deconv_layers.0.weight"][c, c] += kern * np.float32(1.5)
         sd["keypoint_head.deconv_layers.3.weight"][c, c] += kern * np.float32(1.0)
         sd["keypoint_head.final_layer.weight"][k, c, 0, 0] += np.float32(0.03)
