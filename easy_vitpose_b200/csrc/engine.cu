@@ -57,16 +57,18 @@ static int load_driver_api() {
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   return VPB_OK;
 }
-// bf16 row-major [rows, cols] with row pitch `ld` elements; box = [box_rows, 64 cols] (128 B) 128B-swizzled.
-static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+// Row-major [rows, cols] tensor with row pitch `ld` elements; box = [box_rows, 128 bytes of columns], 128B-swizzled.
+// bf16: 64 columns per box (GEMM operands, bf16 outputs); f32: 32 columns per box (the fp32 residual stream).
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, bool f32 = false) {
   VPB_TRY(load_driver_api());
+  const uint64_t esz = f32 ? 4 : 2;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {ld * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(VPB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%u", (int)r,
                                      (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
   return VPB_OK;
@@ -76,27 +78,35 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
 static int g_num_sms = 0;
 static bool g_attr_done = false;
 
+// `tout` is the output tensor map of the TMA epilogues (EPI_BF16, EPI_BF16_GELU: bf16 box 64x32; EPI_F32_ADD: f32 box
+// 32x32); direct epilogues ignore it (pass any valid map).  W maps carry boxes of BN/2 rows: each CTA of the pair
+// fetches half of the W tile and multicasts it.
 template <int BN, int EPI>
-static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tout, const GemmParams& p, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, EPI>;
   auto kern = gemm_bf16_tcgen05<BN, EPI>;
   static bool attr = false;
   if (!attr) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr = true;
   }
-  const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tw, p);
+  const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int pairs = ((num_m + GEMM_CL - 1) / GEMM_CL) * ((p.N + BN - 1) / BN);
+  const int max_clusters = g_num_sms / GEMM_CL;
+  const int grid = GEMM_CL * (pairs < max_clusters ? pairs : max_clusters);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tw, tout, p);
   CU_TRY(cudaGetLastError());
   return VPB_OK;
 }
-static int gemm_launch(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tw, const GemmParams& p, cudaStream_t st) {
+static int gemm_launch(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tout, const GemmParams& p,
+                       cudaStream_t st) {
   if (p.K % GEMM_BK != 0 || p.K <= 0) return fail(VPB_ERR_ARG, "gemm: K=%d must be a positive multiple of 64", p.K);
+  if (epi_uses_tma(epi) && (p.N % 64 != 0 || p.bias == nullptr)) return fail(VPB_ERR_ARG, "gemm: TMA epilogue wants N %% 64 == 0 and a bias");
 #define VPB_CASE(BN_, EPI_) \
-  if (bn == BN_ && epi == EPI_) return gemm_launch_t<BN_, EPI_>(ta, tw, p, st);
+  if (bn == BN_ && epi == EPI_) return gemm_launch_t<BN_, EPI_>(ta, tw, tout, p, st);
   VPB_CASE(256, EPI_BF16) VPB_CASE(128, EPI_BF16)
   VPB_CASE(256, EPI_BF16_GELU) VPB_CASE(128, EPI_BF16_GELU)
+  VPB_CASE(256, EPI_F32_ADD) VPB_CASE(128, EPI_F32_ADD)
   VPB_CASE(256, EPI_F32_RESID) VPB_CASE(128, EPI_F32_RESID)
   VPB_CASE(256, EPI_BF16_RELU_UP)
   VPB_CASE(32, EPI_F32_NCHW) VPB_CASE(144, EPI_F32_NCHW)
@@ -173,7 +183,8 @@ struct vpb_engine {
   __nv_bfloat16 *patch_rows, *xn, *qkv, *attn, *hid, *col1, *d1, *col2, *d2;
   float *x, *heat, *kpts;
   int32_t *idx, *org_wh;
-  CUtensorMap m_patch_rows, m_xn, m_attn, m_hid, m_col1[4], m_col2[4], m_d2, m_qkv_att;
+  CUtensorMap m_patch_rows, m_xn, m_attn, m_hid, m_col1[4], m_col2[4], m_d2, m_qkv_att;   // A operands / attention boxes
+  CUtensorMap o_qkv, o_hid, o_x;                                                             // TMA-epilogue outputs
 };
 
 template <typename T>
@@ -277,7 +288,7 @@ static int pack_linear(vpb_engine* e, LinearW& L, const std::string& wkey, const
   if (!bkey.empty()) pack_bias<<<cdiv(n_pad, 256), 256>>>(e->staged[bkey].first, L.b, n, n_pad, scaled_rows, scale);
   else CU_TRY(cudaMemset(L.b, 0, n_pad * sizeof(float)));
   CU_TRY(cudaGetLastError());
-  return make_map(&L.map, L.w, n_pad, k, k, bn);
+  return make_map(&L.map, L.w, n_pad, k, k, bn / GEMM_CL);
 }
 
 static int copy_vec(vpb_engine* e, float** dst, const std::string& key) {
@@ -330,7 +341,7 @@ extern "C" int vpb_finalize(vpb_engine* e) {
     CU_TRY(cudaGetLastError());
     for (int ph = 0; ph < 4; ++ph) {
       dc[ph].w = wp + static_cast<size_t>(ph) * 256 * 4 * cin; dc[ph].b = shift; dc[ph].n = 256; dc[ph].k = 4 * cin; dc[ph].bn = 256;
-      VPB_TRY(make_map(&dc[ph].map, dc[ph].w, 256, 4 * cin, 4 * cin, 256));
+      VPB_TRY(make_map(&dc[ph].map, dc[ph].w, 256, 4 * cin, 4 * cin, 256 / GEMM_CL));
     }
     cin = 256;
   }
@@ -364,6 +375,9 @@ extern "C" int vpb_finalize(vpb_engine* e) {
   }
   VPB_TRY(make_map(&e->m_d2, e->d2, B * 3072, 256, 256, 128));
   VPB_TRY(make_map(&e->m_qkv_att, e->qkv, M, 3 * D, 3 * D, 192));
+  VPB_TRY(make_map(&e->o_qkv, e->qkv, M, 3 * D, 3 * D, 32));
+  VPB_TRY(make_map(&e->o_hid, e->hid, M, 4 * D, 4 * D, 32));
+  VPB_TRY(make_map(&e->o_x, e->x, M, D, D, 32, /*f32=*/true));
   CU_TRY(cudaDeviceSynchronize());
   for (auto& kv : e->staged) cudaFree(kv.second.first);
   e->staged.clear();
@@ -409,7 +423,7 @@ static int backbone(vpb_engine* e, const float* d_crops, int B, cudaStream_t st)
     GemmParams p = gp(M, D, 768, nullptr, e->x, D);
     p.resid = e->pos_bias; p.resid_mod = 192;
     e->prof.begin(KC_GEMM_PATCH, st);
-    VPB_TRY(gemm_launch(e->patch.bn, EPI_F32_RESID, e->m_patch_rows, e->patch.map, p, st));
+    VPB_TRY(gemm_launch(e->patch.bn, EPI_F32_RESID, e->m_patch_rows, e->patch.map, e->m_patch_rows, p, st));
     e->prof.end(st);
   }
   if (stop == 2) return VPB_OK;
@@ -420,7 +434,7 @@ static int backbone(vpb_engine* e, const float* d_crops, int B, cudaStream_t st)
     e->prof.end(st);
     if (stop == 3) return VPB_OK;
     e->prof.begin(KC_GEMM_QKV, st);
-    VPB_TRY(gemm_launch(b.qkv.bn, EPI_BF16, e->m_xn, b.qkv.map, gp(M, 3 * D, D, b.qkv.b, e->qkv, 3 * D), st));
+    VPB_TRY(gemm_launch(b.qkv.bn, EPI_BF16, e->m_xn, b.qkv.map, e->o_qkv, gp(M, 3 * D, D, b.qkv.b, e->qkv, 3 * D), st));
     e->prof.end(st);
     if (stop == 4) return VPB_OK;
     {
@@ -434,10 +448,9 @@ static int backbone(vpb_engine* e, const float* d_crops, int B, cudaStream_t st)
     }
     if (stop == 5) return VPB_OK;
     {
-      GemmParams p = gp(M, D, D, b.proj.b, e->x, D);
-      p.resid = e->x;
+      GemmParams p = gp(M, D, D, b.proj.b, e->x, D);     // x += attn * Wproj^T + b   (TMA reduce-add into the fp32 stream)
       e->prof.begin(KC_GEMM_PROJ, st);
-      VPB_TRY(gemm_launch(b.proj.bn, EPI_F32_RESID, e->m_attn, b.proj.map, p, st));
+      VPB_TRY(gemm_launch(b.proj.bn, EPI_F32_ADD, e->m_attn, b.proj.map, e->o_x, p, st));
       e->prof.end(st);
     }
     if (stop == 6) return VPB_OK;
@@ -445,14 +458,13 @@ static int backbone(vpb_engine* e, const float* d_crops, int B, cudaStream_t st)
     VPB_TRY(layernorm(e->x, b.ln2_g, b.ln2_b, e->xn, M, D, 1e-6f, st));
     e->prof.end(st);
     e->prof.begin(KC_GEMM_FC1, st);
-    VPB_TRY(gemm_launch(b.fc1.bn, EPI_BF16_GELU, e->m_xn, b.fc1.map, gp(M, 4 * D, D, b.fc1.b, e->hid, 4 * D), st));
+    VPB_TRY(gemm_launch(b.fc1.bn, EPI_BF16_GELU, e->m_xn, b.fc1.map, e->o_hid, gp(M, 4 * D, D, b.fc1.b, e->hid, 4 * D), st));
     e->prof.end(st);
     if (stop == 7) return VPB_OK;
     {
       GemmParams p = gp(M, D, 4 * D, b.fc2.b, e->x, D);
-      p.resid = e->x;
       e->prof.begin(KC_GEMM_FC2, st);
-      VPB_TRY(gemm_launch(b.fc2.bn, EPI_F32_RESID, e->m_hid, b.fc2.map, p, st));
+      VPB_TRY(gemm_launch(b.fc2.bn, EPI_F32_ADD, e->m_hid, b.fc2.map, e->o_x, p, st));
       e->prof.end(st);
     }
     if (stop == 8) return VPB_OK;
@@ -479,7 +491,7 @@ static int head(vpb_engine* e, int B, float* d_heat, cudaStream_t st) {
       GemmParams p = gp(M, 256, 4 * D, e->dc1[ph].b, e->d1, 256);
       p.up_h = 16; p.up_w = 12; p.up_py = ph >> 1; p.up_px = ph & 1;
       e->prof.begin(KC_GEMM_DECONV, st);
-      VPB_TRY(gemm_launch(256, EPI_BF16_RELU_UP, e->m_col1[ph], e->dc1[ph].map, p, st));
+      VPB_TRY(gemm_launch(256, EPI_BF16_RELU_UP, e->m_col1[ph], e->dc1[ph].map, e->m_col1[ph], p, st));
       e->prof.end(st);
     }
   }
@@ -495,7 +507,7 @@ static int head(vpb_engine* e, int B, float* d_heat, cudaStream_t st) {
       GemmParams p = gp(M, 256, 1024, e->dc2[ph].b, e->d2, 256);
       p.up_h = 32; p.up_w = 24; p.up_py = ph >> 1; p.up_px = ph & 1;
       e->prof.begin(KC_GEMM_DECONV, st);
-      VPB_TRY(gemm_launch(256, EPI_BF16_RELU_UP, e->m_col2[ph], e->dc2[ph].map, p, st));
+      VPB_TRY(gemm_launch(256, EPI_BF16_RELU_UP, e->m_col2[ph], e->dc2[ph].map, e->m_col2[ph], p, st));
       e->prof.end(st);
     }
   }
@@ -504,7 +516,7 @@ static int head(vpb_engine* e, int B, float* d_heat, cudaStream_t st) {
     GemmParams p = gp(B * 3072, e->n_final, 256, e->fin.b, d_heat, 0);
     p.n_valid = e->K; p.pix = 3072;
     e->prof.begin(KC_GEMM_FINAL, st);
-    VPB_TRY(gemm_launch(e->n_final, EPI_F32_NCHW, e->m_d2, e->fin.map, p, st));
+    VPB_TRY(gemm_launch(e->n_final, EPI_F32_NCHW, e->m_d2, e->fin.map, e->m_d2, p, st));
     e->prof.end(st);
   }
   return VPB_OK;
@@ -654,14 +666,17 @@ extern "C" int vpb_gemm(const void* d_a, const void* d_w, const float* d_bias, v
   else bn = bn_for(n);
   if (epilogue != EPI_F32_NCHW && n % bn != 0) return fail(VPB_ERR_ARG, "vpb_gemm: N=%d must be a multiple of %d", n, bn);
   if (epilogue == EPI_F32_NCHW && n != bn) return fail(VPB_ERR_ARG, "vpb_gemm: NCHW epilogue wants W padded to %d rows", bn);
-  CUtensorMap ta, tw;
+  CUtensorMap ta, tw, tout;
   VPB_TRY(make_map(&ta, d_a, m, k, k, 128));
-  VPB_TRY(make_map(&tw, d_w, n, k, k, bn));
+  VPB_TRY(make_map(&tw, d_w, n, k, k, bn / GEMM_CL));
+  tout = ta;
+  if (epilogue == EPI_BF16 || epilogue == EPI_BF16_GELU) VPB_TRY(make_map(&tout, d_out, m, n, n, 32));
+  if (epilogue == EPI_F32_ADD) VPB_TRY(make_map(&tout, d_out, m, n, n, 32, /*f32=*/true));
   GemmParams p = gp(m, n, k, d_bias, d_out, n);
   p.resid = d_resid; p.resid_mod = resid_mod;
   if (epilogue == EPI_F32_NCHW) { p.n_valid = aux0; p.pix = aux1; }
   if (epilogue == EPI_BF16_RELU_UP) { p.up_h = aux0; p.up_w = aux1; p.up_py = aux2; p.up_px = aux3; }
-  return gemm_launch(bn, epilogue, ta, tw, p, static_cast<cudaStream_t>(stream));
+  return gemm_launch(bn, epilogue, ta, tw, tout, p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vpb_attention(const void* d_qkv, int32_t batch, int32_t heads, void* d_out, int32_t v_manual, void* stream) {

@@ -3,11 +3,17 @@
 //   warp 0 (1 thread)  TMA producer: A / W tiles -> 128B-swizzled smem ring, mbarrier full/empty
 //   warp 1 (1 thread)  tcgen05.mma issuer: 128 x BN x 16 UMMAs, fp32 accumulators in TMEM (2 stages)
 //   warp 2             TMEM allocator
-//   warps 4..11        epilogue: tcgen05.ld -> registers -> bias / GELU / ReLU / residual -> global
+//   warps 4..11        epilogue: tcgen05.ld -> registers -> bias / GELU / ReLU -> swizzled smem staging ->
+//                      TMA store (bf16) or TMA reduce-add (fp32 residual, the add happens in L2)
 //
-// Both operands are K-major (nn.Linear keeps W as [N,K]), so no transposes anywhere.  One CTA per SM,
-// tiles handed out statically (tile = blockIdx.x + i * gridDim.x, m fastest so that the CTAs running
-// together share one W tile in L2).  The accumulator double buffer lets the epilogue of tile i overlap
+// Both operands are K-major (nn.Linear keeps W as [N,K]), so no transposes anywhere.
+//
+// L2 -> SM traffic is what bounds a 128 x 256 tile (85 flop/B), so CTAs run as clusters of CL=2 along M:
+// the pair works on two vertically adjacent tiles of the same column block, each CTA fetches its own A tile
+// and HALF of the W tile and multicasts that half into both CTAs' smem (128 flop/B).  A ring slot is reused
+// only after BOTH CTAs' MMAs have retired (tcgen05.commit multicast onto both empty barriers).
+// Clusters are handed pair-tiles statically (pair = clusterid + i * nclusters, m-pair fastest so the clusters
+// running together share one W tile in L2).  The accumulator double buffer lets the epilogue of tile i overlap
 // the main loop of tile i+1.
 #pragma once
 #include <cuda.h>
@@ -17,19 +23,20 @@
 namespace vpb {
 
 enum Epilogue : int {
-  EPI_BF16 = 0,         // out bf16 [M,ldc]   = acc + bias                              (qkv)
-  EPI_BF16_GELU = 1,    // out bf16 [M,ldc]   = gelu_erf(acc + bias)                    (fc1)
-  EPI_BF16_RELU_UP = 2, // out bf16 NHWC, row (b,y,x) -> (b,2y+py,2x+px), relu(acc+bias) (deconv phase)
-  EPI_F32_RESID = 3,    // out f32 [M,ldc]    = resid[row or row%mod] + acc + bias      (proj, fc2, patch embed)
-  EPI_F32_NCHW = 4,     // out f32 [b,n,pix]  = acc + bias for n < n_valid              (final 1x1 conv -> heatmaps)
+  EPI_BF16 = 0,         // out bf16 [M,ldc]   = acc + bias                              (qkv)            TMA store
+  EPI_BF16_GELU = 1,    // out bf16 [M,ldc]   = gelu_erf(acc + bias)                    (fc1)            TMA store
+  EPI_BF16_RELU_UP = 2, // out bf16 NHWC, row (b,y,x) -> (b,2y+py,2x+px), relu(acc+bias) (deconv phase)   direct
+  EPI_F32_RESID = 3,    // out f32 [M,ldc]    = resid[row % mod] + acc + bias           (patch embed)    direct
+  EPI_F32_NCHW = 4,     // out f32 [b,n,pix]  = acc + bias for n < n_valid              (1x1 conv)       direct
+  EPI_F32_ADD = 5,      // out f32 [M,ldc]   += acc + bias                              (proj, fc2)      TMA reduce-add
 };
 
 struct GemmParams {
   int M, N, K;            // problem (rows of A, rows of W, reduction); K % 64 == 0
   const float* bias;      // [N] (padded to the N tile) or nullptr
-  void* out;
-  int ldc;                // row pitch of out in elements (row-major epilogues)
-  const float* resid;     // EPI_F32_RESID: residual source (may alias out)
+  void* out;              // direct epilogues only
+  int ldc;                // row pitch of out in elements (direct row-major epilogues)
+  const float* resid;     // EPI_F32_RESID: residual source
   int resid_mod;          // 0: resid row = row; >0: resid row = row % resid_mod (position embedding)
   int n_valid;            // EPI_F32_NCHW: number of real output channels
   int pix;                // EPI_F32_NCHW: pixels per image (rows per batch item)
@@ -41,34 +48,44 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_CL = 2;                 // CTAs per cluster (along M)
+constexpr int GEMM_STAGE_TILE = 4096;      // one epilogue warp's staging tile: 32 rows x 128 B
 
-template <int BN>
+__host__ __device__ constexpr bool epi_uses_tma(int epi) { return epi == EPI_BF16 || epi == EPI_BF16_GELU || epi == EPI_F32_ADD; }
+
+template <int BN, int EPI>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_SLICE = B_BYTES / GEMM_CL;                // what one CTA fetches and multicasts
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static constexpr int STAGING = epi_uses_tma(EPI) ? GEMM_EPI_WARPS * GEMM_STAGE_TILE : 0;
+  static constexpr int STAGES_RAW = (227 * 1024 - 2048 - STAGING) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int HALF = BN / 2;                              // columns per epilogue warp-group
   static constexpr int CH = (HALF % 32 == 0) ? 32 : (HALF % 16 == 0) ? 16 : 8;
-  static_assert(B_BYTES % 1024 == 0, "W tile must keep 1024-byte alignment of the ring");
+  static_assert(B_SLICE % 1024 == 0, "W slices must keep 1024-byte alignment of the ring");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
   static_assert(HALF % CH == 0, "epilogue chunking");
+  static_assert(!epi_uses_tma(EPI) || HALF % 64 == 0, "TMA epilogues stage 64 bf16 / 32 f32 columns at a time");
+  static_assert(STAGES >= 3, "ring too shallow");
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(GEMM_CL, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                  const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+                  const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+  using Cfg = GemmCfg<BN, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* acc_full = empty_bar + Cfg::STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;               // [2]
@@ -76,17 +93,23 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = static_cast<int>(cluster_ctarank());
+  const int cluster = static_cast<int>(cluster_id_x());
+  const int num_clusters = static_cast<int>(cluster_count_x());
   const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int num_mp = (num_m + GEMM_CL - 1) / GEMM_CL;               // m-block pairs
   const int num_n = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  const int num_pairs = num_mp * num_n;
   const int num_kb = p.K / GEMM_BK;
+  constexpr uint16_t kAllCtas = (1u << GEMM_CL) - 1;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
+    if constexpr (epi_uses_tma(EPI)) tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], GEMM_CL);            // both CTAs' MMAs must have retired before a slot is refilled
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
@@ -96,7 +119,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before_sync();
-  __syncthreads();
+  cluster_sync_all();                               // barriers of BOTH CTAs are live before any multicast / remote arrive
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -104,15 +127,16 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % num_m) * GEMM_BM;
-      const int n0 = (tile / num_m) * BN;
+    for (int pair = cluster; pair < num_pairs; pair += num_clusters) {
+      const int m0 = ((pair % num_mp) * GEMM_CL + cta_rank) * GEMM_BM;   // may lie past M: TMA zero-fills
+      const int n0 = (pair / num_mp) * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);        // own A + both halves of W
         tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
-        tma_load_2d(sa + Cfg::A_BYTES, &tmap_w, &full_bar[stage], kb * GEMM_BK, n0);
+        tma_load_2d_mcast(sa + Cfg::A_BYTES + cta_rank * Cfg::B_SLICE, &tmap_w, &full_bar[stage], kb * GEMM_BK,
+                          n0 + cta_rank * (BN / GEMM_CL), kAllCtas);
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -122,7 +146,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int pair = cluster; pair < num_pairs; pair += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&acc_empty[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
@@ -139,7 +163,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           // +32 B per K=16 step inside the 128-byte swizzle atom (start-address field is >>4)
           umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
         }
-        umma_commit(&empty_bar[stage]);               // smem slot reusable once these MMAs retire
+        umma_commit_mcast(&empty_bar[stage], kAllCtas);   // slot reusable in both CTAs once these MMAs retire
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(&acc_full[acc]);                    // accumulator complete -> epilogue
@@ -149,86 +173,132 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int ew = warp - 4;
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
     const int half = ew >> 2;                         // which half of the BN columns
+    uint8_t* stile = staging + ew * GEMM_STAGE_TILE;  // this warp's 32 x 128 B staging tile (TMA epilogues)
+    const int sw = lane & 7;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int pair = cluster; pair < num_pairs; pair += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile % num_m) * GEMM_BM;
-      const int n0 = (tile / num_m) * BN;
+      const int m0 = ((pair % num_mp) * GEMM_CL + cta_rank) * GEMM_BM;
+      const int n0 = (pair / num_mp) * BN;
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE;
 
-      // per-row output addressing
-      size_t out_row = static_cast<size_t>(row);
-      if constexpr (EPI == EPI_BF16_RELU_UP) {
-        const int hw = p.up_h * p.up_w;
-        const int b = row / hw, r = row % hw;
-        const int y = r / p.up_w, x = r % p.up_w;
-        out_row = (static_cast<size_t>(b) * (2 * p.up_h) + (2 * y + p.up_py)) * (2 * p.up_w) + (2 * x + p.up_px);
-      }
-      size_t res_row = static_cast<size_t>(row);
-      if constexpr (EPI == EPI_F32_RESID) {
-        if (p.resid_mod > 0) res_row = static_cast<size_t>(row % p.resid_mod);
-      }
-
+      if constexpr (epi_uses_tma(EPI)) {
+        // 64 bf16 or 32 f32 output columns (= one 128-byte staging row) per round
+        constexpr int COLS = (EPI == EPI_F32_ADD) ? 32 : 64;
 #pragma unroll 1
-      for (int c = 0; c < Cfg::HALF; c += Cfg::CH) {
-        const int col = half * Cfg::HALF + c;         // column inside the tile
-        const int n = n0 + col;                       // global column
-        uint32_t r[Cfg::CH];
-        tmem_ld<Cfg::CH>(t_row + col, r);
-        tmem_ld_wait();
-        float v[Cfg::CH];
+        for (int c = 0; c < Cfg::HALF; c += COLS) {
+          const int col = half * Cfg::HALF + c;
+          const int n = n0 + col;
+          if (lane == 0) tma_store_wait_read<0>();    // previous store has finished reading the staging tile
+          __syncwarp();
 #pragma unroll
-        for (int j = 0; j < Cfg::CH; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
+          for (int sub = 0; sub < COLS; sub += 32) {
+            uint32_t r[32];
+            tmem_ld32(t_row + col + sub, r);
+            tmem_ld_wait();
+            float v[32];
 #pragma unroll
-          for (int j = 0; j < Cfg::CH; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + sub + j));
+              v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+              v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+            }
+            if constexpr (EPI == EPI_BF16_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            }
+            // staging row = lane, 16-byte chunk index XOR (lane % 8): what a SWIZZLE_128B tensor map expects
+            uint8_t* srow = stile + lane * 128;
+            if constexpr (EPI == EPI_F32_ADD) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4*>(srow + ((q ^ sw) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 w;
+                w.x = pack_bf16(v[8 * q], v[8 * q + 1]); w.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+                w.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); w.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+                *reinterpret_cast<uint4*>(srow + ((((sub >> 3) + q) ^ sw) << 4)) = w;
+              }
+            }
+          }
+          fence_proxy_async_smem();                   // staging writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0 && n < p.N) {
+            if constexpr (EPI == EPI_F32_ADD) tma_reduce_add_2d(&tmap_out, stile, n, m0 + quarter * 32);
+            else tma_store_2d(&tmap_out, stile, n, m0 + quarter * 32);   // rows past M are clipped by the tensor map
+            tma_store_commit();
           }
         }
-        if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU || EPI == EPI_BF16_RELU_UP) {
-          if constexpr (EPI == EPI_BF16_GELU) {
+      } else {
+        // ---- direct epilogues (scattered / transposed outputs)
+        size_t out_row = static_cast<size_t>(row);
+        if constexpr (EPI == EPI_BF16_RELU_UP) {
+          const int hw = p.up_h * p.up_w;
+          const int b = row / hw, r = row % hw;
+          const int y = r / p.up_w, x = r % p.up_w;
+          out_row = (static_cast<size_t>(b) * (2 * p.up_h) + (2 * y + p.up_py)) * (2 * p.up_w) + (2 * x + p.up_px);
+        }
+        size_t res_row = static_cast<size_t>(row);
+        if constexpr (EPI == EPI_F32_RESID) {
+          if (p.resid_mod > 0) res_row = static_cast<size_t>(row % p.resid_mod);
+        }
+#pragma unroll 1
+        for (int c = 0; c < Cfg::HALF; c += Cfg::CH) {
+          const int col = half * Cfg::HALF + c;       // column inside the tile
+          const int n = n0 + col;                     // global column
+          uint32_t r[Cfg::CH];
+          tmem_ld<Cfg::CH>(t_row + col, r);
+          tmem_ld_wait();
+          float v[Cfg::CH];
 #pragma unroll
-            for (int j = 0; j < Cfg::CH; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < Cfg::CH; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < Cfg::CH; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
           }
           if constexpr (EPI == EPI_BF16_RELU_UP) {
 #pragma unroll
             for (int j = 0; j < Cfg::CH; ++j) v[j] = fmaxf(v[j], 0.0f);
-          }
-          if (row_ok && n < p.N) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + n;
+            if (row_ok && n < p.N) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + n;
 #pragma unroll
-            for (int j = 0; j < Cfg::CH; j += 8) {
-              uint4 q;
-              q.x = pack_bf16(v[j], v[j + 1]); q.y = pack_bf16(v[j + 2], v[j + 3]);
-              q.z = pack_bf16(v[j + 4], v[j + 5]); q.w = pack_bf16(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = q;
+              for (int j = 0; j < Cfg::CH; j += 8) {
+                uint4 q;
+                q.x = pack_bf16(v[j], v[j + 1]); q.y = pack_bf16(v[j + 2], v[j + 3]);
+                q.z = pack_bf16(v[j + 4], v[j + 5]); q.w = pack_bf16(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(o + j) = q;
+              }
             }
-          }
-        } else if constexpr (EPI == EPI_F32_RESID) {
-          if (row_ok && n < p.N) {
-            const float* rs = p.resid + res_row * p.ldc + n;
-            float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldc + n;
+          } else if constexpr (EPI == EPI_F32_RESID) {
+            if (row_ok && n < p.N) {
+              const float* rs = p.resid + res_row * p.ldc + n;
+              float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldc + n;
 #pragma unroll
-            for (int j = 0; j < Cfg::CH; j += 4) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rs + j);
-              float4 w4;
-              w4.x = v[j] + r4.x; w4.y = v[j + 1] + r4.y; w4.z = v[j + 2] + r4.z; w4.w = v[j + 3] + r4.w;
-              *reinterpret_cast<float4*>(o + j) = w4;
+              for (int j = 0; j < Cfg::CH; j += 4) {
+                const float4 r4 = *reinterpret_cast<const float4*>(rs + j);
+                float4 w4;
+                w4.x = v[j] + r4.x; w4.y = v[j + 1] + r4.y; w4.z = v[j + 2] + r4.z; w4.w = v[j + 3] + r4.w;
+                *reinterpret_cast<float4*>(o + j) = w4;
+              }
             }
-          }
-        } else {  // EPI_F32_NCHW: a warp's 32 lanes are 32 consecutive pixels -> coalesced per channel
-          if (row_ok) {
-            const int b = row / p.pix, pix = row % p.pix;
-            float* o = reinterpret_cast<float*>(p.out) + (static_cast<size_t>(b) * p.n_valid) * p.pix + pix;
+          } else {  // EPI_F32_NCHW: a warp's 32 lanes are 32 consecutive pixels -> coalesced per channel
+            if (row_ok) {
+              const int b = row / p.pix, pix = row % p.pix;
+              float* o = reinterpret_cast<float*>(p.out) + (static_cast<size_t>(b) * p.n_valid) * p.pix + pix;
 #pragma unroll
-            for (int j = 0; j < Cfg::CH; ++j) {
-              if (n + j < p.n_valid) o[static_cast<size_t>(n + j) * p.pix] = v[j];
+              for (int j = 0; j < Cfg::CH; ++j) {
+                if (n + j < p.n_valid) o[static_cast<size_t>(n + j) * p.pix] = v[j];
+              }
             }
           }
         }
@@ -237,10 +307,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
+    if constexpr (epi_uses_tma(EPI)) {
+      if (lane == 0) tma_store_wait_all<0>();         // staging must stay alive until the last store has drained
+    }
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  cluster_sync_all();                                 // the peer may still multicast into / arrive on this CTA
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 

@@ -109,7 +109,7 @@ def test_gemm_gelu():
 
 
 def test_gemm_residual_inplace_and_posmod():
-    from gpu_util import EPI_F32_RESID, gemm
+    from gpu_util import EPI_F32_ADD, EPI_F32_RESID, gemm
     torch.manual_seed(2)
     M, N, K = 576, 768, 768
     a = (torch.randn(M, K, device=_dev()) * 0.5).bfloat16()
@@ -117,7 +117,7 @@ def test_gemm_residual_inplace_and_posmod():
     bias = torch.randn(N, device=_dev())
     x = torch.randn(M, N, device=_dev())
     ref = x + a.float() @ w.float().T + bias
-    gemm(a, w, bias, x, EPI_F32_RESID, resid=x)                      # in place, like proj / fc2
+    gemm(a, w, bias, x, EPI_F32_ADD)                                 # x += ..., like proj / fc2 (TMA reduce-add)
     assert _rel(x, ref) < 2e-3
     pos = torch.randn(192, N, device=_dev())
     out = torch.zeros(M, N, device=_dev())
