@@ -116,6 +116,8 @@ static int gemm_launch(int bn, int epi, const CUtensorMap& ta, const CUtensorMap
 static int bn_for(int n) { return (n % 256 == 0) ? 256 : 128; }
 
 static int device_check(int device) {
+  static int checked_device = -1;
+  if (checked_device == device && g_num_sms > 0) return VPB_OK;
   cudaDeviceProp prop;
   CU_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(VPB_ERR_ARG, "device %d is sm_%d%d; this library only runs on sm_100 (B200), no fallback", device,
@@ -125,6 +127,7 @@ static int device_check(int device) {
     CU_TRY(cudaFuncSetAttribute(attention_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     g_attr_done = true;
   }
+  checked_device = device;
   return VPB_OK;
 }
 
@@ -402,9 +405,17 @@ static int layernorm(const float* x, const float* g, const float* b, __nv_bfloat
   return VPB_OK;
 }
 
+static int g_dbg_stages = 0;
+static long long* g_dbg_buf = nullptr;
+extern "C" int vpb_debug_gemm(int32_t stages_limit, void* d_counters) {   // counters: int64 [grid*8], see GemmParams::dbg
+  g_dbg_stages = stages_limit;
+  g_dbg_buf = reinterpret_cast<long long*>(d_counters);
+  return VPB_OK;
+}
 static GemmParams gp(int M, int N, int K, const float* bias, void* out, int ldc) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  p.stages_limit = g_dbg_stages; p.dbg = g_dbg_buf;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldc = ldc;
   return p;
 }

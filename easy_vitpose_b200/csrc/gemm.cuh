@@ -1,20 +1,21 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
 //
 //   warp 0 (1 thread)  TMA producer: A / W tiles -> 128B-swizzled smem ring, mbarrier full/empty
-//   warp 1 (1 thread)  tcgen05.mma issuer: 128 x BN x 16 UMMAs, fp32 accumulators in TMEM (2 stages)
+//   warp 1 (1 thread)  tcgen05.mma issuer (leader CTA): 256 x BN x 16 pair-UMMAs, fp32 accumulators in TMEM (2 stages)
 //   warp 2             TMEM allocator
 //   warps 4..11        epilogue: tcgen05.ld -> registers -> bias / GELU / ReLU -> swizzled smem staging ->
 //                      TMA store (bf16) or TMA reduce-add (fp32 residual, the add happens in L2)
 //
 // Both operands are K-major (nn.Linear keeps W as [N,K]), so no transposes anywhere.
 //
-// L2 -> SM traffic is what bounds a 128 x 256 tile (85 flop/B), so CTAs run as clusters of CL=2 along M:
-// the pair works on two vertically adjacent tiles of the same column block, each CTA fetches its own A tile
-// and HALF of the W tile and multicasts that half into both CTAs' smem (128 flop/B).  A ring slot is reused
-// only after BOTH CTAs' MMAs have retired (tcgen05.commit multicast onto both empty barriers).
-// Clusters are handed pair-tiles statically (pair = clusterid + i * nclusters, m-pair fastest so the clusters
-// running together share one W tile in L2).  The accumulator double buffer lets the epilogue of tile i overlap
-// the main loop of tile i+1.
+// CTAs run as pairs (cluster of 2 along M, tcgen05 cta_group::2): the pair owns a 256 x BN output tile, each CTA
+// fetches its own 128 x 64 A tile and HALF of the BN x 64 W tile per k-block (32 KB instead of 48 KB at BN = 256:
+// 128 flop per L2 byte instead of 85, and 6 ring stages instead of 4 -- the ring depth is what hides the ~2000-cycle
+// TMA round trip, measured with the cycle counters in GemmParams::dbg).  The leader CTA's single MMA thread issues
+// M = 256 UMMAs that read both CTAs' smem and write both CTAs' TMEM; every TMA load of the pair completes on the
+// leader's full barrier; tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs.
+// Pairs are handed tiles statically (tile = clusterid + i * nclusters, m fastest so the pairs running together share
+// one W tile in L2).  The accumulator double buffer lets the epilogue of tile i overlap the main loop of tile i+1.
 #pragma once
 #include <cuda.h>
 
@@ -42,6 +43,9 @@ struct GemmParams {
   int pix;                // EPI_F32_NCHW: pixels per image (rows per batch item)
   int up_h, up_w;         // EPI_BF16_RELU_UP: input grid
   int up_py, up_px;       // EPI_BF16_RELU_UP: sub-pixel phase
+  int stages_limit;       // debug: use at most this many ring stages (0 = all)
+  long long* dbg;         // debug: per-CTA cycle counters [8] (nullptr = off): 0 mma total, 1 mma wait full, 2 mma wait acc,
+                          //        3 producer total, 4 producer wait empty, 5 epilogue(warp 4) total, 6 epilogue wait acc_full
 };
 
 constexpr int GEMM_BM = 128;
@@ -57,8 +61,8 @@ template <int BN, int EPI>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
-  static constexpr int B_SLICE = B_BYTES / GEMM_CL;                // what one CTA fetches and multicasts
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int B_SLICE = B_BYTES / GEMM_CL;                // the half of the W tile this CTA holds
+  static constexpr int STAGE_BYTES = A_BYTES + B_SLICE;
   static constexpr int STAGING = epi_uses_tma(EPI) ? GEMM_EPI_WARPS * GEMM_STAGE_TILE : 0;
   static constexpr int STAGES_RAW = (227 * 1024 - 2048 - STAGING) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -101,6 +105,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int num_n = (p.N + BN - 1) / BN;
   const int num_pairs = num_mp * num_n;
   const int num_kb = p.K / GEMM_BK;
+  const int num_stages = (p.stages_limit > 0 && p.stages_limit < Cfg::STAGES) ? p.stages_limit : Cfg::STAGES;
   constexpr uint16_t kAllCtas = (1u << GEMM_CL) - 1;
 
   if (threadIdx.x == 0) {
@@ -108,18 +113,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tma_prefetch_desc(&tmap_w);
     if constexpr (epi_uses_tma(EPI)) tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], GEMM_CL);            // both CTAs' MMAs must have retired before a slot is refilled
+      mbar_init(&full_bar[s], 1);                   // used in the leader only: its producer arms it for BOTH CTAs' bytes
+      mbar_init(&empty_bar[s], 1);                  // one multicast tcgen05.commit per use
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], GEMM_EPI_WARPS);
+      mbar_init(&acc_empty[s], GEMM_CL * GEMM_EPI_WARPS);   // leader only: the epilogue warps of both CTAs arrive
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 2) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before_sync();
-  cluster_sync_all();                               // barriers of BOTH CTAs are live before any multicast / remote arrive
+  cluster_sync_all();                               // barriers + TMEM of BOTH CTAs are live before any remote arrive / pair MMA
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -127,33 +132,43 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
+    long long t_wait = 0;
+    const long long t_begin = clock64();
     for (int pair = cluster; pair < num_pairs; pair += num_clusters) {
       const int m0 = ((pair % num_mp) * GEMM_CL + cta_rank) * GEMM_BM;   // may lie past M: TMA zero-fills
       const int n0 = (pair / num_mp) * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
+        const long long w0 = clock64();
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        t_wait += clock64() - w0;
         uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);        // own A + both halves of W
-        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
-        tma_load_2d_mcast(sa + Cfg::A_BYTES + cta_rank * Cfg::B_SLICE, &tmap_w, &full_bar[stage], kb * GEMM_BK,
-                          n0 + cta_rank * (BN / GEMM_CL), kAllCtas);
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], GEMM_CL * Cfg::STAGE_BYTES);   // bytes of both CTAs land here
+        tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+        tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_w, &full_bar[stage], kb * GEMM_BK, n0 + cta_rank * (BN / GEMM_CL));
+        if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+    if (p.dbg) { p.dbg[blockIdx.x * 8 + 3] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 4] = t_wait; }
+  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA of the pair only)
+    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_CL * GEMM_BM, BN);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    long long t_wfull = 0, t_wacc = 0;
+    const long long t_begin = clock64();
     for (int pair = cluster; pair < num_pairs; pair += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      long long w0 = clock64();
       mbar_wait(&acc_empty[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
+      t_wacc += clock64() - w0;
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
       for (int kb = 0; kb < num_kb; ++kb) {
+        w0 = clock64();
         mbar_wait(&full_bar[stage], phase);
+        t_wfull += clock64() - w0;
         tc_fence_after_sync();
         const uint32_t sa = smem_u32(ring + stage * Cfg::STAGE_BYTES);
         const uint64_t adesc = umma_desc_sw128(sa, 1024);
@@ -161,13 +176,14 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
         for (int k = 0; k < GEMM_BK / 16; ++k) {
           // +32 B per K=16 step inside the 128-byte swizzle atom (start-address field is >>4)
-          umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
         }
-        umma_commit_mcast(&empty_bar[stage], kAllCtas);   // slot reusable in both CTAs once these MMAs retire
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        umma_commit_pair(&empty_bar[stage], kAllCtas);    // slot reusable in both CTAs once these MMAs retire
+        if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&acc_full[acc]);                    // accumulator complete -> epilogue
+      umma_commit_pair(&acc_full[acc], kAllCtas);     // accumulators complete in both CTAs -> epilogues
     }
+    if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 1] = t_wfull; p.dbg[blockIdx.x * 8 + 2] = t_wacc; }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int ew = warp - 4;
@@ -176,6 +192,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint8_t* stile = staging + ew * GEMM_STAGE_TILE;  // this warp's 32 x 128 B staging tile (TMA epilogues)
     const int sw = lane & 7;
     int it = 0;
+    long long t_wfull = 0;
+    const long long t_begin = clock64();
     for (int pair = cluster; pair < num_pairs; pair += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -183,7 +201,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int n0 = (pair / num_mp) * BN;
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < p.M;
+      const long long w0 = clock64();
       mbar_wait(&acc_full[acc], acc_phase);
+      t_wfull += clock64() - w0;
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE;
 
@@ -305,16 +325,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);   // the leader's MMA thread waits for both CTAs' epilogues
     }
     if constexpr (epi_uses_tma(EPI)) {
       if (lane == 0) tma_store_wait_all<0>();         // staging must stay alive until the last store has drained
     }
+    if (p.dbg && warp == 4 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 6] = t_wfull; }
   }
 
   tc_fence_before_sync();
-  cluster_sync_all();                                 // the peer may still multicast into / arrive on this CTA
-  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  cluster_sync_all();                                 // the peer may still read this CTA's smem / arrive on its barriers
+  if (warp == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
 }
 
 }  // namespace vpb
