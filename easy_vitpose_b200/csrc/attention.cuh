@@ -76,6 +76,8 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();                                               // qkv from the previous GEMM is complete
 
   auto load_qk = [&](int item) {
     const int b = item / p.heads, h = item % p.heads;

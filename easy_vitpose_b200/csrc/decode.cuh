@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(256) decode_heatmaps(const DecodeParams p) {
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x * 8 + wib;                       // map index n*K + k
   const int total = p.n * p.k;
+  pdl_launch_dependents();
+  pdl_wait();
   if (g >= total) return;
   const float* hm = p.heatmaps + static_cast<size_t>(g) * HM_PIX;
 

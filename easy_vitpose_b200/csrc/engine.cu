@@ -74,6 +74,37 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
   return VPB_OK;
 }
 
+// bf16 NHWC feature map [B,H,W,C] as a 4-D tensor (C, W, H, B); box = 64 channels x W x box_h rows x 1 image, 128B-swizzled:
+// the A operand of the implicit-GEMM deconv (shifted boxes, zero fill outside the map).
+static int make_map_nhwc(CUtensorMap* m, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t box_h) {
+  VPB_TRY(load_driver_api());
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(W), box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VPB_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed (%d) B=%llu H=%llu W=%llu C=%llu", (int)r,
+                                     (unsigned long long)B, (unsigned long long)H, (unsigned long long)W, (unsigned long long)C);
+  return VPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ launches
+// Every kernel of the chain is launched with programmatic stream serialization (see ptx.cuh: pdl_wait).
+static bool g_pdl = true;
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------ GEMM dispatch
 static int g_num_sms = 0;
 static bool g_attr_done = false;
@@ -90,12 +121,12 @@ static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, const CUt
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr = true;
   }
-  const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM;
-  const int pairs = ((num_m + GEMM_CL - 1) / GEMM_CL) * ((p.N + BN - 1) / BN);
+  const bool deconv = (EPI == EPI_BF16_RELU_UP);
+  const int num_m = deconv ? p.M / 96 : (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int pairs = ((num_m + GEMM_CL - 1) / GEMM_CL) * (deconv ? 4 : (p.N + BN - 1) / BN);
   const int max_clusters = g_num_sms / GEMM_CL;
   const int grid = GEMM_CL * (pairs < max_clusters ? pairs : max_clusters);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tw, tout, p);
-  CU_TRY(cudaGetLastError());
+  CU_TRY(launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, ta, tw, tout, p));
   return VPB_OK;
 }
 static int gemm_launch(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tout, const GemmParams& p,
@@ -135,9 +166,9 @@ static int device_check(int device) {
 // Optional ("profile" option): a CUDA-event pair around every launch, on the launch stream, summed per kernel
 // class by vpb_profile_collect.  bench.py uses it to report the dominant kernel's achieved FLOP/s live.
 enum KClass : int { KC_PATCH_IM2COL, KC_GEMM_PATCH, KC_LN, KC_GEMM_QKV, KC_ATTN, KC_GEMM_PROJ, KC_GEMM_FC1, KC_GEMM_FC2,
-                    KC_DECONV_IM2COL, KC_GEMM_DECONV, KC_GEMM_FINAL, KC_DECODE, KC_COUNT };
+                    KC_GEMM_DECONV, KC_GEMM_FINAL, KC_DECODE, KC_COUNT };
 static const char* kclass_names[KC_COUNT] = {"patch_im2col", "gemm_patch_embed", "layernorm", "gemm_qkv", "attention", "gemm_proj",
-                                             "gemm_fc1_gelu", "gemm_fc2", "deconv_im2col", "gemm_deconv", "gemm_final_conv", "decode"};
+                                             "gemm_fc1_gelu", "gemm_fc2", "gemm_deconv", "gemm_final_conv", "decode"};
 struct ProfRec { int cls; cudaEvent_t a, b; };
 struct Profiler {
   bool on = false;
@@ -181,12 +212,13 @@ struct vpb_engine {
   float* pos_bias = nullptr;   // [192, D]
   std::vector<BlockW> blocks;
   float *lnf_g = nullptr, *lnf_b = nullptr;
-  LinearW dc1[4], dc2[4], fin;
+  LinearW dc1, dc2, fin;            // dc*: the 4 phase matrices stacked [4*256, 4*Cin]
   // workspace
-  __nv_bfloat16 *patch_rows, *xn, *qkv, *attn, *hid, *col1, *d1, *col2, *d2;
-  float *x, *heat, *kpts;
+  __nv_bfloat16 *patch_rows, *xn, *qkv, *attn, *hid, *d1, *d2;
+  float *x, *heat, *kpts, *crops_stage;   // crops_stage: device landing buffer of vpb_infer_host
   int32_t *idx, *org_wh;
-  CUtensorMap m_patch_rows, m_xn, m_attn, m_hid, m_col1[4], m_col2[4], m_d2, m_qkv_att;   // A operands / attention boxes
+  CUtensorMap m_patch_rows, m_xn, m_attn, m_hid, m_d2, m_qkv_att;   // A operands / attention boxes
+  CUtensorMap m_feat_nhwc, m_d1_nhwc;                                 // implicit-GEMM deconv inputs (4-D)
   CUtensorMap o_qkv, o_hid, o_x;                                                             // TMA-epilogue outputs
 };
 
@@ -331,21 +363,18 @@ extern "C" int vpb_finalize(vpb_engine* e) {
   // deconv layers: 4 phase matrices [256, 4*Cin] each, BN folded (eps 1e-5 = nn.BatchNorm2d default)
   int cin = D;
   for (int layer = 0; layer < 2; ++layer) {
-    LinearW* dc = layer == 0 ? e->dc1 : e->dc2;
+    LinearW& dc = layer == 0 ? e->dc1 : e->dc2;
     const std::string wk = "keypoint_head.deconv_layers." + std::to_string(layer * 3) + ".weight";
     const std::string bnp = "keypoint_head.deconv_layers." + std::to_string(layer * 3 + 1) + ".";
-    __nv_bfloat16* wp; float* shift;
-    VPB_TRY(dev_alloc(e, &wp, static_cast<size_t>(4) * 256 * 4 * cin));
-    VPB_TRY(dev_alloc(e, &shift, 256));
+    VPB_TRY(dev_alloc(e, &dc.w, static_cast<size_t>(4) * 256 * 4 * cin));
+    VPB_TRY(dev_alloc(e, &dc.b, 256));
     const long long tot = 4LL * 256 * 4 * cin;
     pack_deconv<<<cdiv(tot, 256), 256>>>(e->staged[wk].first, e->staged[bnp + "weight"].first, e->staged[bnp + "bias"].first,
-                                         e->staged[bnp + "running_mean"].first, e->staged[bnp + "running_var"].first, wp, shift,
+                                         e->staged[bnp + "running_mean"].first, e->staged[bnp + "running_var"].first, dc.w, dc.b,
                                          cin, 256, 1e-5f);
     CU_TRY(cudaGetLastError());
-    for (int ph = 0; ph < 4; ++ph) {
-      dc[ph].w = wp + static_cast<size_t>(ph) * 256 * 4 * cin; dc[ph].b = shift; dc[ph].n = 256; dc[ph].k = 4 * cin; dc[ph].bn = 256;
-      VPB_TRY(make_map(&dc[ph].map, dc[ph].w, 256, 4 * cin, 4 * cin, 256 / GEMM_CL));
-    }
+    dc.n = 256; dc.k = 4 * cin; dc.bn = 256;
+    VPB_TRY(make_map(&dc.map, dc.w, 4 * 256, 4 * cin, 4 * cin, 256 / GEMM_CL));
     cin = 256;
   }
   {  // final 1x1 conv: [K,256] zero-padded to the N tile
@@ -360,22 +389,19 @@ extern "C" int vpb_finalize(vpb_engine* e) {
   VPB_TRY(dev_alloc(e, &e->qkv, M * 3 * D));
   VPB_TRY(dev_alloc(e, &e->attn, M * D));
   VPB_TRY(dev_alloc(e, &e->hid, M * 4 * D));
-  VPB_TRY(dev_alloc(e, &e->col1, 4 * M * 4 * D));
   VPB_TRY(dev_alloc(e, &e->d1, B * 768 * 256));
-  VPB_TRY(dev_alloc(e, &e->col2, 4 * B * 768 * 1024));
   VPB_TRY(dev_alloc(e, &e->d2, B * 3072 * 256));
   VPB_TRY(dev_alloc(e, &e->heat, B * e->K * 3072));
   VPB_TRY(dev_alloc(e, &e->kpts, B * e->K * 3));
   VPB_TRY(dev_alloc(e, &e->idx, B * e->K));
   VPB_TRY(dev_alloc(e, &e->org_wh, B * 2));
+  VPB_TRY(dev_alloc(e, &e->crops_stage, B * 3 * 256 * 192));
   VPB_TRY(make_map(&e->m_patch_rows, e->patch_rows, M, 768, 768, 128));
   VPB_TRY(make_map(&e->m_xn, e->xn, M, D, D, 128));
   VPB_TRY(make_map(&e->m_attn, e->attn, M, D, D, 128));
   VPB_TRY(make_map(&e->m_hid, e->hid, M, 4 * D, 4 * D, 128));
-  for (int ph = 0; ph < 4; ++ph) {
-    VPB_TRY(make_map(&e->m_col1[ph], e->col1 + ph * M * 4 * D, M, 4 * D, 4 * D, 128));
-    VPB_TRY(make_map(&e->m_col2[ph], e->col2 + ph * B * 768 * 1024, B * 768, 1024, 1024, 128));
-  }
+  VPB_TRY(make_map_nhwc(&e->m_feat_nhwc, e->xn, B, 16, 12, D, 8));     // 8 rows x 12 = 96 positions per M tile
+  VPB_TRY(make_map_nhwc(&e->m_d1_nhwc, e->d1, B, 32, 24, 256, 4));    // 4 rows x 24 = 96 positions per M tile
   VPB_TRY(make_map(&e->m_d2, e->d2, B * 3072, 256, 256, 128));
   VPB_TRY(make_map(&e->m_qkv_att, e->qkv, M, 3 * D, 3 * D, 192));
   VPB_TRY(make_map(&e->o_qkv, e->qkv, M, 3 * D, 3 * D, 32));
@@ -391,7 +417,7 @@ extern "C" int vpb_finalize(vpb_engine* e) {
 // ------------------------------------------------------------------------------------------------ forward
 template <int D>
 static void ln_launch(const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, float eps, cudaStream_t st) {
-  layernorm_f32_to_bf16<D><<<cdiv(rows, 8), 256, 0, st>>>(x, g, b, y, rows, eps);
+  launch_k(layernorm_f32_to_bf16<D>, dim3(cdiv(rows, 8)), dim3(256), 0, st, x, g, b, y, rows, eps);
 }
 static int layernorm(const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, int D, float eps, cudaStream_t st) {
   switch (D) {
@@ -426,7 +452,7 @@ static int backbone(vpb_engine* e, const float* d_crops, int B, cudaStream_t st)
   const int D = e->D, M = B * 192;
   const int stop = e->stop_after;
   e->prof.begin(KC_PATCH_IM2COL, st);
-  patch_im2col<<<cdiv(static_cast<long long>(B) * 3 * 256 * 24, 256), 256, 0, st>>>(d_crops, e->patch_rows, B);
+  launch_k(patch_im2col, dim3(cdiv(static_cast<long long>(B) * 3 * 256 * 24, 256)), dim3(256), 0, st, d_crops, e->patch_rows, B);
   e->prof.end(st);
   CU_TRY(cudaGetLastError());
   if (stop == 1) return VPB_OK;
@@ -453,7 +479,7 @@ static int backbone(vpb_engine* e, const float* d_crops, int B, cudaStream_t st)
       ap.batch = B; ap.heads = e->heads; ap.dim = D; ap.out = e->attn; ap.qkv = e->qkv; ap.v_manual = e->attn_v_manual;
       const int items = B * e->heads;
       e->prof.begin(KC_ATTN, st);
-      attention_tcgen05<<<items < g_num_sms ? items : g_num_sms, ATT_THREADS, ATT_SMEM, st>>>(e->m_qkv_att, ap);
+      launch_k(attention_tcgen05, dim3(items < g_num_sms ? items : g_num_sms), dim3(ATT_THREADS), ATT_SMEM, st, e->m_qkv_att, ap);
       e->prof.end(st);
       CU_TRY(cudaGetLastError());
     }
@@ -490,37 +516,20 @@ static int backbone(vpb_engine* e, const float* d_crops, int B, cudaStream_t st)
 static int head(vpb_engine* e, int B, float* d_heat, cudaStream_t st) {
   const int D = e->D;
   const int stop = e->stop_after;
-  // deconv 1: tokens (NHWC 16x12xD) -> d1 (NHWC 32x24x256)
-  {
-    const int M = B * 192;
-    const long long tot = static_cast<long long>(M) * 4 * (D / 8);
-    e->prof.begin(KC_DECONV_IM2COL, st);
-    deconv_phase_im2col<<<dim3(cdiv(tot, 256), 4), 256, 0, st>>>(e->xn, e->col1, B, 16, 12, D, static_cast<size_t>(e->maxB) * 192 * 4 * D);
+  {  // deconv 1: tokens as NHWC 16x12xD -> d1 NHWC 32x24x256, all four sub-pixel phases in one implicit-GEMM launch
+    GemmParams p = gp(B * 192, 256, 4 * D, e->dc1.b, e->d1, 256);
+    p.up_h = 16; p.up_w = 12; p.up_tr = 8; p.up_c = D;
+    e->prof.begin(KC_GEMM_DECONV, st);
+    VPB_TRY(gemm_launch(256, EPI_BF16_RELU_UP, e->m_feat_nhwc, e->dc1.map, e->m_xn, p, st));
     e->prof.end(st);
-    CU_TRY(cudaGetLastError());
-    for (int ph = 0; ph < 4; ++ph) {
-      GemmParams p = gp(M, 256, 4 * D, e->dc1[ph].b, e->d1, 256);
-      p.up_h = 16; p.up_w = 12; p.up_py = ph >> 1; p.up_px = ph & 1;
-      e->prof.begin(KC_GEMM_DECONV, st);
-      VPB_TRY(gemm_launch(256, EPI_BF16_RELU_UP, e->m_col1[ph], e->dc1[ph].map, e->m_col1[ph], p, st));
-      e->prof.end(st);
-    }
   }
   if (stop == 11) return VPB_OK;
-  {
-    const int M = B * 768;
-    const long long tot = static_cast<long long>(M) * 4 * (256 / 8);
-    e->prof.begin(KC_DECONV_IM2COL, st);
-    deconv_phase_im2col<<<dim3(cdiv(tot, 256), 4), 256, 0, st>>>(e->d1, e->col2, B, 32, 24, 256, static_cast<size_t>(e->maxB) * 768 * 1024);
+  {  // deconv 2: d1 -> d2 NHWC 64x48x256
+    GemmParams p = gp(B * 768, 256, 1024, e->dc2.b, e->d2, 256);
+    p.up_h = 32; p.up_w = 24; p.up_tr = 4; p.up_c = 256;
+    e->prof.begin(KC_GEMM_DECONV, st);
+    VPB_TRY(gemm_launch(256, EPI_BF16_RELU_UP, e->m_d1_nhwc, e->dc2.map, e->m_xn, p, st));
     e->prof.end(st);
-    CU_TRY(cudaGetLastError());
-    for (int ph = 0; ph < 4; ++ph) {
-      GemmParams p = gp(M, 256, 1024, e->dc2[ph].b, e->d2, 256);
-      p.up_h = 32; p.up_w = 24; p.up_py = ph >> 1; p.up_px = ph & 1;
-      e->prof.begin(KC_GEMM_DECONV, st);
-      VPB_TRY(gemm_launch(256, EPI_BF16_RELU_UP, e->m_col2[ph], e->dc2[ph].map, e->m_col2[ph], p, st));
-      e->prof.end(st);
-    }
   }
   if (stop == 12) return VPB_OK;
   {
@@ -567,7 +576,7 @@ extern "C" int vpb_decode(const float* d_heatmaps, int32_t n, int32_t k, const i
   if (n == 0) return VPB_OK;
   DecodeParams p;
   p.heatmaps = d_heatmaps; p.org_wh = d_org_wh; p.kpts = d_kpts; p.idx = d_idx; p.n = n; p.k = k; p.wrap_batch = wrap_batch;
-  decode_heatmaps<<<cdiv(static_cast<long long>(n) * k, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  launch_k(decode_heatmaps, dim3(cdiv(static_cast<long long>(n) * k, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   CU_TRY(cudaGetLastError());
   return VPB_OK;
 }
@@ -590,9 +599,7 @@ extern "C" int vpb_infer_host(vpb_engine* e, const float* h_crops, const int32_t
   VPB_TRY(check_ready(e, batch));
   if (!h_crops || !h_org_wh || !h_kpts) return fail(VPB_ERR_ARG, "vpb_infer_host: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // the crop staging buffer aliases the im2col scratch of deconv 2 (unused until the head runs, and the
-  // patch gather has consumed the crops long before): [B,3,256,192] f32 = 589 824 B/crop <= 4*768*1024*2 B/crop
-  float* d_crops = reinterpret_cast<float*>(e->col2);
+  float* d_crops = e->crops_stage;
   CU_TRY(cudaMemcpyAsync(d_crops, h_crops, static_cast<size_t>(batch) * 3 * 256 * 192 * sizeof(float), cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(e->org_wh, h_org_wh, static_cast<size_t>(batch) * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   VPB_TRY(vpb_infer(e, d_crops, e->org_wh, batch, e->kpts, e->idx, nullptr, st));
@@ -613,8 +620,8 @@ extern "C" void vpb_host_free(void* p) {
 
 extern "C" int vpb_kernel_launches(const vpb_engine* e, int32_t) {
   if (!e) return -1;
-  // patch im2col + patch GEMM + depth*(LN, qkv, attention, proj, LN, fc1, fc2) + LN + 2*(im2col + 4 GEMM) + 1x1 GEMM + decode
-  return 2 + e->depth * 7 + 1 + 2 * 5 + 1 + 1;
+  // patch im2col + patch GEMM + depth*(LN, qkv, attention, proj, LN, fc1, fc2) + LN + 2 deconv GEMMs + 1x1 GEMM + decode
+  return 2 + e->depth * 7 + 1 + 2 + 1 + 1;
 }
 
 extern "C" int vpb_set_option(vpb_engine* e, const char* name, int32_t value) {
@@ -622,6 +629,7 @@ extern "C" int vpb_set_option(vpb_engine* e, const char* name, int32_t value) {
   if (!strcmp(name, "stop_after")) e->stop_after = value;
   else if (!strcmp(name, "attn_v_manual")) e->attn_v_manual = value;
   else if (!strcmp(name, "profile")) e->prof.on = value != 0;
+  else if (!strcmp(name, "pdl")) g_pdl = value != 0;
   else return fail(VPB_ERR_ARG, "unknown option %s", name);
   return VPB_OK;
 }
@@ -678,15 +686,23 @@ extern "C" int vpb_gemm(const void* d_a, const void* d_w, const float* d_bias, v
   if (epilogue != EPI_F32_NCHW && n % bn != 0) return fail(VPB_ERR_ARG, "vpb_gemm: N=%d must be a multiple of %d", n, bn);
   if (epilogue == EPI_F32_NCHW && n != bn) return fail(VPB_ERR_ARG, "vpb_gemm: NCHW epilogue wants W padded to %d rows", bn);
   CUtensorMap ta, tw, tout;
-  VPB_TRY(make_map(&ta, d_a, m, k, k, 128));
-  VPB_TRY(make_map(&tw, d_w, n, k, k, bn / GEMM_CL));
-  tout = ta;
+  if (epilogue == EPI_BF16_RELU_UP) {
+    // d_a: NHWC input [m / (H*W), H, W, C] with H = aux0, W = aux1, rows per tile aux2 (W * aux2 == 96), C = aux3 = k / 4;
+    // d_w: the four phase matrices stacked [4*256, 4*C]
+    if (aux1 * aux2 != 96 || aux3 * 4 != k || aux0 % aux2 != 0 || m % (aux0 * aux1) != 0) return fail(VPB_ERR_ARG, "vpb_gemm: bad deconv geometry");
+    VPB_TRY(make_map_nhwc(&ta, d_a, m / (aux0 * aux1), aux0, aux1, aux3, aux2));
+    VPB_TRY(make_map(&tw, d_w, 4 * n, k, k, bn / GEMM_CL));
+  } else {
+    VPB_TRY(make_map(&ta, d_a, m, k, k, 128));
+    VPB_TRY(make_map(&tw, d_w, n, k, k, bn / GEMM_CL));
+  }
+  VPB_TRY(make_map(&tout, d_w, n, k, k, bn / GEMM_CL));   // placeholder for direct epilogues
   if (epilogue == EPI_BF16 || epilogue == EPI_BF16_GELU) VPB_TRY(make_map(&tout, d_out, m, n, n, 32));
   if (epilogue == EPI_F32_ADD) VPB_TRY(make_map(&tout, d_out, m, n, n, 32, /*f32=*/true));
   GemmParams p = gp(m, n, k, d_bias, d_out, n);
   p.resid = d_resid; p.resid_mod = resid_mod;
   if (epilogue == EPI_F32_NCHW) { p.n_valid = aux0; p.pix = aux1; }
-  if (epilogue == EPI_BF16_RELU_UP) { p.up_h = aux0; p.up_w = aux1; p.up_py = aux2; p.up_px = aux3; }
+  if (epilogue == EPI_BF16_RELU_UP) { p.up_h = aux0; p.up_w = aux1; p.up_tr = aux2; p.up_c = aux3; }
   return gemm_launch(bn, epilogue, ta, tw, tout, p, static_cast<cudaStream_t>(stream));
 }
 
@@ -702,7 +718,7 @@ extern "C" int vpb_attention(const void* d_qkv, int32_t batch, int32_t heads, vo
   ap.batch = batch; ap.heads = heads; ap.dim = D; ap.out = reinterpret_cast<__nv_bfloat16*>(d_out);
   ap.qkv = reinterpret_cast<const __nv_bfloat16*>(d_qkv); ap.v_manual = v_manual;
   const int items = batch * heads;
-  attention_tcgen05<<<items < g_num_sms ? items : g_num_sms, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(tq, ap);
+  launch_k(attention_tcgen05, dim3(items < g_num_sms ? items : g_num_sms), dim3(ATT_THREADS), ATT_SMEM, static_cast<cudaStream_t>(stream), tq, ap);
   CU_TRY(cudaGetLastError());
   return VPB_OK;
 }

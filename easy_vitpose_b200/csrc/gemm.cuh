@@ -1,10 +1,11 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T  (+ fused epilogue)
 //
-//   warp 0 (1 thread)  TMA producer: A / W tiles -> 128B-swizzled smem ring, mbarrier full/empty
-//   warp 1 (1 thread)  tcgen05.mma issuer (leader CTA): 256 x BN x 16 pair-UMMAs, fp32 accumulators in TMEM (2 stages)
-//   warp 2             TMEM allocator
-//   warps 4..11        epilogue: tcgen05.ld -> registers -> bias / GELU / ReLU -> swizzled smem staging ->
+//   warps 0..7         epilogue: tcgen05.ld -> registers -> bias / GELU / ReLU -> swizzled smem staging ->
 //                      TMA store (bf16) or TMA reduce-add (fp32 residual, the add happens in L2)
+//   warp 8             TMEM allocator
+//   warp 10 (1 thread) TMA producer: A / W tiles -> 128B-swizzled smem ring, mbarrier full/empty
+//   warp 11 (1 thread) tcgen05.mma issuer (leader CTA): 256 x BN x 16 pair-UMMAs, fp32 accumulators in TMEM (2 stages)
+// (the warp scheduler favours high warp ids: the two single-thread roles must never queue behind epilogue math)
 //
 // Both operands are K-major (nn.Linear keeps W as [N,K]), so no transposes anywhere.
 //
@@ -26,7 +27,8 @@ namespace vpb {
 enum Epilogue : int {
   EPI_BF16 = 0,         // out bf16 [M,ldc]   = acc + bias                              (qkv)            TMA store
   EPI_BF16_GELU = 1,    // out bf16 [M,ldc]   = gelu_erf(acc + bias)                    (fc1)            TMA store
-  EPI_BF16_RELU_UP = 2, // out bf16 NHWC, row (b,y,x) -> (b,2y+py,2x+px), relu(acc+bias) (deconv phase)   direct
+  EPI_BF16_RELU_UP = 2, // implicit-GEMM deconv: A = shifted NHWC boxes (4-D TMA), all 4 sub-pixel phases in one launch,
+                        // out bf16 NHWC (b,2y+py,2x+px) = relu(acc + bias)                                direct
   EPI_F32_RESID = 3,    // out f32 [M,ldc]    = resid[row % mod] + acc + bias           (patch embed)    direct
   EPI_F32_NCHW = 4,     // out f32 [b,n,pix]  = acc + bias for n < n_valid              (1x1 conv)       direct
   EPI_F32_ADD = 5,      // out f32 [M,ldc]   += acc + bias                              (proj, fc2)      TMA reduce-add
@@ -41,8 +43,9 @@ struct GemmParams {
   int resid_mod;          // 0: resid row = row; >0: resid row = row % resid_mod (position embedding)
   int n_valid;            // EPI_F32_NCHW: number of real output channels
   int pix;                // EPI_F32_NCHW: pixels per image (rows per batch item)
-  int up_h, up_w;         // EPI_BF16_RELU_UP: input grid
-  int up_py, up_px;       // EPI_BF16_RELU_UP: sub-pixel phase
+  int up_h, up_w;         // EPI_BF16_RELU_UP: input grid (H, W); W * up_tr == 96 rows per M tile
+  int up_tr;              // EPI_BF16_RELU_UP: image rows per M tile
+  int up_c;               // EPI_BF16_RELU_UP: input channels (K = 4 taps * up_c)
   int stages_limit;       // debug: use at most this many ring stages (0 = all)
   long long* dbg;         // debug: per-CTA cycle counters [8] (nullptr = off): 0 mma total, 1 mma wait full, 2 mma wait acc,
                           //        3 producer total, 4 producer wait empty, 5 epilogue(warp 4) total, 6 epilogue wait acc_full
@@ -100,14 +103,21 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int cta_rank = static_cast<int>(cluster_ctarank());
   const int cluster = static_cast<int>(cluster_id_x());
   const int num_clusters = static_cast<int>(cluster_count_x());
-  const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  constexpr bool kDeconv = (EPI == EPI_BF16_RELU_UP);
+  // deconv: an M tile is up_tr image rows (96 positions) of one crop, p.M counts positions; the 4 phases play the n-blocks
+  const int num_m = kDeconv ? p.M / 96 : (p.M + GEMM_BM - 1) / GEMM_BM;
   const int num_mp = (num_m + GEMM_CL - 1) / GEMM_CL;               // m-block pairs
-  const int num_n = (p.N + BN - 1) / BN;
+  const int num_n = kDeconv ? 4 : (p.N + BN - 1) / BN;
   const int num_pairs = num_mp * num_n;
   const int num_kb = p.K / GEMM_BK;
   const int num_stages = (p.stages_limit > 0 && p.stages_limit < Cfg::STAGES) ? p.stages_limit : Cfg::STAGES;
   constexpr uint16_t kAllCtas = (1u << GEMM_CL) - 1;
 
+  long long t_cta0 = 0, t_ns0 = 0;
+  if (p.dbg && threadIdx.x == 0) {
+    t_cta0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ns0));
+  }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
@@ -122,34 +132,52 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == 8) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before_sync();
   cluster_sync_all();                               // barriers + TMEM of BOTH CTAs are live before any remote arrive / pair MMA
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();                          // the next kernel may start its prologue as SMs free up
+  pdl_wait();                                       // previous kernel's outputs (our A operand / residual) are complete
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 10 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
     long long t_wait = 0;
     const long long t_begin = clock64();
     for (int pair = cluster; pair < num_pairs; pair += num_clusters) {
-      const int m0 = ((pair % num_mp) * GEMM_CL + cta_rank) * GEMM_BM;   // may lie past M: TMA zero-fills
-      const int n0 = (pair / num_mp) * BN;
+      const int mt = (pair % num_mp) * GEMM_CL + cta_rank;               // this CTA's M tile
+      const int m0 = mt * GEMM_BM;                                       // may lie past M: TMA zero-fills
+      const int nb = pair / num_mp;                                      // n-block (deconv: sub-pixel phase)
+      const int n0 = nb * BN;
+      const int tiles_per_img = kDeconv ? p.up_h / p.up_tr : 1;
+      const int kb_per_tap = kDeconv ? p.up_c / GEMM_BK : 1;
       for (int kb = 0; kb < num_kb; ++kb) {
         const long long w0 = clock64();
         mbar_wait(&empty_bar[stage], phase ^ 1);
         t_wait += clock64() - w0;
         uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
-        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], GEMM_CL * Cfg::STAGE_BYTES);   // bytes of both CTAs land here
-        tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+        if constexpr (kDeconv) {
+          // A tile = 96 positions (up_tr rows x W) of the input map shifted by the tap's (dy, dx); the 4-D box is zero
+          // filled outside the map (= the transposed conv's border).  Rows 96..127 of the smem tile are never written:
+          // they only feed accumulator rows nobody stores.
+          const int tap = kb / kb_per_tap, c0 = (kb % kb_per_tap) * GEMM_BK;
+          const int py = nb >> 1, px = nb & 1, iy = tap >> 1, ix = tap & 1;
+          const int dy = py ? (iy ? 0 : 1) : (iy ? -1 : 0);
+          const int dx = px ? (ix ? 0 : 1) : (ix ? -1 : 0);
+          if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], GEMM_CL * (96 * 128 + Cfg::B_SLICE));
+          tma_load_4d_pair(sa, &tmap_a, &full_bar[stage], c0, dx, (mt % tiles_per_img) * p.up_tr + dy, mt / tiles_per_img);
+        } else {
+          if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], GEMM_CL * Cfg::STAGE_BYTES);   // bytes of both CTAs land here
+          tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+        }
         tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_w, &full_bar[stage], kb * GEMM_BK, n0 + cta_rank * (BN / GEMM_CL));
         if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
     }
     if (p.dbg) { p.dbg[blockIdx.x * 8 + 3] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 4] = t_wait; }
-  } else if (warp == 1 && lane == 0 && cta_rank == 0) {
+  } else if (warp == 11 && lane == 0 && cta_rank == 0) {
     // ------------------------------------------------------------ MMA issuer (leader CTA of the pair only)
     constexpr uint32_t idesc = umma_idesc_bf16(GEMM_CL * GEMM_BM, BN);
     int stage = 0;
@@ -184,9 +212,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       umma_commit_pair(&acc_full[acc], kAllCtas);     // accumulators complete in both CTAs -> epilogues
     }
     if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 1] = t_wfull; p.dbg[blockIdx.x * 8 + 2] = t_wacc; }
-  } else if (warp >= 4) {
+  } else if (warp < GEMM_EPI_WARPS) {
     // ------------------------------------------------------------ epilogue
-    const int ew = warp - 4;
+    const int ew = warp;
     const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
     const int half = ew >> 2;                         // which half of the BN columns
     uint8_t* stile = staging + ew * GEMM_STAGE_TILE;  // this warp's 32 x 128 B staging tile (TMA epilogues)
@@ -197,10 +225,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int pair = cluster; pair < num_pairs; pair += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = ((pair % num_mp) * GEMM_CL + cta_rank) * GEMM_BM;
-      const int n0 = (pair / num_mp) * BN;
+      const int mt = (pair % num_mp) * GEMM_CL + cta_rank;
+      const int m0 = mt * GEMM_BM;
+      const int nb = pair / num_mp;
+      const int n0 = kDeconv ? 0 : nb * BN;
       const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      const bool row_ok = kDeconv ? (quarter * 32 + lane < 96 && mt < num_m) : (row < p.M);
       const long long w0 = clock64();
       mbar_wait(&acc_full[acc], acc_phase);
       t_wfull += clock64() - w0;
@@ -260,10 +290,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // ---- direct epilogues (scattered / transposed outputs)
         size_t out_row = static_cast<size_t>(row);
         if constexpr (EPI == EPI_BF16_RELU_UP) {
-          const int hw = p.up_h * p.up_w;
-          const int b = row / hw, r = row % hw;
-          const int y = r / p.up_w, x = r % p.up_w;
-          out_row = (static_cast<size_t>(b) * (2 * p.up_h) + (2 * y + p.up_py)) * (2 * p.up_w) + (2 * x + p.up_px);
+          const int tiles_per_img = p.up_h / p.up_tr;
+          const int r = quarter * 32 + lane;                              // position inside the tile (valid < 96)
+          const int b = mt / tiles_per_img;
+          const int y = (mt % tiles_per_img) * p.up_tr + r / p.up_w, x = r % p.up_w;
+          out_row = (static_cast<size_t>(b) * (2 * p.up_h) + (2 * y + (nb >> 1))) * (2 * p.up_w) + (2 * x + (nb & 1));
         }
         size_t res_row = static_cast<size_t>(row);
         if constexpr (EPI == EPI_F32_RESID) {
@@ -330,12 +361,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if constexpr (epi_uses_tma(EPI)) {
       if (lane == 0) tma_store_wait_all<0>();         // staging must stay alive until the last store has drained
     }
-    if (p.dbg && warp == 4 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 6] = t_wfull; }
+    if (p.dbg && warp == 0 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 6] = t_wfull; }
   }
 
   tc_fence_before_sync();
   cluster_sync_all();                                 // the peer may still read this CTA's smem / arrive on its barriers
-  if (warp == 2) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+  if (warp == 8) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+  if (p.dbg && threadIdx.x == 0) {                    // CTA lifetime in SM cycles, and (odd CTAs, slot 0) in nanoseconds
+    long long t_ns1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ns1));
+    p.dbg[blockIdx.x * 8 + 7] = clock64() - t_cta0;
+    if (cta_rank == 1) p.dbg[blockIdx.x * 8 + 0] = t_ns1 - t_ns0;
+  }
 }
 
 }  // namespace vpb

@@ -1,5 +1,5 @@
-// HBM/L2-bound helper kernels around the tensor-core GEMMs: LayerNorm, the two im2col gathers
-// (patch embedding, deconv sub-pixel phases) and the one-time weight packing.  All of them move
+// HBM/L2-bound helper kernels around the tensor-core GEMMs: LayerNorm, the patch-embedding im2col gather
+// and the one-time weight packing (the deconvs need no gather: gemm.cuh reads shifted NHWC boxes by 4-D TMA).  All of them move
 // 16 bytes per thread per access and keep a warp on consecutive addresses.
 #pragma once
 #include "ptx.cuh"
@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(256) layernorm_f32_to_bf16(const float* __rest
   constexpr int V = D / 128;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
   float4 v[V];
@@ -59,6 +61,8 @@ __global__ void __launch_bounds__(256) layernorm_f32_to_bf16(const float* __rest
 __global__ void __launch_bounds__(256) patch_im2col(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int batch) {
   const int total = batch * 3 * 256 * 24;                  // (b, c, y', xchunk)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();            // the previous step may still be reading patch rows through its first GEMM
   if (i >= total) return;
   const int xc = i % 24;
   const int yp = (i / 24) % 256;                           // y' = 16*py + ky
@@ -90,36 +94,6 @@ __global__ void __launch_bounds__(256) patch_im2col(const float* __restrict__ x,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Deconv sub-pixel im2col.  ConvTranspose2d(k4,s2,p1) = 4 phases (py,px); output (2m+py, 2n+px) sums
-// 2x2 taps of the input (head/topdown_heatmap_simple_head.py:305-313):
-//   T(0) = {(ky=1,dy=0),(ky=3,dy=-1)}   T(1) = {(ky=0,dy=+1),(ky=2,dy=0)}        (same along x)
-// in  bf16 NHWC [B,H,W,C];  out[phase] bf16 [B*H*W, 4C], col = (iy*2+ix)*C + ci  =  in[b, m+dy, n+dx, ci]
-// blockIdx.y = phase (matrices `phase_stride` elements apart).  One thread = 8 channels (16 B).
-__global__ void __launch_bounds__(256) deconv_phase_im2col(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                                           int batch, int H, int W, int C, size_t phase_stride) {
-  const int phase = blockIdx.y, py = phase >> 1, px = phase & 1;
-  const int cv = C / 8;
-  const long long total = static_cast<long long>(batch) * H * W * 4 * cv;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = static_cast<int>(i % cv);
-  const int tap = static_cast<int>((i / cv) % 4);
-  const long long pos = i / (4 * cv);                       // (b, m, n)
-  const int n = static_cast<int>(pos % W);
-  const int m = static_cast<int>((pos / W) % H);
-  const int b = static_cast<int>(pos / (static_cast<long long>(W) * H));
-  const int iy = tap >> 1, ix = tap & 1;
-  const int dy = py ? (iy ? 0 : 1) : (iy ? -1 : 0);
-  const int dx = px ? (ix ? 0 : 1) : (ix ? -1 : 0);
-  const int yy = m + dy, xx = n + dx;
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-    v = *reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * H + yy) * W + xx) * C + c8 * 8);
-  __nv_bfloat16* dst = out + static_cast<size_t>(phase) * phase_stride;   // elements between phase matrices
-  *reinterpret_cast<uint4*>(dst + static_cast<size_t>(pos) * 4 * C + tap * C + c8 * 8) = v;
-}
-
-// ------------------------------------------------------------------------------------------------
 // One-time weight packing (fp32 state_dict tensors already on the device -> bf16 / folded fp32).
 // Linear weight [N,K] f32 -> bf16, rows < scaled_rows multiplied by `scale` in fp32 first
 // (the q rows of attn.qkv get head_dim^-0.5: vit.py:170 scales q before QK^T).
@@ -143,8 +117,11 @@ __global__ void pack_pos_bias(const float* __restrict__ pos, const float* __rest
   const int t = i / D, d = i % D;
   out[i] = pos[(1 + t) * D + d] + pos[d] + pbias[d];
 }
-// ConvTranspose2d weight [Cin,Cout,4,4] + eval BatchNorm -> 4 phase matrices bf16 [Cout, 4*Cin] with the
-// BN scale folded into the rows, and the BN shift as bias (SURVEY.md 9.4).
+// ConvTranspose2d(k4,s2,p1) = 4 sub-pixel phases (py,px); output (2m+py, 2n+px) sums 2x2 taps of the input
+// (head/topdown_heatmap_simple_head.py:305-313):
+//   T(0) = {(ky=1,dy=0),(ky=3,dy=-1)}   T(1) = {(ky=0,dy=+1),(ky=2,dy=0)}        (same along x)
+// weight [Cin,Cout,4,4] + eval BatchNorm -> 4 phase matrices bf16 [Cout, 4*Cin] (tap-major K) with the
+// BN scale folded into the rows, and the BN shift as bias.
 //   Wp[phase][co][(iy*2+ix)*Cin + ci] = W[ci][co][ky(py,iy)][kx(px,ix)] * gamma[co]/sqrt(var[co]+eps)
 __global__ void pack_deconv(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
                             const float* __restrict__ mean, const float* __restrict__ var, __nv_bfloat16* __restrict__ wp,

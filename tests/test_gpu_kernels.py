@@ -126,20 +126,47 @@ def test_gemm_residual_inplace_and_posmod():
     assert _rel(out, ref2) < 2e-3
 
 
-def test_gemm_deconv_phase_scatter_relu():
+@pytest.mark.parametrize("B,H,W,C,TR", [(3, 16, 12, 768, 8), (2, 32, 24, 256, 4), (5, 16, 12, 384, 8)])
+def test_gemm_implicit_deconv_bn_relu(B, H, W, C, TR):
+    """ConvTranspose2d(k4,s2,p1) + eval BatchNorm + ReLU as ONE implicit-GEMM launch (4 phases, shifted 4-D TMA boxes)
+    against torch's conv_transpose2d on the same bf16-rounded operands."""
     from gpu_util import EPI_BF16_RELU_UP, gemm
-    torch.manual_seed(3)
-    B, H, W, K = 3, 16, 12, 1024
-    M = B * H * W
-    a = (torch.randn(M, K, device=_dev()) * 0.5).bfloat16()
-    w = (torch.randn(256, K, device=_dev()) * 0.05).bfloat16()
-    bias = torch.randn(256, device=_dev())
-    out = torch.full((B, 2 * H, 2 * W, 256), -7.0, dtype=torch.bfloat16, device=_dev())
-    gemm(a, w, bias, out, EPI_BF16_RELU_UP, aux=(H, W, 1, 0))
-    ref = torch.relu(a.float() @ w.float().T + bias).reshape(B, H, W, 256)
-    got = out[:, 1::2, 0::2].float()
-    assert _rel(got, ref) < 1e-2
-    assert float(out[:, 0::2].float().max()) == -7.0                 # other phases untouched
+    torch.manual_seed(B * H + C)
+    dev = _dev()
+    x = (torch.randn(B, H, W, C, device=dev) * 0.5).bfloat16()                      # NHWC
+    w = torch.randn(C, 256, 4, 4, device=dev) / (C ** 0.5)
+    scale = torch.rand(256, device=dev) + 0.5
+    shift = torch.randn(256, device=dev) * 0.2
+    wp = torch.empty(4, 256, 4, C, device=dev)                                      # [phase, co, tap, ci]
+    for py in (0, 1):
+        for px in (0, 1):
+            for iy in (0, 1):
+                for ix in (0, 1):
+                    ky = (2 if iy else 0) if py else (3 if iy else 1)
+                    kx = (2 if ix else 0) if px else (3 if ix else 1)
+                    wp[py * 2 + px, :, iy * 2 + ix, :] = (w[:, :, ky, kx] * scale[None, :]).T
+    wp = wp.reshape(4 * 256, 4 * C).bfloat16().contiguous()
+    out = torch.full((B, 2 * H, 2 * W, 256), -7.0, dtype=torch.bfloat16, device=dev)
+    a_view = x.reshape(B * H * W, C)                                                # gemm() takes M from shape[0], K from W
+    from easy_vitpose_b200 import _lib
+    from gpu_util import ptr, stream
+    _lib.check(_lib.lib().vpb_gemm(ptr(a_view), ptr(wp), ptr(shift), ptr(out), B * H * W, 256, 4 * C, EPI_BF16_RELU_UP, None, 0,
+                                   H, W, TR, C, stream()))
+    torch.cuda.synchronize()
+    w_eff = (wp.float().reshape(4, 256, 4, C))                                      # reference from the SAME rounded weights
+    w_full = torch.zeros(C, 256, 4, 4, device=dev)
+    for py in (0, 1):
+        for px in (0, 1):
+            for iy in (0, 1):
+                for ix in (0, 1):
+                    ky = (2 if iy else 0) if py else (3 if iy else 1)
+                    kx = (2 if ix else 0) if px else (3 if ix else 1)
+                    w_full[:, :, ky, kx] = w_eff[py * 2 + px, :, iy * 2 + ix, :].T
+    ref = torch.nn.functional.conv_transpose2d(x.float().permute(0, 3, 1, 2), w_full, stride=2, padding=1)
+    ref = torch.relu(ref + shift[None, :, None, None]).permute(0, 2, 3, 1)
+    r = _rel(out.float(), ref)
+    print("implicit deconv rel err", r)
+    assert r < 1e-2
 
 
 @pytest.mark.parametrize("Kk,Npad", [(17, 32), (25, 32), (133, 144)])

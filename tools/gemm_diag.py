@@ -18,7 +18,7 @@ for name, (K, N, epi) in shapes.items():
     w = (torch.randn(N, K, device=dev) * 0.03).bfloat16()
     bias = torch.randn(N, device=dev)
     out = torch.zeros(M, N, dtype=torch.float32 if epi == EPI_F32_ADD else torch.bfloat16, device=dev)
-    for stages in (0, 3, 2):
+    for stages in (0,):
         L.vpb_debug_gemm(stages, None)
         for _ in range(3):
             gemm(a, w, bias, out, epi)
@@ -38,4 +38,6 @@ for name, (K, N, epi) in shapes.items():
     m[:3] = d[0::2, :3].mean(0)        # the MMA thread only exists in the leader (even) CTA of each pair
     print(f"      cycles/CTA: mma total {m[0]:.0f} wait_full {m[1]:.0f} ({m[1]/m[0]:.0%}) wait_acc_empty {m[2]:.0f} ({m[2]/m[0]:.0%}) | "
           f"producer total {m[3]:.0f} wait_empty {m[4]:.0f} ({m[4]/max(m[3],1):.0%}) | epilogue total {m[5]:.0f} wait_acc_full {m[6]:.0f} ({m[6]/max(m[5],1):.0%})")
+    life_cyc = d[:, 7].mean(); life_ns = d[1::2, 0].mean()
+    print(f"      CTA lifetime {life_cyc:.0f} cycles = {life_ns/1e3:.1f} us -> SM clock {life_cyc/life_ns:.2f} GHz")
     L.vpb_debug_gemm(0, None)
