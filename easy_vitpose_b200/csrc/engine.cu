@@ -203,7 +203,7 @@ struct vpb_engine {
   vpb_config cfg;
   int D, depth, heads, K, maxB, n_final;   // n_final = padded channel count of the 1x1 conv GEMM
   bool finalized = false;
-  int stop_after = 0, attn_v_manual = 0;
+  int stop_after = 0;
   Profiler prof;
   std::map<std::string, std::pair<float*, int64_t>> staged;   // fp32 state_dict tensors on device until finalize
   std::vector<void*> allocs;
@@ -476,10 +476,10 @@ static int backbone(vpb_engine* e, const float* d_crops, int B, cudaStream_t st)
     if (stop == 4) return VPB_OK;
     {
       AttnParams ap;
-      ap.batch = B; ap.heads = e->heads; ap.dim = D; ap.out = e->attn; ap.qkv = e->qkv; ap.v_manual = e->attn_v_manual;
+      ap.batch = B; ap.heads = e->heads; ap.dim = D; ap.out = e->attn;
       const int items = B * e->heads;
       e->prof.begin(KC_ATTN, st);
-      launch_k(attention_tcgen05, dim3(items < g_num_sms ? items : g_num_sms), dim3(ATT_THREADS), ATT_SMEM, st, e->m_qkv_att, ap);
+      launch_k(attention_tcgen05, dim3(items < 2 * g_num_sms ? items : 2 * g_num_sms), dim3(ATT_THREADS), ATT_SMEM, st, e->m_qkv_att, ap);
       e->prof.end(st);
       CU_TRY(cudaGetLastError());
     }
@@ -627,7 +627,6 @@ extern "C" int vpb_kernel_launches(const vpb_engine* e, int32_t) {
 extern "C" int vpb_set_option(vpb_engine* e, const char* name, int32_t value) {
   if (!e || !name) return fail(VPB_ERR_ARG, "vpb_set_option: null argument");
   if (!strcmp(name, "stop_after")) e->stop_after = value;
-  else if (!strcmp(name, "attn_v_manual")) e->attn_v_manual = value;
   else if (!strcmp(name, "profile")) e->prof.on = value != 0;
   else if (!strcmp(name, "pdl")) g_pdl = value != 0;
   else return fail(VPB_ERR_ARG, "unknown option %s", name);
@@ -706,7 +705,7 @@ extern "C" int vpb_gemm(const void* d_a, const void* d_w, const float* d_bias, v
   return gemm_launch(bn, epilogue, ta, tw, tout, p, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int vpb_attention(const void* d_qkv, int32_t batch, int32_t heads, void* d_out, int32_t v_manual, void* stream) {
+extern "C" int vpb_attention(const void* d_qkv, int32_t batch, int32_t heads, void* d_out, void* stream) {
   int dev = 0;
   CU_TRY(cudaGetDevice(&dev));
   VPB_TRY(device_check(dev));
@@ -716,9 +715,8 @@ extern "C" int vpb_attention(const void* d_qkv, int32_t batch, int32_t heads, vo
   VPB_TRY(make_map(&tq, d_qkv, static_cast<uint64_t>(batch) * 192, 3 * D, 3 * D, 192));
   AttnParams ap;
   ap.batch = batch; ap.heads = heads; ap.dim = D; ap.out = reinterpret_cast<__nv_bfloat16*>(d_out);
-  ap.qkv = reinterpret_cast<const __nv_bfloat16*>(d_qkv); ap.v_manual = v_manual;
   const int items = batch * heads;
-  launch_k(attention_tcgen05, dim3(items < g_num_sms ? items : g_num_sms), dim3(ATT_THREADS), ATT_SMEM, static_cast<cudaStream_t>(stream), tq, ap);
+  launch_k(attention_tcgen05, dim3(items < 2 * g_num_sms ? items : 2 * g_num_sms), dim3(ATT_THREADS), ATT_SMEM, static_cast<cudaStream_t>(stream), tq, ap);
   CU_TRY(cudaGetLastError());
   return VPB_OK;
 }

@@ -187,19 +187,18 @@ def test_gemm_heatmap_nchw(Kk, Npad):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("v_manual", [0, 1])
-@pytest.mark.parametrize("B,heads", [(1, 1), (3, 12), (40, 16)])
-def test_attention(B, heads, v_manual):
+@pytest.mark.parametrize("B,heads", [(1, 1), (3, 12), (40, 16), (64, 12)])
+def test_attention(B, heads):
     from gpu_util import attention
     torch.manual_seed(B * 100 + heads)
     D = heads * 64
     qkv = torch.randn(B * 192, 3 * D, device=_dev())
     qkv[:, :D] *= 0.125 * 2.0                                        # q arrives pre-scaled; keep logits O(few)
     qkv = qkv.bfloat16()
-    out = attention(qkv, B, heads, v_manual).float()
+    out = attention(qkv, B, heads).float()
     q, k, v = (qkv.float().reshape(B, 192, 3, heads, 64)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
     p = torch.softmax(q @ k.transpose(-1, -2), -1)
     ref = (p @ v).permute(0, 2, 1, 3).reshape(B * 192, D)
     r = _rel(out, ref)
-    print("attention rel err", r, "v_manual", v_manual)
+    print("attention rel err", r)
     assert r < 2e-2
