@@ -1,18 +1,20 @@
-// Fused multi-head attention for one ViTPose crop: T = 192 tokens, head_dim 64, everything on chip.
+// Fused multi-head attention for one ViTPose crop: T = 192 tokens, head_dim 32 / 64 / 80 (ViT-S / B,L / H), on chip.
 //
-// Work item = (crop b, head h); a CTA walks items blockIdx.x, +gridDim.x, ...  Two CTAs share an SM (72 KB smem,
+// Work item = (crop b, head h); a CTA walks items blockIdx.x, +gridDim.x, ...  Two CTAs share an SM (<= 92 KB smem,
 // 256 TMEM columns each), so one CTA's softmax overlaps the other's tensor-core phases.  Per item, for each of the
 // two 128-row M tiles (tokens 0..127, then 128..191):
-//   TMA    Q,K,V [192 x 64] bf16 boxes straight out of the qkv activation [M, 3D] -> 128B-swizzled smem (once per item)
+//   TMA    Q,K,V [192 x hd] bf16 boxes straight out of the qkv activation [M, 3D] -> swizzled smem (once per item)
 //   UMMA   S = Q K^T              M=128 x N=192, fp32 -> TMEM columns [0,192)                (q arrives pre-scaled)
 //   SIMT   row softmax out of TMEM (one thread per row): max, exp2, sum; P is written back IN PLACE as packed bf16
 //          (tcgen05.st, columns [0,96)) -- P never touches shared memory
 //   UMMA   O = P V                A = P from TMEM, B = V as an MN-major smem operand, i.e. exactly the [token][dim]
-//          box TMA delivered (no transpose); fp32 -> TMEM columns [192,256)
-//   SIMT   O / rowsum -> bf16 -> attn_out[b*192 + t, h*64 + d]
-// The second tile only has 64 live rows.  Even items take A rows 128..255 (live rows in TMEM lanes 0..63, the rest
-// reads past Q into K: UMMA rows are independent, they only feed lanes nobody reads); odd items take A rows 64..191
-// (live rows in lanes 64..127), so the half-tile work alternates between warps 0-1 and warps 2-3.
+//          box TMA delivered (no transpose); fp32 -> TMEM columns [O_COL0, O_COL0+hd)
+//   SIMT   O / rowsum -> bf16 -> attn_out[b*192 + t, h*hd + d]
+// Operand tiles: head_dim 64 -> one 128-byte-swizzled box per operand; 32 -> one 64-byte-swizzled box; 80 -> a
+// 128B-swizzled box of 64 dims plus a 32B-swizzled box of the last 16 (QK^T: 4+1 K steps; PV: an N=64 and an N=16 MMA).
+// The second M tile only has 64 live rows.  Even items take A rows 128..255 (live rows in TMEM lanes 0..63, the rest
+// reads past Q into what follows: UMMA rows are independent, they only feed lanes nobody reads); odd items take A rows
+// 64..191 (live rows in lanes 64..127), so the half-tile work alternates between warps 0-1 and warps 2-3.
 //
 // Warps 0..3: softmax / epilogue (warp w owns TMEM lane quarter w).  Warp 4, one thread: TMA + MMA issue.
 // Q/K of the next item are fetched as soon as the item's last S is done, V as soon as its last PV is done.
@@ -24,18 +26,29 @@
 namespace vpb {
 
 constexpr int ATT_T = 192;
-constexpr int ATT_HD = 64;
 constexpr int ATT_WORKERS = 128;
 constexpr int ATT_THREADS = ATT_WORKERS + 32;
-constexpr int ATT_TILE_BYTES = ATT_T * ATT_HD * 2;          // 24576: one Q/K/V box
-constexpr int ATT_SMEM = 3 * ATT_TILE_BYTES + 1024 + 128;
 constexpr int ATT_TMEM_COLS = 256;
-constexpr int ATT_O_COL0 = 192;                             // O accumulator behind the S tile
+
+template <int HD>
+struct AttCfg {
+  static_assert(HD == 32 || HD == 64 || HD == 80, "head_dim");
+  static constexpr int MAIN = HD == 32 ? 32 : 64;             // dims in the main box
+  static constexpr int TAIL = HD - MAIN;                      // 0 or 16 dims in the 32B-swizzled tail box
+  static constexpr int MAIN_ROW = MAIN * 2;                   // bytes per row = swizzle span (128 or 64)
+  static constexpr int MAIN_BYTES = ATT_T * MAIN_ROW;         // 24576 / 12288
+  static constexpr int TAIL_BYTES = TAIL ? ATT_T * 32 : 0;    // 6144
+  static constexpr int OPER_BYTES = MAIN_BYTES + TAIL_BYTES;  // one of Q / K / V
+  static constexpr int SMEM = 3 * OPER_BYTES + 1024 + 128;
+  // O accumulator: behind S when it fits in 256 columns, else inside the dead upper half of S (P only needs [0,96))
+  static constexpr int O_COL0 = HD <= 64 ? 192 : 96;
+  static constexpr bool O_IN_S = O_COL0 < 192;
+};
 
 struct AttnParams {
   int batch;              // crops
   int heads;
-  int dim;                // D = heads * 64
+  int dim;                // D = heads * head_dim
   __nv_bfloat16* out;     // [batch*192, D]
 };
 
@@ -57,14 +70,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// tmap_main: box [192 rows x MAIN cols] (swizzle = MAIN*2 bytes); tmap_tail: box [192 x 16] (32B swizzle), hd 80 only.
+template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
-attention_tcgen05(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p) {
+attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_constant__ CUtensorMap tmap_tail, const AttnParams p) {
+  using Cfg = AttCfg<HD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATT_TILE_BYTES;
-  uint8_t* sV = sK + ATT_TILE_BYTES;
-  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(sV + ATT_TILE_BYTES);
+  uint8_t* sQ = smem;                                       // each operand: main tile, then tail tile
+  uint8_t* sK = sQ + Cfg::OPER_BYTES;
+  uint8_t* sV = sK + Cfg::OPER_BYTES;
+  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(sV + Cfg::OPER_BYTES);
   uint64_t* bar_v = bar_qk + 1;
   uint64_t* bar_s = bar_qk + 2;      // S tile complete            (MMA commit -> workers)
   uint64_t* bar_p = bar_qk + 3;      // P written, S consumed      (128 workers -> MMA thread)
@@ -77,7 +93,8 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams
   const int items = p.batch * p.heads;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_main);
+    if constexpr (Cfg::TAIL > 0) tma_prefetch_desc(&tmap_tail);
     mbar_init(bar_qk, 1);
     mbar_init(bar_v, 1);
     mbar_init(bar_s, 1);
@@ -97,34 +114,43 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams
   if (warp == 4) {
     if (lane == 0) {
       // ------------------------------------------------------------------ TMA + MMA issue (one thread)
+      auto load_oper = [&](uint8_t* dst, uint64_t* bar, int col0, int row0) {
+        tma_load_2d(dst, &tmap_main, bar, col0, row0);
+        if constexpr (Cfg::TAIL > 0) tma_load_2d(dst + Cfg::MAIN_BYTES, &tmap_tail, bar, col0 + Cfg::MAIN, row0);
+      };
       auto load_qk = [&](int item) {
         const int b = item / p.heads, h = item % p.heads;
-        mbar_expect_tx(bar_qk, 2 * ATT_TILE_BYTES);
-        tma_load_2d(sQ, &tmap_qkv, bar_qk, h * ATT_HD, b * ATT_T);
-        tma_load_2d(sK, &tmap_qkv, bar_qk, p.dim + h * ATT_HD, b * ATT_T);
+        mbar_expect_tx(bar_qk, 2 * Cfg::OPER_BYTES);
+        load_oper(sQ, bar_qk, h * HD, b * ATT_T);
+        load_oper(sK, bar_qk, p.dim + h * HD, b * ATT_T);
       };
       auto load_v = [&](int item) {
         const int b = item / p.heads, h = item % p.heads;
-        mbar_expect_tx(bar_v, ATT_TILE_BYTES);
-        tma_load_2d(sV, &tmap_qkv, bar_v, 2 * p.dim + h * ATT_HD, b * ATT_T);
+        mbar_expect_tx(bar_v, Cfg::OPER_BYTES);
+        load_oper(sV, bar_v, 2 * p.dim + h * HD, b * ATT_T);
       };
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, ATT_T);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_HD, /*b_mn_major=*/true);
+      constexpr uint32_t idesc_o_main = umma_idesc_bf16(128, Cfg::MAIN, /*b_mn_major=*/true);
+      constexpr uint32_t idesc_o_tail = umma_idesc_bf16(128, 16, /*b_mn_major=*/true);
       if (blockIdx.x < items) { load_qk(blockIdx.x); load_v(blockIdx.x); }
       uint32_t step = 0;                                    // tile steps done so far: parity of bar_s/p/o/e
       uint32_t it = 0;                                      // items done so far: parity of bar_qk/bar_v
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         const int next = item + gridDim.x;
-        const uint64_t kdesc = umma_desc_sw128(smem_u32(sK), 1024);
         mbar_wait(bar_qk, it & 1);
         tc_fence_after_sync();
         for (int mt = 0; mt < 2; ++mt, ++step) {
           const uint32_t par = step & 1;
+          if (Cfg::O_IN_S && step > 0) { mbar_wait(bar_e, (step - 1) & 1); tc_fence_after_sync(); }   // O lives inside S here
           // S = Q K^T.  The S/P columns are free: the previous tile's PV (their last reader) was waited for below.
           const int q_row0 = mt == 0 ? 0 : ((it & 1) ? 64 : 128);
-          const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ) + q_row0 * 128, 1024);
+          const uint64_t qd = umma_desc_rows<Cfg::MAIN_ROW>(smem_u32(sQ) + q_row0 * Cfg::MAIN_ROW);
+          const uint64_t kd = umma_desc_rows<Cfg::MAIN_ROW>(smem_u32(sK));
 #pragma unroll
-          for (int k = 0; k < ATT_HD / 16; ++k) umma_bf16(tmem_base, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+          for (int k = 0; k < Cfg::MAIN / 16; ++k) umma_bf16(tmem_base, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+          if constexpr (Cfg::TAIL > 0)
+            umma_bf16(tmem_base, umma_desc_rows<32>(smem_u32(sQ) + Cfg::MAIN_BYTES + q_row0 * 32),
+                      umma_desc_rows<32>(smem_u32(sK) + Cfg::MAIN_BYTES), idesc_s, true);
           umma_commit(bar_s);
           if (mt == 1) {                                    // last S of the item done -> Q/K smem can be refilled
             mbar_wait(bar_s, par);
@@ -132,13 +158,17 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams
           }
           // O = P V once P is in TMEM and the previous O has been drained
           mbar_wait(bar_p, par);
-          if (step > 0) mbar_wait(bar_e, (step - 1) & 1);
+          if (!Cfg::O_IN_S && step > 0) mbar_wait(bar_e, (step - 1) & 1);
           if (mt == 0) mbar_wait(bar_v, it & 1);
           tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < ATT_T / 16; ++kk) {
-            // P: 16 bf16 of K = 8 packed TMEM columns per step.  V (MN-major): 16 tokens = two 8-row groups of 1024 B.
-            umma_bf16_ts(tmem_base + ATT_O_COL0, tmem_base + kk * 8, umma_desc_sw128(smem_u32(sV) + kk * 2048, 1024), idesc_o, kk != 0);
+            // P: 16 bf16 of K = 8 packed TMEM columns per step.  V (MN-major): 16 tokens = two 8-row groups.
+            umma_bf16_ts(tmem_base + Cfg::O_COL0, tmem_base + kk * 8,
+                         umma_desc_rows<Cfg::MAIN_ROW>(smem_u32(sV) + kk * 16 * Cfg::MAIN_ROW), idesc_o_main, kk != 0);
+            if constexpr (Cfg::TAIL > 0)
+              umma_bf16_ts(tmem_base + Cfg::O_COL0 + Cfg::MAIN, tmem_base + kk * 8,
+                           umma_desc_rows<32>(smem_u32(sV) + Cfg::MAIN_BYTES + kk * 16 * 32), idesc_o_tail, kk != 0);
           }
           umma_commit(bar_o);
           mbar_wait(bar_o, par);                            // PV retired: P columns and (after the item's last tile) V are free
@@ -156,11 +186,11 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams
       const int b = item / p.heads, h = item % p.heads;
       for (int mt = 0; mt < 2; ++mt, ++step) {
         const uint32_t par = step & 1;
-        // token handled by this thread, or -1 if its lane is padding in this tile
+        // token handled by this thread; in the half tile only one pair of warps holds live rows
         int token;
         if (mt == 0) token = tl;
-        else if (it & 1) token = tl >= 64 ? 64 + tl : -1;   // A rows 64..191 -> lanes 64..127 hold tokens 128..191
-        else token = tl < 64 ? 128 + tl : -1;               // A rows 128..255 -> lanes 0..63 hold tokens 128..191
+        else if (it & 1) token = 64 + tl;                   // A rows 64..191 -> lanes 64..127 hold tokens 128..191
+        else token = 128 + tl;                              // A rows 128..255 -> lanes 0..63 hold tokens 128..191
         const bool live_warp = (mt == 0) || ((it & 1) ? quarter >= 2 : quarter < 2);   // warp-uniform
 
         mbar_wait(bar_s, par);
@@ -200,27 +230,28 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams
 
         mbar_wait(bar_o, par);
         tc_fence_after_sync();
-        uint32_t o[2][32];
+        constexpr int OCH = HD / 16;                        // 16-column chunks of O
+        uint32_t o[OCH][16];
         if (live_warp) {
-          tmem_ld32(lane_addr + ATT_O_COL0, o[0]);
-          tmem_ld32(lane_addr + ATT_O_COL0 + 32, o[1]);
+#pragma unroll
+          for (int q = 0; q < OCH; ++q) tmem_ld16(lane_addr + Cfg::O_COL0 + 16 * q, o[q]);
           tmem_ld_wait();
         }
         tc_fence_before_sync();
-        mbar_arrive(bar_e);                                 // O is in registers: the next PV may overwrite it
-        if (live_warp && token >= 0) {
+        mbar_arrive(bar_e);                                 // O is in registers: the next MMA may overwrite it
+        if (live_warp) {
           const float inv = 1.0f / sum;
-          __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * ATT_T + token) * p.dim + h * ATT_HD;
+          __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * ATT_T + token) * p.dim + h * HD;
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          for (int q = 0; q < OCH; ++q) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int v = 0; v < 2; ++v) {
               uint4 w;
-              w.x = pack_bf16(__uint_as_float(o[half][8 * q + 0]) * inv, __uint_as_float(o[half][8 * q + 1]) * inv);
-              w.y = pack_bf16(__uint_as_float(o[half][8 * q + 2]) * inv, __uint_as_float(o[half][8 * q + 3]) * inv);
-              w.z = pack_bf16(__uint_as_float(o[half][8 * q + 4]) * inv, __uint_as_float(o[half][8 * q + 5]) * inv);
-              w.w = pack_bf16(__uint_as_float(o[half][8 * q + 6]) * inv, __uint_as_float(o[half][8 * q + 7]) * inv);
-              *reinterpret_cast<uint4*>(orow + half * 32 + 8 * q) = w;
+              w.x = pack_bf16(__uint_as_float(o[q][8 * v + 0]) * inv, __uint_as_float(o[q][8 * v + 1]) * inv);
+              w.y = pack_bf16(__uint_as_float(o[q][8 * v + 2]) * inv, __uint_as_float(o[q][8 * v + 3]) * inv);
+              w.z = pack_bf16(__uint_as_float(o[q][8 * v + 4]) * inv, __uint_as_float(o[q][8 * v + 5]) * inv);
+              w.w = pack_bf16(__uint_as_float(o[q][8 * v + 6]) * inv, __uint_as_float(o[q][8 * v + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + 16 * q + 8 * v) = w;
             }
           }
         }

@@ -59,15 +59,18 @@ static int load_driver_api() {
 }
 // Row-major [rows, cols] tensor with row pitch `ld` elements; box = [box_rows, 128 bytes of columns], 128B-swizzled.
 // bf16: 64 columns per box (GEMM operands, bf16 outputs); f32: 32 columns per box (the fp32 residual stream).
-static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, bool f32 = false) {
+// `span` = bytes of one box row = swizzle span (128 default; 64 / 32 for the narrow attention operand boxes).
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, bool f32 = false,
+                    uint32_t span = 128) {
   VPB_TRY(load_driver_api());
   const uint64_t esz = f32 ? 4 : 2;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * esz};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), box_rows};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(span / esz), box_rows};
   cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = span == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = g_encode(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
-                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(VPB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%u", (int)r,
                                      (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
@@ -155,10 +158,35 @@ static int device_check(int device) {
                                     prop.major, prop.minor);
   g_num_sms = prop.multiProcessorCount;
   if (!g_attr_done) {
-    CU_TRY(cudaFuncSetAttribute(attention_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    CU_TRY(cudaFuncSetAttribute(attention_tcgen05<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<32>::SMEM));
+    CU_TRY(cudaFuncSetAttribute(attention_tcgen05<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<64>::SMEM));
+    CU_TRY(cudaFuncSetAttribute(attention_tcgen05<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<80>::SMEM));
     g_attr_done = true;
   }
   checked_device = device;
+  return VPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ attention dispatch
+// qkv bf16 [rows, 3*D]: main operand boxes [192 x 64] (128B swizzle) or [192 x 32] (64B swizzle, head_dim 32), plus a
+// [192 x 16] 32B-swizzled box for the last 16 dims of head_dim 80.
+static int make_attn_maps(CUtensorMap* main, CUtensorMap* tail, const void* qkv, uint64_t rows, int D, int hd) {
+  VPB_TRY(make_map(main, qkv, rows, 3 * D, 3 * D, 192, false, hd == 32 ? 64 : 128));
+  if (hd == 80) VPB_TRY(make_map(tail, qkv, rows, 3 * D, 3 * D, 192, false, 32));
+  else *tail = *main;
+  return VPB_OK;
+}
+static int attention_launch(int hd, const CUtensorMap& main, const CUtensorMap& tail, const AttnParams& ap, cudaStream_t st) {
+  const int items = ap.batch * ap.heads;
+  const dim3 grid(items < 2 * g_num_sms ? items : 2 * g_num_sms);
+  cudaError_t err;
+  switch (hd) {
+    case 32: err = launch_k(attention_tcgen05<32>, grid, dim3(ATT_THREADS), AttCfg<32>::SMEM, st, main, tail, ap); break;
+    case 64: err = launch_k(attention_tcgen05<64>, grid, dim3(ATT_THREADS), AttCfg<64>::SMEM, st, main, tail, ap); break;
+    case 80: err = launch_k(attention_tcgen05<80>, grid, dim3(ATT_THREADS), AttCfg<80>::SMEM, st, main, tail, ap); break;
+    default: return fail(VPB_ERR_ARG, "attention: head_dim %d not built (32, 64, 80)", hd);
+  }
+  if (err != cudaSuccess) return fail(VPB_ERR_CUDA, "attention launch: %s", cudaGetErrorString(err));
   return VPB_OK;
 }
 
@@ -217,7 +245,7 @@ struct vpb_engine {
   __nv_bfloat16 *patch_rows, *xn, *qkv, *attn, *hid, *d1, *d2;
   float *x, *heat, *kpts, *crops_stage;   // crops_stage: device landing buffer of vpb_infer_host
   int32_t *idx, *org_wh;
-  CUtensorMap m_patch_rows, m_xn, m_attn, m_hid, m_d2, m_qkv_att;   // A operands / attention boxes
+  CUtensorMap m_patch_rows, m_xn, m_attn, m_hid, m_d2, m_qkv_att, m_qkv_att_tail;   // A operands / attention boxes
   CUtensorMap m_feat_nhwc, m_d1_nhwc;                                 // implicit-GEMM deconv inputs (4-D)
   CUtensorMap o_qkv, o_hid, o_x;                                                             // TMA-epilogue outputs
 };
@@ -264,9 +292,10 @@ extern "C" int vpb_create(const vpb_config* cfg, vpb_engine** out) {
   *out = nullptr;
   if (cfg->embed_dim % 128 != 0 || cfg->num_heads <= 0 || cfg->embed_dim % cfg->num_heads != 0)
     return fail(VPB_ERR_ARG, "embed_dim=%d / num_heads=%d unsupported", cfg->embed_dim, cfg->num_heads);
-  if (cfg->embed_dim / cfg->num_heads != 64)
-    return fail(VPB_ERR_ARG, "head_dim=%d: the attention kernel currently covers head_dim 64 (ViT-B, ViT-L)",
-                cfg->embed_dim / cfg->num_heads);
+  {
+    const int hd = cfg->embed_dim / cfg->num_heads;
+    if (hd != 32 && hd != 64 && hd != 80) return fail(VPB_ERR_ARG, "head_dim=%d: attention is built for 32, 64 and 80 (ViT-S / B,L / H)", hd);
+  }
   if (cfg->embed_dim != 384 && cfg->embed_dim != 768 && cfg->embed_dim != 1024 && cfg->embed_dim != 1280)
     return fail(VPB_ERR_ARG, "embed_dim=%d has no LayerNorm instantiation", cfg->embed_dim);
   if (cfg->num_keypoints < 1 || cfg->num_keypoints > 144) return fail(VPB_ERR_ARG, "num_keypoints=%d out of range 1..144", cfg->num_keypoints);
@@ -403,7 +432,7 @@ extern "C" int vpb_finalize(vpb_engine* e) {
   VPB_TRY(make_map_nhwc(&e->m_feat_nhwc, e->xn, B, 16, 12, D, 8));     // 8 rows x 12 = 96 positions per M tile
   VPB_TRY(make_map_nhwc(&e->m_d1_nhwc, e->d1, B, 32, 24, 256, 4));    // 4 rows x 24 = 96 positions per M tile
   VPB_TRY(make_map(&e->m_d2, e->d2, B * 3072, 256, 256, 128));
-  VPB_TRY(make_map(&e->m_qkv_att, e->qkv, M, 3 * D, 3 * D, 192));
+  VPB_TRY(make_attn_maps(&e->m_qkv_att, &e->m_qkv_att_tail, e->qkv, M, D, D / e->heads));
   VPB_TRY(make_map(&e->o_qkv, e->qkv, M, 3 * D, 3 * D, 32));
   VPB_TRY(make_map(&e->o_hid, e->hid, M, 4 * D, 4 * D, 32));
   VPB_TRY(make_map(&e->o_x, e->x, M, D, D, 32, /*f32=*/true));
@@ -477,11 +506,9 @@ static int backbone(vpb_engine* e, const float* d_crops, int B, cudaStream_t st)
     {
       AttnParams ap;
       ap.batch = B; ap.heads = e->heads; ap.dim = D; ap.out = e->attn;
-      const int items = B * e->heads;
       e->prof.begin(KC_ATTN, st);
-      launch_k(attention_tcgen05, dim3(items < 2 * g_num_sms ? items : 2 * g_num_sms), dim3(ATT_THREADS), ATT_SMEM, st, e->m_qkv_att, ap);
+      VPB_TRY(attention_launch(D / e->heads, e->m_qkv_att, e->m_qkv_att_tail, ap, st));
       e->prof.end(st);
-      CU_TRY(cudaGetLastError());
     }
     if (stop == 5) return VPB_OK;
     {
@@ -705,20 +732,17 @@ extern "C" int vpb_gemm(const void* d_a, const void* d_w, const float* d_bias, v
   return gemm_launch(bn, epilogue, ta, tw, tout, p, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int vpb_attention(const void* d_qkv, int32_t batch, int32_t heads, void* d_out, void* stream) {
+extern "C" int vpb_attention(const void* d_qkv, int32_t batch, int32_t heads, int32_t head_dim, void* d_out, void* stream) {
   int dev = 0;
   CU_TRY(cudaGetDevice(&dev));
   VPB_TRY(device_check(dev));
   if (!d_qkv || !d_out || batch < 1 || heads < 1) return fail(VPB_ERR_ARG, "vpb_attention: bad argument");
-  const int D = heads * 64;
-  CUtensorMap tq;
-  VPB_TRY(make_map(&tq, d_qkv, static_cast<uint64_t>(batch) * 192, 3 * D, 3 * D, 192));
+  const int D = heads * head_dim;
+  CUtensorMap tm, tt;
+  VPB_TRY(make_attn_maps(&tm, &tt, d_qkv, static_cast<uint64_t>(batch) * 192, D, head_dim));
   AttnParams ap;
   ap.batch = batch; ap.heads = heads; ap.dim = D; ap.out = reinterpret_cast<__nv_bfloat16*>(d_out);
-  const int items = batch * heads;
-  launch_k(attention_tcgen05, dim3(items < 2 * g_num_sms ? items : 2 * g_num_sms), dim3(ATT_THREADS), ATT_SMEM, static_cast<cudaStream_t>(stream), tq, ap);
-  CU_TRY(cudaGetLastError());
-  return VPB_OK;
+  return attention_launch(head_dim, tm, tt, ap, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int vpb_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_y, int32_t rows, int32_t dim, float eps,

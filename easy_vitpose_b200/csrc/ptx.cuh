@@ -209,14 +209,22 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
 //   [46,48) version = 1 (sm_100)   [49,52) base offset                [61,64) layout: 0 none, 2 SW128, 4 SW64, 6 SW32
 // K-major operand, 128-byte swizzle: a row is 64 bf16 = 128 B, the 16-byte chunks of row r are
 // XOR-ed with (r % 8), 8-row groups are 1024 B apart (SBO); LBO is unused.  Tile base 1024-aligned.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
   d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) { return umma_desc(smem_addr, sbo_bytes, 2); }
+// Operand tiles whose rows are W bytes wide (W = 128 / 64 / 32 = the swizzle span): 8-row groups are 8*W bytes apart.
+// Works for both majors: K-major reads 16 elements (32 B) of each row per MMA, MN-major reads 16 whole rows.
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t umma_desc_rows(uint32_t smem_addr) {
+  static_assert(ROW_BYTES == 128 || ROW_BYTES == 64 || ROW_BYTES == 32, "swizzle span");
+  return umma_desc(smem_addr, 8 * ROW_BYTES, ROW_BYTES == 128 ? 2 : ROW_BYTES == 64 ? 4 : 6);
 }
 // Instruction descriptor, kind::f16, bf16 x bf16 -> f32:
 //   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)

@@ -24,9 +24,9 @@ def gemm(a, w, bias, out, epi, resid=None, resid_mod=0, aux=(0, 0, 0, 0)):
     torch.cuda.synchronize()
 
 
-def attention(qkv, batch, heads):
-    out = torch.empty((batch * 192, heads * 64), dtype=torch.bfloat16, device=qkv.device)
-    _lib.check(_lib.lib().vpb_attention(ptr(qkv), batch, heads, ptr(out), stream()))
+def attention(qkv, batch, heads, head_dim=64):
+    out = torch.empty((batch * 192, heads * head_dim), dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(_lib.lib().vpb_attention(ptr(qkv), batch, heads, head_dim, ptr(out), stream()))
     torch.cuda.synchronize()
     return out
 

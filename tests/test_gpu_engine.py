@@ -26,7 +26,7 @@ def _engine(g, max_batch=8):
     return m, O.make_crops(B, xseed)
 
 
-@pytest.mark.parametrize("name", ["b_coco", "l_coco_25"])
+@pytest.mark.parametrize("name", ["s_coco", "b_coco", "l_coco_25", "h_wholebody"])
 def test_forward_heatmaps_vs_reference(golden_dir, name):
     g = np.load(os.path.join(golden_dir, f"fwd_{name}.npz"))
     m, x = _engine(g)

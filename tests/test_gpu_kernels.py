@@ -187,18 +187,19 @@ def test_gemm_heatmap_nchw(Kk, Npad):
 
 
 # ------------------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("B,heads", [(1, 1), (3, 12), (40, 16), (64, 12)])
-def test_attention(B, heads):
+@pytest.mark.parametrize("B,heads,hd", [(1, 1, 64), (3, 12, 64), (40, 16, 64), (64, 12, 64),
+                                        (1, 1, 32), (5, 12, 32), (1, 1, 80), (4, 16, 80), (33, 16, 80)])
+def test_attention(B, heads, hd):
     from gpu_util import attention
-    torch.manual_seed(B * 100 + heads)
-    D = heads * 64
+    torch.manual_seed(B * 100 + heads + hd)
+    D = heads * hd
     qkv = torch.randn(B * 192, 3 * D, device=_dev())
-    qkv[:, :D] *= 0.125 * 2.0                                        # q arrives pre-scaled; keep logits O(few)
+    qkv[:, :D] *= (hd ** -0.5) * 2.0                                 # q arrives pre-scaled; keep logits O(few)
     qkv = qkv.bfloat16()
-    out = attention(qkv, B, heads).float()
-    q, k, v = (qkv.float().reshape(B, 192, 3, heads, 64)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    out = attention(qkv, B, heads, hd).float()
+    q, k, v = (qkv.float().reshape(B, 192, 3, heads, hd)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
     p = torch.softmax(q @ k.transpose(-1, -2), -1)
     ref = (p @ v).permute(0, 2, 1, 3).reshape(B * 192, D)
     r = _rel(out, ref)
-    print("attention rel err", r)
+    print("attention rel err", r, "hd", hd)
     assert r < 2e-2

@@ -26,6 +26,6 @@ for _ in range(reps):
     gemm(xn, wproj, b1, x, EPI_F32_ADD)
     gemm(xn, wfc1, b4, h, EPI_BF16_GELU)
     gemm(hid, wfc2, b1, x, EPI_F32_ADD)
-    attention(qkv, 64, 12)
+    attention(qkv, 64, 12, 64)
     layernorm(x, b1, b1)
 print("done")
