@@ -6,6 +6,7 @@ csrc/ holds the hand-written CUDA (tcgen05 GEMM + attention, LayerNorm, gathers,
 (include/vitpose_b200.h); the Python modules mirror the reference's interface for this path:
 model.ViTPose, top_down_eval.keypoints_from_heatmaps, inference.install / B200PoseBackend.
 """
+from . import distributed  # noqa: F401
 from .configs import data_cfg, dyn_model_import, model_cfg  # noqa: F401
 from .inference import B200PoseBackend, install  # noqa: F401
 from .model import ViTPose  # noqa: F401

@@ -243,8 +243,12 @@ struct vpb_engine {
   LinearW dc1, dc2, fin;            // dc*: the 4 phase matrices stacked [4*256, 4*Cin]
   // workspace
   __nv_bfloat16 *patch_rows, *xn, *qkv, *attn, *hid, *d1, *d2;
-  float *x, *heat, *kpts, *crops_stage;   // crops_stage: device landing buffer of vpb_infer_host
-  int32_t *idx, *org_wh;
+  float *x, *heat;
+  // host-facing path: two staging slots (crops, org_wh in; kpts, idx out) so that slot i+1's H2D overlaps slot i's compute
+  float *crops_stage[2], *kpts[2];
+  int32_t *idx[2], *org_wh[2];
+  cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   CUtensorMap m_patch_rows, m_xn, m_attn, m_hid, m_d2, m_qkv_att, m_qkv_att_tail;   // A operands / attention boxes
   CUtensorMap m_feat_nhwc, m_d1_nhwc;                                 // implicit-GEMM deconv inputs (4-D)
   CUtensorMap o_qkv, o_hid, o_x;                                                             // TMA-epilogue outputs
@@ -314,6 +318,12 @@ extern "C" void vpb_destroy(vpb_engine* e) {
   if (!e) return;
   for (auto& kv : e->staged) cudaFree(kv.second.first);
   for (void* p : e->allocs) cudaFree(p);
+  for (int s = 0; s < 2; ++s) {
+    if (e->ev_h2d[s]) cudaEventDestroy(e->ev_h2d[s]);
+    if (e->ev_done[s]) cudaEventDestroy(e->ev_done[s]);
+  }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->compute_stream) cudaStreamDestroy(e->compute_stream);
   delete e;
 }
 
@@ -421,10 +431,16 @@ extern "C" int vpb_finalize(vpb_engine* e) {
   VPB_TRY(dev_alloc(e, &e->d1, B * 768 * 256));
   VPB_TRY(dev_alloc(e, &e->d2, B * 3072 * 256));
   VPB_TRY(dev_alloc(e, &e->heat, B * e->K * 3072));
-  VPB_TRY(dev_alloc(e, &e->kpts, B * e->K * 3));
-  VPB_TRY(dev_alloc(e, &e->idx, B * e->K));
-  VPB_TRY(dev_alloc(e, &e->org_wh, B * 2));
-  VPB_TRY(dev_alloc(e, &e->crops_stage, B * 3 * 256 * 192));
+  for (int s = 0; s < 2; ++s) {
+    VPB_TRY(dev_alloc(e, &e->kpts[s], B * e->K * 3));
+    VPB_TRY(dev_alloc(e, &e->idx[s], B * e->K));
+    VPB_TRY(dev_alloc(e, &e->org_wh[s], B * 2));
+    VPB_TRY(dev_alloc(e, &e->crops_stage[s], B * 3 * 256 * 192));
+    CU_TRY(cudaEventCreateWithFlags(&e->ev_h2d[s], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&e->ev_done[s], cudaEventDisableTiming));
+  }
+  CU_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&e->compute_stream, cudaStreamNonBlocking));
   VPB_TRY(make_map(&e->m_patch_rows, e->patch_rows, M, 768, 768, 128));
   VPB_TRY(make_map(&e->m_xn, e->xn, M, D, D, 128));
   VPB_TRY(make_map(&e->m_attn, e->attn, M, D, D, 128));
@@ -460,17 +476,18 @@ static int layernorm(const float* x, const float* g, const float* b, __nv_bfloat
   return VPB_OK;
 }
 
-static int g_dbg_stages = 0;
+static int g_dbg_stages = 0, g_dbg_flags = 0;
 static long long* g_dbg_buf = nullptr;
 extern "C" int vpb_debug_gemm(int32_t stages_limit, void* d_counters) {   // counters: int64 [grid*8], see GemmParams::dbg
-  g_dbg_stages = stages_limit;
+  g_dbg_flags = stages_limit >> 8;       // bits 8.. carry GemmParams::dbg_flags
+  g_dbg_stages = stages_limit & 0xff;
   g_dbg_buf = reinterpret_cast<long long*>(d_counters);
   return VPB_OK;
 }
 static GemmParams gp(int M, int N, int K, const float* bias, void* out, int ldc) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.stages_limit = g_dbg_stages; p.dbg = g_dbg_buf;
+  p.stages_limit = g_dbg_stages; p.dbg = g_dbg_buf; p.dbg_flags = g_dbg_flags;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldc = ldc;
   return p;
 }
@@ -626,13 +643,39 @@ extern "C" int vpb_infer_host(vpb_engine* e, const float* h_crops, const int32_t
   VPB_TRY(check_ready(e, batch));
   if (!h_crops || !h_org_wh || !h_kpts) return fail(VPB_ERR_ARG, "vpb_infer_host: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  float* d_crops = e->crops_stage;
-  CU_TRY(cudaMemcpyAsync(d_crops, h_crops, static_cast<size_t>(batch) * 3 * 256 * 192 * sizeof(float), cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemcpyAsync(e->org_wh, h_org_wh, static_cast<size_t>(batch) * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  VPB_TRY(vpb_infer(e, d_crops, e->org_wh, batch, e->kpts, e->idx, nullptr, st));
-  CU_TRY(cudaMemcpyAsync(h_kpts, e->kpts, static_cast<size_t>(batch) * e->K * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (h_idx) CU_TRY(cudaMemcpyAsync(h_idx, e->idx, static_cast<size_t>(batch) * e->K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(e->crops_stage[0], h_crops, static_cast<size_t>(batch) * 3 * 256 * 192 * sizeof(float), cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(e->org_wh[0], h_org_wh, static_cast<size_t>(batch) * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  VPB_TRY(vpb_infer(e, e->crops_stage[0], e->org_wh[0], batch, e->kpts[0], e->idx[0], nullptr, st));
+  CU_TRY(cudaMemcpyAsync(h_kpts, e->kpts[0], static_cast<size_t>(batch) * e->K * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (h_idx) CU_TRY(cudaMemcpyAsync(h_idx, e->idx[0], static_cast<size_t>(batch) * e->K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
+  return VPB_OK;
+}
+
+// Pipelined form of vpb_infer_host: submit(slot) enqueues H2D on the engine's copy stream and the path + D2H on its compute
+// stream and returns; wait(slot) blocks until that slot's keypoints are in the caller's buffer.  With two slots in flight
+// the H2D of batch i+1 runs under the compute of batch i.  Host buffers must stay valid (and should be pinned) until wait().
+extern "C" int vpb_submit_host(vpb_engine* e, const float* h_crops, const int32_t* h_org_wh, int32_t batch, float* h_kpts,
+                               int32_t* h_idx, int32_t slot) {
+  VPB_TRY(check_ready(e, batch));
+  if (!h_crops || !h_org_wh || !h_kpts || slot < 0 || slot > 1) return fail(VPB_ERR_ARG, "vpb_submit_host: bad argument");
+  CU_TRY(cudaSetDevice(e->cfg.device));
+  // the slot's previous use must have finished with its staging buffers before they are overwritten
+  CU_TRY(cudaStreamWaitEvent(e->copy_stream, e->ev_done[slot], 0));
+  CU_TRY(cudaMemcpyAsync(e->crops_stage[slot], h_crops, static_cast<size_t>(batch) * 3 * 256 * 192 * sizeof(float), cudaMemcpyHostToDevice,
+                         e->copy_stream));
+  CU_TRY(cudaMemcpyAsync(e->org_wh[slot], h_org_wh, static_cast<size_t>(batch) * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, e->copy_stream));
+  CU_TRY(cudaEventRecord(e->ev_h2d[slot], e->copy_stream));
+  CU_TRY(cudaStreamWaitEvent(e->compute_stream, e->ev_h2d[slot], 0));
+  VPB_TRY(vpb_infer(e, e->crops_stage[slot], e->org_wh[slot], batch, e->kpts[slot], e->idx[slot], nullptr, e->compute_stream));
+  CU_TRY(cudaMemcpyAsync(h_kpts, e->kpts[slot], static_cast<size_t>(batch) * e->K * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->compute_stream));
+  if (h_idx) CU_TRY(cudaMemcpyAsync(h_idx, e->idx[slot], static_cast<size_t>(batch) * e->K * sizeof(int32_t), cudaMemcpyDeviceToHost, e->compute_stream));
+  CU_TRY(cudaEventRecord(e->ev_done[slot], e->compute_stream));
+  return VPB_OK;
+}
+extern "C" int vpb_wait_host(vpb_engine* e, int32_t slot) {
+  if (!e || slot < 0 || slot > 1) return fail(VPB_ERR_ARG, "vpb_wait_host: bad argument");
+  CU_TRY(cudaEventSynchronize(e->ev_done[slot]));
   return VPB_OK;
 }
 

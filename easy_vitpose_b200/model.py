@@ -233,6 +233,23 @@ class ViTPose:
                                                  kp.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p), self._stream()))
         return kp, idx
 
+    def submit_host(self, crops: np.ndarray, org_wh: np.ndarray, kpts_out: np.ndarray, idx_out: np.ndarray, slot: int) -> None:
+        """Asynchronous vpb_submit_host: the arrays must be C-contiguous float32 / int32, stay alive and unmodified until
+        wait_host(slot); pinned memory (torch.Tensor.pin_memory().numpy()) gives real copy/compute overlap."""
+        self._ensure()
+        B = crops.shape[0]
+        if crops.dtype != np.float32 or org_wh.dtype != np.int32 or kpts_out.dtype != np.float32 or idx_out.dtype != np.int32:
+            raise TypeError("submit_host takes float32 crops / keypoints and int32 org_wh / idx")
+        if crops.shape[1:] != (3, IMG_H, IMG_W) or org_wh.shape != (B, 2) or kpts_out.shape != (B, self.num_keypoints, 3) \
+                or idx_out.shape != (B, self.num_keypoints) or not all(a.flags.c_contiguous for a in (crops, org_wh, kpts_out, idx_out)):
+            raise ValueError("submit_host: wrong shapes or non-contiguous arrays")
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().vpb_submit_host(self._handle, crops.ctypes.data_as(C.c_void_p), org_wh.ctypes.data_as(C.c_void_p), B,
+                                                  kpts_out.ctypes.data_as(C.c_void_p), idx_out.ctypes.data_as(C.c_void_p), int(slot)))
+
+    def wait_host(self, slot: int) -> None:
+        _lib.check(_lib.lib().vpb_wait_host(self._handle, int(slot)))
+
     def kernel_launches(self, batch: int) -> int:
         self._ensure()
         return int(_lib.lib().vpb_kernel_launches(self._handle, batch))

@@ -77,6 +77,12 @@ int vpb_infer(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, int3
  * (vpb_host_alloc) makes the copies asynchronous DMA. */
 int vpb_infer_host(vpb_engine* e, const float* h_crops, const int32_t* h_org_wh, int32_t batch, float* h_kpts,
                    int32_t* h_idx, void* stream);
+/* Pipelined form: vpb_submit_host(slot 0|1) enqueues H2D (engine copy stream), the path and D2H (engine compute stream)
+ * and returns; vpb_wait_host(slot) blocks until that slot's keypoints are in h_kpts.  Keeping two slots in flight hides
+ * the H2D of batch i+1 under the compute of batch i.  Host buffers must stay valid until the wait (pinned: real overlap). */
+int vpb_submit_host(vpb_engine* e, const float* h_crops, const int32_t* h_org_wh, int32_t batch, float* h_kpts,
+                    int32_t* h_idx, int32_t slot);
+int vpb_wait_host(vpb_engine* e, int32_t slot);
 void* vpb_host_alloc(int64_t bytes);   /* cudaHostAlloc; NULL on failure */
 void vpb_host_free(void* p);
 

@@ -73,6 +73,23 @@ def test_host_api_matches_device_api(golden_dir):
     assert np.array_equal(kp_d.cpu().numpy(), kp_h) and np.array_equal(idx_d.cpu().numpy(), idx_h)
 
 
+def test_pipelined_host_api(golden_dir):
+    g = np.load(os.path.join(golden_dir, "fwd_b_coco.npz"))
+    m, _ = _engine(g, max_batch=4)
+    xs = [torch.from_numpy(O.make_crops(n, 50 + n)).pin_memory().numpy() for n in (4, 3, 4, 1)]
+    orgs = [np.tile(np.array([[170 + 3 * n, 230 - n]], np.int32), (x.shape[0], 1)) for n, x in enumerate(xs)]
+    ref = [m.infer_host(x, o) for x, o in zip(xs, orgs)]
+    kps = [np.empty((x.shape[0], 17, 3), np.float32) for x in xs]
+    ids = [np.empty((x.shape[0], 17), np.int32) for x in xs]
+    m.submit_host(xs[0], orgs[0], kps[0], ids[0], 0)
+    for i in range(1, len(xs)):
+        m.submit_host(xs[i], orgs[i], kps[i], ids[i], i % 2)
+        m.wait_host((i - 1) % 2)
+    m.wait_host((len(xs) - 1) % 2)
+    for (rk, ri), k, i in zip(ref, kps, ids):
+        assert np.array_equal(rk, k) and np.array_equal(ri, i)
+
+
 def test_batch_invariance_and_ragged_batches(golden_dir):
     """crops are independent units: any batch split gives the same per-crop result (what lets them shard)."""
     g = np.load(os.path.join(golden_dir, "fwd_b_coco.npz"))

@@ -18,7 +18,7 @@ for name, (K, N, epi) in shapes.items():
     w = (torch.randn(N, K, device=dev) * 0.03).bfloat16()
     bias = torch.randn(N, device=dev)
     out = torch.zeros(M, N, dtype=torch.float32 if epi == EPI_F32_ADD else torch.bfloat16, device=dev)
-    for stages in (0,):
+    for stages in (0, 1 << 8, 2 << 8, 3 << 8, 4 << 8):   # bits 8..: 1 same A, 2 same W, 4 n-fastest order
         L.vpb_debug_gemm(stages, None)
         for _ in range(3):
             gemm(a, w, bias, out, epi)
@@ -29,7 +29,7 @@ for name, (K, N, epi) in shapes.items():
                                   M, N, K, epi, None, 0, 0, 0, 0, 0, None))
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 100
-        print(f"{name:5s} stages={stages or 'max'} {us:8.1f} us  {2*M*N*K/us/1e6:8.1f} TFLOP/s")
+        print(f"{name:5s} flags={stages >> 8} {us:8.1f} us  {2*M*N*K/us/1e6:8.1f} TFLOP/s")
     dbg = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
     L.vpb_debug_gemm(0, C.c_void_p(dbg.data_ptr()))
     gemm(a, w, bias, out, epi)
