@@ -164,6 +164,7 @@ def run_gpu(args) -> None:
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"          # the version banner would land on stdout next to the JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     D, depth, heads = MODELS[args.model]
@@ -249,11 +250,21 @@ def run_gpu(args) -> None:
     sync_dt = time.perf_counter() - t0
     barrier()
     t0 = time.perf_counter()
-    model.submit_host(hc[0], ho, hk[0], hi[0], 0)
-    for i in range(1, e_steps):
-        model.submit_host(hc[i % 2], ho, hk[i % 2], hi[i % 2], i % 2)
-        model.wait_host((i - 1) % 2)
-    model.wait_host((e_steps - 1) % 2)
+    if world == 1:
+        model.submit_host(hc[0], ho, hk[0], hi[0], 0)
+        for i in range(1, e_steps):
+            model.submit_host(hc[i % 2], ho, hk[i % 2], hi[i % 2], i % 2)
+            model.wait_host((i - 1) % 2)
+        model.wait_host((e_steps - 1) % 2)
+    else:
+        # N > 1: the user-level call is infer_crops on this rank's shard + the keypoint gather; host buffers in and out
+        from easy_vitpose_b200.distributed import gather_keypoints
+        x_dev = torch.empty((B, 3, 256, 192), dtype=torch.float32, device=dev)
+        for i in range(e_steps):
+            x_dev.copy_(h_crops[i % 2], non_blocking=True)
+            kp, _ = model.infer_crops(x_dev, org_wh)
+            full = gather_keypoints(kp, world * B)
+            h_all = full.cpu()                           # D2H of the gathered result + sync
     e_dt = time.perf_counter() - t0
     te = torch.tensor([e_dt, sync_dt], dtype=torch.float64, device=dev)
     if world > 1:
@@ -275,9 +286,16 @@ def run_gpu(args) -> None:
         # dominant kernel = the class with the largest share of device time
         dom = max((k for k in kernels if "tflops" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))   # timed inside a long step
+        traffic = None          # dram__bytes_read+write of the dominant kernel, one ncu --set full capture (profiles/)
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+                traffic = json.load(fh)["dram_bytes_per_launch"].get(dom) if args.model == "b" and B == 64 else None
+        except Exception:
+            traffic = None
         roofline = {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": kernels[dom]["tflops"] / peak_tf, "peak_source": f"{peak_src} bf16_tflops_sustained",
-                    "traffic": None,
+                    "traffic": traffic, "traffic_unit": "bytes/launch (ncu, cold cache)",
+                    "flops_per_launch": fl[dom] * B / max(1.0, kernels[dom]["launches_per_step"]),
                     "whole_step_tflops": fl["total"] * B * args.steps / (ms_total / 1e3) / 1e12,
                     "attention_gemm_tflops": (fl["gemm_qkv"] + fl["attention"] + fl["gemm_proj"]) * B * args.steps /
                     ((prof["gemm_qkv"][0] + prof["attention"][0] + prof["gemm_proj"][0]) / 1e3) / 1e12}
@@ -297,7 +315,8 @@ def run_gpu(args) -> None:
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": int(B * 3 * 256 * 192 * 4 + B * 8),
                     "d2h_bytes_per_step": int(B * K * 3 * 4 + B * K * 4), "steps": e_steps,
-                    "api": "vpb_submit_host / vpb_wait_host (C ABI), 2 batches in flight, pinned host buffers",
+                    "api": ("vpb_submit_host / vpb_wait_host (C ABI), 2 batches in flight, pinned host buffers" if world == 1 else
+                            "pinned host crops -> infer_crops on the rank's shard -> NCCL all_gather of keypoints -> host"),
                     "single_call_value": e2e_sync_value, "single_call_api": "vpb_infer_host (H2D, path, D2H, sync per call)"},
             "gpu_launches": model.kernel_launches(B) * args.steps,
             "roofline": roofline,
