@@ -110,19 +110,61 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ CPU oracle arm
 def oracle_throughput(model: str, K: int, sample_crops: int, steps: int, warmup: int) -> tuple[float, float, int]:
-    """crops/s of the CPU restatement (oracle/) -- forward + decode -- on `sample_crops` crops per step."""
+    """crops/s of the reference path restated on the CPU (oracle/): the torch fp32 forward the reference itself runs
+    (oracle/torch_ref.py, same ops as vit_models/*) + the numpy decode restatement, on `sample_crops` crops per step,
+    with every host core torch / BLAS will use."""
+    import torch
+
+    from oracle import torch_ref as T
     from oracle import vitpose_oracle as O
     D, depth, heads = MODELS[model]
-    sd = O.make_state_dict(D, depth, K, seed=1, peaky=0.1, bumps=True)
-    x = O.make_crops(sample_crops, seed=2)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)                     # torchrun pins OMP_NUM_THREADS=1 otherwise
+    sd = T.to_device(O.make_state_dict(D, depth, K, seed=1, peaky=0.1, bumps=True), "cpu", torch.float32)
+    x = torch.from_numpy(O.make_crops(sample_crops, seed=2))
     org = np.tile(np.array([[192, 256]], np.int32), (sample_crops, 1))
+
+    def one():
+        with torch.no_grad():
+            hm = T.forward(x, sd, depth, heads).numpy()
+        return O.decode_maps(hm, org, wrap="crop")
+
     for _ in range(warmup):
-        O.infer_crops(x, org, sd, depth, heads)
+        one()
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.infer_crops(x, org, sd, depth, heads)
+        one()
     dt = time.perf_counter() - t0
-    return sample_crops * steps / dt, dt / steps * 1e3, os.cpu_count() or 1
+    return sample_crops * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def torch_cuda_eager(model: str, K: int, B: int, dev) -> dict:
+    """The target the north star names: the reference's torch-CUDA eager forward (library kernels), restated in
+    oracle/torch_ref.py because the reference package cannot travel; fp32 as shipped and .to(bfloat16), forward only."""
+    import torch
+
+    from oracle import torch_ref as T
+    from oracle import vitpose_oracle as O
+    D, depth, heads = MODELS[model]
+    sd_np = O.make_state_dict(D, depth, K, seed=1, peaky=0.1, bumps=True)
+    out = {}
+    for name, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        sd = T.to_device(sd_np, dev, dt)
+        x = torch.randn((B, 3, 256, 192), device=dev, dtype=dt)
+        with torch.no_grad():
+            for _ in range(5):
+                T.forward(x, sd, depth, heads)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                T.forward(x, sd, depth, heads)
+            e1.record()
+            torch.cuda.synchronize()
+        out[name + "_crops_per_s"] = B * 20 / (e0.elapsed_time(e1) / 1e3)
+        del sd, x
+    out["note"] = "torch eager forward only (no decode), same box, same run; allow_tf32 as torch ships it"
+    return out
 
 
 def run_reference(args) -> None:
@@ -139,7 +181,7 @@ def run_reference(args) -> None:
         "config": {"workload": f"ViT-{args.model.upper()} COCO-{args.keypoints}, 256x192 crops, CPU sample of {sample} crops per step",
                    "batch_per_gpu": args.batch},
         "cpu_baseline": {"value": value, "unit": "crops/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} crops/step x {args.steps} steps, numpy/OpenBLAS fp32 oracle (forward + decode)"},
+                         "sample": f"{sample} crops/step x {args.steps} steps, torch CPU fp32 forward + numpy decode (oracle/)"},
         "e2e": {"value": value, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -301,8 +343,10 @@ def run_gpu(args) -> None:
                     ((prof["gemm_qkv"][0] + prof["attention"][0] + prof["gemm_proj"][0]) / 1e3) / 1e12}
         # CPU baseline: the oracle port on this box's host cores, bounded sample
         cpu_val, cpu_ms, cores = (None, None, os.cpu_count())
+        eager = None
         if world == 1 and not args.no_cpu_baseline:
             cpu_val, cpu_ms, cores = oracle_throughput(args.model, K, args.cpu_sample, 3, 1)
+            eager = torch_cuda_eager(args.model, K, B, dev)
         line = {
             "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -324,7 +368,8 @@ def run_gpu(args) -> None:
             "kernels": kernels,
             "cpu_baseline": None if cpu_val is None else {
                 "value": cpu_val, "unit": "crops/s", "cores": cores, "kind": "port",
-                "sample": f"{args.cpu_sample} crops x 3 steps, numpy/OpenBLAS fp32 oracle (forward + decode)"},
+                "sample": f"{args.cpu_sample} crops x 3 steps, torch CPU fp32 forward + numpy decode (oracle/)"},
+            "torch_cuda_eager": eager,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -39,7 +39,9 @@ struct AttCfg {
   static constexpr int MAIN_BYTES = ATT_T * MAIN_ROW;         // 24576 / 12288
   static constexpr int TAIL_BYTES = TAIL ? ATT_T * 32 : 0;    // 6144
   static constexpr int OPER_BYTES = MAIN_BYTES + TAIL_BYTES;  // one of Q / K / V
-  static constexpr int SMEM = 3 * OPER_BYTES + 1024 + 128;
+  static constexpr int OUT_PITCH = HD * 2 + 16;               // staging row pitch (bytes): conflict-free 16-byte accesses
+  static constexpr int OUT_STAGE = 4 * 32 * OUT_PITCH;        // 4 worker warps x 32 rows
+  static constexpr int SMEM = 3 * OPER_BYTES + OUT_STAGE + 1024 + 128;
   // O accumulator: behind S when it fits in 256 columns, else inside the dead upper half of S (P only needs [0,96))
   static constexpr int O_COL0 = HD <= 64 ? 192 : 96;
   static constexpr bool O_IN_S = O_COL0 < 192;
@@ -50,6 +52,8 @@ struct AttnParams {
   int heads;
   int dim;                // D = heads * head_dim
   __nv_bfloat16* out;     // [batch*192, D]
+  long long* dbg;         // debug cycle counters per CTA [8] or nullptr: 0 lifetime, 1 worker wait S, 2 softmax, 3 worker wait O,
+                          //   4 epilogue, 5 ctl wait P, 6 ctl wait O, 7 ctl wait loads
 };
 
 // P (A operand) from TMEM, V (B operand) from smem
@@ -80,7 +84,8 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
   uint8_t* sQ = smem;                                       // each operand: main tile, then tail tile
   uint8_t* sK = sQ + Cfg::OPER_BYTES;
   uint8_t* sV = sK + Cfg::OPER_BYTES;
-  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(sV + Cfg::OPER_BYTES);
+  uint8_t* sOut = sV + Cfg::OPER_BYTES;                      // per-warp output staging (coalesced global stores)
+  uint64_t* bar_qk = reinterpret_cast<uint64_t*>(sOut + Cfg::OUT_STAGE);
   uint64_t* bar_v = bar_qk + 1;
   uint64_t* bar_s = bar_qk + 2;      // S tile complete            (MMA commit -> workers)
   uint64_t* bar_p = bar_qk + 3;      // P written, S consumed      (128 workers -> MMA thread)
@@ -91,6 +96,7 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int items = p.batch * p.heads;
+  const long long t_cta0 = p.dbg ? clock64() : 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_main);
@@ -135,9 +141,12 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
       if (blockIdx.x < items) { load_qk(blockIdx.x); load_v(blockIdx.x); }
       uint32_t step = 0;                                    // tile steps done so far: parity of bar_s/p/o/e
       uint32_t it = 0;                                      // items done so far: parity of bar_qk/bar_v
+      long long c_wp = 0, c_wo = 0, c_wl = 0, c0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         const int next = item + gridDim.x;
+        c0 = clock64();
         mbar_wait(bar_qk, it & 1);
+        c_wl += clock64() - c0;
         tc_fence_after_sync();
         for (int mt = 0; mt < 2; ++mt, ++step) {
           const uint32_t par = step & 1;
@@ -157,9 +166,13 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
             if (next < items) load_qk(next);
           }
           // O = P V once P is in TMEM and the previous O has been drained
+          c0 = clock64();
           mbar_wait(bar_p, par);
           if (!Cfg::O_IN_S && step > 0) mbar_wait(bar_e, (step - 1) & 1);
+          c_wp += clock64() - c0;
+          c0 = clock64();
           if (mt == 0) mbar_wait(bar_v, it & 1);
+          c_wl += clock64() - c0;
           tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < ATT_T / 16; ++kk) {
@@ -171,10 +184,13 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
                            umma_desc_rows<32>(smem_u32(sV) + Cfg::MAIN_BYTES + kk * 16 * 32), idesc_o_tail, kk != 0);
           }
           umma_commit(bar_o);
+          c0 = clock64();
           mbar_wait(bar_o, par);                            // PV retired: P columns and (after the item's last tile) V are free
+          c_wo += clock64() - c0;
           if (mt == 1 && next < items) load_v(next);
         }
       }
+      if (p.dbg) { p.dbg[blockIdx.x * 8 + 5] = c_wp; p.dbg[blockIdx.x * 8 + 6] = c_wo; p.dbg[blockIdx.x * 8 + 7] = c_wl; }
     }
   } else {
     // -------------------------------------------------------------------- softmax + epilogue (warps 0..3)
@@ -182,6 +198,7 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
     const int tl = quarter * 32 + lane;                     // TMEM lane = row of the M tile
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t step = 0, it = 0;
+    long long w_s = 0, w_sm = 0, w_o = 0, w_ep = 0, c0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       const int b = item / p.heads, h = item % p.heads;
       for (int mt = 0; mt < 2; ++mt, ++step) {
@@ -193,26 +210,31 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
         else token = 128 + tl;                              // A rows 128..255 -> lanes 0..63 hold tokens 128..191
         const bool live_warp = (mt == 0) || ((it & 1) ? quarter >= 2 : quarter < 2);   // warp-uniform
 
+        c0 = clock64();
         mbar_wait(bar_s, par);
+        w_s += clock64() - c0;
+        c0 = clock64();
         tc_fence_after_sync();
         float sum = 1.0f;
         if (live_warp) {
+          // Both passes keep one TMEM load in flight while the previous chunk is processed (ra / rb ping-pong).
+          uint32_t ra[32], rb[32];
           float mx = -INFINITY;
-#pragma unroll 1
-          for (int c = 0; c < ATT_T; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(lane_addr + c, r);
-            tmem_ld_wait();
+          tmem_ld32(lane_addr, ra);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+          for (int c = 0; c < ATT_T; c += 64) {
+            tmem_ld_wait();
+            tmem_ld32(lane_addr + c + 32, rb);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(ra[j]));
+            tmem_ld_wait();
+            if (c + 64 < ATT_T) tmem_ld32(lane_addr + c + 64, ra);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(rb[j]));
           }
           const float mscaled = mx * 1.4426950408889634f;
           sum = 0.0f;
-#pragma unroll 1
-          for (int c = 0; c < ATT_T; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(lane_addr + c, r);
-            tmem_ld_wait();
+          auto exp_chunk = [&](const uint32_t (&r)[32], int c) {
             uint32_t pk[16];
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
@@ -222,13 +244,27 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
               pk[j >> 1] = pack_bf16(e0, e1);
             }
             tmem_st16(lane_addr + (c >> 1), pk);            // P columns [c/2, c/2+16) trail the S read frontier
+          };
+          tmem_ld32(lane_addr, ra);
+#pragma unroll
+          for (int c = 0; c < ATT_T; c += 64) {
+            tmem_ld_wait();
+            tmem_ld32(lane_addr + c + 32, rb);              // S columns ahead of every P column written so far
+            exp_chunk(ra, c);
+            tmem_ld_wait();
+            if (c + 64 < ATT_T) tmem_ld32(lane_addr + c + 64, ra);
+            exp_chunk(rb, c + 32);
           }
           tmem_st_wait();
         }
         tc_fence_before_sync();
         mbar_arrive(bar_p);
+        w_sm += clock64() - c0;
 
+        c0 = clock64();
         mbar_wait(bar_o, par);
+        w_o += clock64() - c0;
+        c0 = clock64();
         tc_fence_after_sync();
         constexpr int OCH = HD / 16;                        // 16-column chunks of O
         uint32_t o[OCH][16];
@@ -240,8 +276,11 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
         tc_fence_before_sync();
         mbar_arrive(bar_e);                                 // O is in registers: the next MMA may overwrite it
         if (live_warp) {
+          // O rows -> this warp's smem staging (row pitch hd*2+16 B: conflict-free), then the warp writes its 32 rows
+          // with consecutive lanes on consecutive 16-byte chunks of a row (full 128-byte lines instead of 32 rows per store).
           const float inv = 1.0f / sum;
-          __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * ATT_T + token) * p.dim + h * HD;
+          uint8_t* stage = sOut + quarter * 32 * Cfg::OUT_PITCH;
+          uint8_t* srow = stage + lane * Cfg::OUT_PITCH;
 #pragma unroll
           for (int q = 0; q < OCH; ++q) {
 #pragma unroll
@@ -251,17 +290,33 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
               w.y = pack_bf16(__uint_as_float(o[q][8 * v + 2]) * inv, __uint_as_float(o[q][8 * v + 3]) * inv);
               w.z = pack_bf16(__uint_as_float(o[q][8 * v + 4]) * inv, __uint_as_float(o[q][8 * v + 5]) * inv);
               w.w = pack_bf16(__uint_as_float(o[q][8 * v + 6]) * inv, __uint_as_float(o[q][8 * v + 7]) * inv);
-              *reinterpret_cast<uint4*>(orow + 16 * q + 8 * v) = w;
+              *reinterpret_cast<uint4*>(srow + 32 * q + 16 * v) = w;
             }
           }
+          __syncwarp();
+          constexpr int CPR = HD / 8;                       // 16-byte chunks per row
+          const int token0 = token - lane;                  // token of this warp's row 0 (rows are consecutive tokens)
+          __nv_bfloat16* obase = p.out + (static_cast<size_t>(b) * ATT_T + token0) * p.dim + h * HD;
+#pragma unroll
+          for (int i = lane; i < 32 * CPR; i += 32) {
+            const int rr = i / CPR, ch = i % CPR;
+            const uint4 w = *reinterpret_cast<const uint4*>(stage + rr * Cfg::OUT_PITCH + ch * 16);
+            *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * p.dim + ch * 8) = w;
+          }
+          __syncwarp();                                     // staging is reused by this warp's next tile
         }
+        w_ep += clock64() - c0;
       }
+    }
+    if (p.dbg && threadIdx.x == 0) {
+      p.dbg[blockIdx.x * 8 + 1] = w_s; p.dbg[blockIdx.x * 8 + 2] = w_sm; p.dbg[blockIdx.x * 8 + 3] = w_o; p.dbg[blockIdx.x * 8 + 4] = w_ep;
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 4) tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 0] = clock64() - t_cta0;
 }
 
 }  // namespace vpb

@@ -93,6 +93,9 @@ static int make_map_nhwc(CUtensorMap* m, const void* base, uint64_t B, uint64_t 
   return VPB_OK;
 }
 
+static int g_dbg_stages = 0, g_dbg_flags = 0;      // debug knobs set by vpb_debug_gemm
+static long long* g_dbg_buf = nullptr;
+
 // ------------------------------------------------------------------------------------------------ launches
 // Every kernel of the chain is launched with programmatic stream serialization (see ptx.cuh: pdl_wait).
 static bool g_pdl = true;
@@ -476,8 +479,6 @@ static int layernorm(const float* x, const float* g, const float* b, __nv_bfloat
   return VPB_OK;
 }
 
-static int g_dbg_stages = 0, g_dbg_flags = 0;
-static long long* g_dbg_buf = nullptr;
 extern "C" int vpb_debug_gemm(int32_t stages_limit, void* d_counters) {   // counters: int64 [grid*8], see GemmParams::dbg
   g_dbg_flags = stages_limit >> 8;       // bits 8.. carry GemmParams::dbg_flags
   g_dbg_stages = stages_limit & 0xff;
@@ -522,7 +523,7 @@ static int backbone(vpb_engine* e, const float* d_crops, int B, cudaStream_t st)
     if (stop == 4) return VPB_OK;
     {
       AttnParams ap;
-      ap.batch = B; ap.heads = e->heads; ap.dim = D; ap.out = e->attn;
+      ap.batch = B; ap.heads = e->heads; ap.dim = D; ap.out = e->attn; ap.dbg = nullptr;
       e->prof.begin(KC_ATTN, st);
       VPB_TRY(attention_launch(D / e->heads, e->m_qkv_att, e->m_qkv_att_tail, ap, st));
       e->prof.end(st);
@@ -784,7 +785,7 @@ extern "C" int vpb_attention(const void* d_qkv, int32_t batch, int32_t heads, in
   CUtensorMap tm, tt;
   VPB_TRY(make_attn_maps(&tm, &tt, d_qkv, static_cast<uint64_t>(batch) * 192, D, head_dim));
   AttnParams ap;
-  ap.batch = batch; ap.heads = heads; ap.dim = D; ap.out = reinterpret_cast<__nv_bfloat16*>(d_out);
+  ap.batch = batch; ap.heads = heads; ap.dim = D; ap.out = reinterpret_cast<__nv_bfloat16*>(d_out); ap.dbg = g_dbg_buf;
   return attention_launch(head_dim, tm, tt, ap, static_cast<cudaStream_t>(stream));
 }
 

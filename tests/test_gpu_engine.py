@@ -114,3 +114,29 @@ def test_errors_are_loud():
         m(torch.zeros(3, 3, 256, 192, device="cuda"))                # > max_batch
     with pytest.raises(ValueError):
         m(torch.zeros(1, 3, 224, 224, device="cuda"))
+
+
+def test_ragged_video_stream_batches():
+    """BASELINE configs[4]: ViT-B AP-10k (K=17), a stream of frames each with its own number of crops and crop sizes.
+    Every frame's keypoints must equal the oracle decode of the engine's heatmaps for that frame, and must not depend on
+    what the previous frame was (the workspace is reused)."""
+    from easy_vitpose_b200 import ViTPose, dyn_model_import
+    m = ViTPose(dyn_model_import("ap10k", "b"), max_batch=32)
+    sd = O.make_state_dict(768, 12, 17, 4321, peaky=0.1, bumps=True)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}).to("cuda:0")
+    rs = np.random.RandomState(7)
+    counts = np.clip(rs.poisson(6, size=6), 1, 32)
+    first = None
+    for f, n in enumerate(counts):
+        x = torch.from_numpy(O.make_crops(int(n), 900 + f)).cuda()
+        org = np.stack([rs.randint(64, 513, size=n), rs.randint(64, 513, size=n)], 1).astype(np.int32)
+        kp, idx, hm = m.infer_crops(x, torch.from_numpy(org), return_heatmaps=True)
+        hm = hm.cpu().numpy()
+        okp, oidx = O.decode_maps(hm, org, wrap="crop")
+        assert np.array_equal(idx.cpu().numpy(), oidx)
+        vis = okp[..., 2] > 0.3
+        assert np.abs(kp.cpu().numpy() - okp)[vis].max() < 5e-3 * max(1.0, org.max() / 48.0)
+        if f == 0:
+            first = (x, org, kp.cpu().numpy())
+    kp_again, _ = m.infer_crops(first[0], torch.from_numpy(first[1]))
+    assert np.array_equal(kp_again.cpu().numpy(), first[2])

@@ -62,3 +62,18 @@ def test_live_reference_decode_matches_oracle():
         kp, _ = O.decode_maps(maps[i:i + 1], np.array([[200 + i, 300 + i]]), wrap="crop")
         assert np.array_equal(kp[..., 2], ref[..., 2])
         assert np.abs(kp - ref).max() < 1e-3 + 1e-3 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("name", ["s_coco", "b_coco"])
+def test_torch_restatement_matches_reference(golden_dir, name):
+    """oracle/torch_ref.py (the torch-ops restatement bench.py times as the CPU / torch-CUDA baselines) against the
+    reference outputs: same library ops as the reference modules -> agreement to fp32 round-off."""
+    import torch
+
+    from oracle import torch_ref as T
+    g = _load(golden_dir, "fwd_" + name)
+    D, depth, heads, K, B, wseed, xseed = (int(v) for v in g["meta"])
+    sd = T.to_device(O.make_state_dict(D, depth, K, wseed, peaky=float(g["peaky"]), bumps=True), "cpu", torch.float32)
+    with torch.no_grad():
+        hm = T.forward(torch.from_numpy(O.make_crops(B, xseed)), sd, depth, heads).numpy()
+    assert np.abs(hm - g["heatmaps"]).max() < 1e-5 * np.abs(g["heatmaps"]).max()

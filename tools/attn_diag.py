@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""Where the attention kernel's threads spend their cycles (AttnParams::dbg counters)."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import ctypes as C
+import torch
+from easy_vitpose_b200 import _lib
+from gpu_util import attention
+
+dev = torch.device("cuda", 0)
+L = _lib.lib()
+for heads, hd, B in ((12, 64, 64), (16, 80, 32), (12, 32, 64)):
+    D = heads * hd
+    qkv = (torch.randn(B * 192, 3 * D, device=dev) * 0.5).bfloat16()
+    for _ in range(3):
+        attention(qkv, B, heads, hd)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = torch.empty((B * 192, D), dtype=torch.bfloat16, device=dev)
+    e0.record()
+    for _ in range(10):
+        _lib.check(L.vpb_attention(C.c_void_p(qkv.data_ptr()), B, heads, hd, C.c_void_p(out.data_ptr()), None))
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 100
+    n = min(B * heads, 296)
+    dbg = torch.zeros(n * 8, dtype=torch.int64, device=dev)
+    L.vpb_debug_gemm(0, C.c_void_p(dbg.data_ptr()))
+    attention(qkv, B, heads, hd)
+    L.vpb_debug_gemm(0, None)
+    m = dbg.cpu().reshape(n, 8).double().mean(0)
+    steps = 2 * B * heads / n
+    print(f"hd={hd} B={B} heads={heads}: {us:.1f} us/launch; per CTA: lifetime {m[0]:.0f} cyc, {steps:.1f} tile steps -> {m[0]/steps:.0f} cyc/step")
+    print(f"   worker0: wait S {m[1]/steps:.0f}  softmax {m[2]/steps:.0f}  wait O {m[3]/steps:.0f}  epilogue {m[4]/steps:.0f}   | ctl: wait P {m[5]/steps:.0f}  wait O {m[6]/steps:.0f}  wait loads {m[7]/steps:.0f}  (cycles per tile step)")
