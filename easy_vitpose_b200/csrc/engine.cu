@@ -236,6 +236,15 @@ struct vpb_engine {
   bool finalized = false;
   int stop_after = 0;
   Profiler prof;
+  // CUDA-graph replay of the kernel chain behind the patch gather, one graph per batch size: removes ~90 launches of CPU
+  // work per call, which is what bounds small ragged batches (video streams).  The graph only touches engine-owned
+  // memory (the caller's crops are consumed by the eagerly launched patch_im2col; org_wh / keypoints / argmax / heatmaps
+  // move by small device copies), so it is valid for any caller pointers.  Captured on a batch size's second use.
+  struct GraphEntry { int batch; int seen; cudaGraphExec_t exec; };
+  std::vector<GraphEntry> graphs;
+  bool use_graph = true;
+  float* g_kpts = nullptr;      // graph-owned outputs / decode inputs: the captured chain only touches engine memory
+  int32_t *g_idx = nullptr, *g_org = nullptr;
   std::map<std::string, std::pair<float*, int64_t>> staged;   // fp32 state_dict tensors on device until finalize
   std::vector<void*> allocs;
   // packed weights
@@ -321,6 +330,7 @@ extern "C" void vpb_destroy(vpb_engine* e) {
   if (!e) return;
   for (auto& kv : e->staged) cudaFree(kv.second.first);
   for (void* p : e->allocs) cudaFree(p);
+  for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (int s = 0; s < 2; ++s) {
     if (e->ev_h2d[s]) cudaEventDestroy(e->ev_h2d[s]);
     if (e->ev_done[s]) cudaEventDestroy(e->ev_done[s]);
@@ -442,6 +452,9 @@ extern "C" int vpb_finalize(vpb_engine* e) {
     CU_TRY(cudaEventCreateWithFlags(&e->ev_h2d[s], cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&e->ev_done[s], cudaEventDisableTiming));
   }
+  VPB_TRY(dev_alloc(e, &e->g_kpts, B * e->K * 3));
+  VPB_TRY(dev_alloc(e, &e->g_idx, B * e->K));
+  VPB_TRY(dev_alloc(e, &e->g_org, B * 2));
   CU_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   CU_TRY(cudaStreamCreateWithFlags(&e->compute_stream, cudaStreamNonBlocking));
   VPB_TRY(make_map(&e->m_patch_rows, e->patch_rows, M, 768, 768, 128));
@@ -495,13 +508,16 @@ static GemmParams gp(int M, int N, int K, const float* bias, void* out, int ldc)
 
 // stop_after stages (debug): 1 patch rows, 2 patch embed, 3 first LN, 4 first qkv, 5 first attention, 6 first proj,
 // 7 first fc1, 8 first block, 9 all blocks, 10 last norm, 11 deconv1, 12 deconv2
-static int backbone(vpb_engine* e, const float* d_crops, int B, cudaStream_t st) {
+static int patch_gather(vpb_engine* e, const float* d_crops, int B, cudaStream_t st) {
+  e->prof.begin(KC_PATCH_IM2COL, st);
+  CU_TRY(launch_k(patch_im2col, dim3(cdiv(static_cast<long long>(B) * 3 * 256 * 24, 256)), dim3(256), 0, st, d_crops, e->patch_rows, B));
+  e->prof.end(st);
+  return VPB_OK;
+}
+// everything after the patch gather, up to last_norm
+static int backbone(vpb_engine* e, int B, cudaStream_t st) {
   const int D = e->D, M = B * 192;
   const int stop = e->stop_after;
-  e->prof.begin(KC_PATCH_IM2COL, st);
-  launch_k(patch_im2col, dim3(cdiv(static_cast<long long>(B) * 3 * 256 * 24, 256)), dim3(256), 0, st, d_crops, e->patch_rows, B);
-  e->prof.end(st);
-  CU_TRY(cudaGetLastError());
   if (stop == 1) return VPB_OK;
   {  // tokens = rows * Wpatch^T + (pos_embed[1+t] + pos_embed[0] + conv bias)
     GemmParams p = gp(M, D, 768, nullptr, e->x, D);
@@ -598,7 +614,8 @@ extern "C" int vpb_forward(vpb_engine* e, const float* d_crops, int32_t batch, f
   VPB_TRY(check_ready(e, batch));
   if (!d_crops || !d_heatmaps) return fail(VPB_ERR_ARG, "vpb_forward: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  VPB_TRY(backbone(e, d_crops, batch, st));
+  VPB_TRY(patch_gather(e, d_crops, batch, st));
+  VPB_TRY(backbone(e, batch, st));
   if (e->stop_after && e->stop_after <= 10) return VPB_OK;
   return head(e, batch, d_heatmaps, st);
 }
@@ -607,7 +624,8 @@ extern "C" int vpb_forward_features(vpb_engine* e, const float* d_crops, int32_t
   VPB_TRY(check_ready(e, batch));
   if (!d_crops || !d_features) return fail(VPB_ERR_ARG, "vpb_forward_features: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  VPB_TRY(backbone(e, d_crops, batch, st));
+  VPB_TRY(patch_gather(e, d_crops, batch, st));
+  VPB_TRY(backbone(e, batch, st));
   const long long tot = static_cast<long long>(batch) * e->D * 192;
   tokens_to_nchw<<<cdiv(tot, 256), 256, 0, st>>>(e->xn, d_features, batch, e->D);
   CU_TRY(cudaGetLastError());
@@ -626,16 +644,51 @@ extern "C" int vpb_decode(const float* d_heatmaps, int32_t n, int32_t k, const i
   return VPB_OK;
 }
 
-extern "C" int vpb_infer(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, int32_t batch, float* d_kpts, int32_t* d_idx,
-                         float* d_heatmaps, void* stream) {
-  VPB_TRY(check_ready(e, batch));
-  if (!d_crops || !d_org_wh || !d_kpts) return fail(VPB_ERR_ARG, "vpb_infer: null pointer");
-  float* heat = d_heatmaps ? d_heatmaps : e->heat;
+static int infer_enqueue(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, int32_t batch, float* d_kpts, int32_t* d_idx,
+                         float* heat, void* stream) {
   VPB_TRY(vpb_forward(e, d_crops, batch, heat, stream));
   if (e->stop_after) return VPB_OK;
   e->prof.begin(KC_DECODE, static_cast<cudaStream_t>(stream));
   VPB_TRY(vpb_decode(heat, batch, e->K, d_org_wh, d_kpts, d_idx, 0, stream));
   e->prof.end(static_cast<cudaStream_t>(stream));
+  return VPB_OK;
+}
+
+extern "C" int vpb_infer(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, int32_t batch, float* d_kpts, int32_t* d_idx,
+                         float* d_heatmaps, void* stream) {
+  VPB_TRY(check_ready(e, batch));
+  if (!d_crops || !d_org_wh || !d_kpts) return fail(VPB_ERR_ARG, "vpb_infer: null pointer");
+  float* heat = d_heatmaps ? d_heatmaps : e->heat;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!e->use_graph || e->prof.on || e->stop_after || st == nullptr)      // the legacy default stream cannot be captured
+    return infer_enqueue(e, d_crops, d_org_wh, batch, d_kpts, d_idx, heat, stream);
+  vpb_engine::GraphEntry* g = nullptr;
+  for (auto& c : e->graphs)
+    if (c.batch == batch) g = &c;
+  if (!g) {                                                               // first use of this batch size: run eagerly
+    e->graphs.push_back({batch, 1, nullptr});
+    return infer_enqueue(e, d_crops, d_org_wh, batch, d_kpts, d_idx, heat, stream);
+  }
+  VPB_TRY(patch_gather(e, d_crops, batch, st));
+  CU_TRY(cudaMemcpyAsync(e->g_org, d_org_wh, static_cast<size_t>(batch) * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  if (!g->exec) {                                                         // second use: capture, instantiate
+    cudaGraph_t graph = nullptr;
+    CU_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = backbone(e, batch, st);
+    if (rc == VPB_OK) rc = head(e, batch, e->heat, st);
+    if (rc == VPB_OK) rc = vpb_decode(e->heat, batch, e->K, e->g_org, e->g_kpts, e->g_idx, 0, stream);
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != VPB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(VPB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&g->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { g->exec = nullptr; return fail(VPB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ie)); }
+  }
+  CU_TRY(cudaGraphLaunch(g->exec, st));
+  CU_TRY(cudaMemcpyAsync(d_kpts, e->g_kpts, static_cast<size_t>(batch) * e->K * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (d_idx) CU_TRY(cudaMemcpyAsync(d_idx, e->g_idx, static_cast<size_t>(batch) * e->K * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  if (d_heatmaps)
+    CU_TRY(cudaMemcpyAsync(d_heatmaps, e->heat, static_cast<size_t>(batch) * e->K * 3072 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return VPB_OK;
 }
 
@@ -700,6 +753,7 @@ extern "C" int vpb_set_option(vpb_engine* e, const char* name, int32_t value) {
   if (!strcmp(name, "stop_after")) e->stop_after = value;
   else if (!strcmp(name, "profile")) e->prof.on = value != 0;
   else if (!strcmp(name, "pdl")) g_pdl = value != 0;
+  else if (!strcmp(name, "graph")) e->use_graph = value != 0;
   else return fail(VPB_ERR_ARG, "unknown option %s", name);
   return VPB_OK;
 }

@@ -75,6 +75,7 @@ class ViTPose:
         self._loaded = False
         self._state: "OrderedDict[str, torch.Tensor] | None" = None
         self._device = None
+        self._side = None
         if device is not None:
             self.to(device)
 
@@ -212,9 +213,24 @@ class ViTPose:
         idx = torch.empty((B, self.num_keypoints), dtype=torch.int32, device=x.device)
         hm = torch.empty((B, self.num_keypoints, HM_H, HM_W), dtype=torch.float32, device=x.device) if return_heatmaps else None
         with torch.cuda.device(self._device):
+            cur = torch.cuda.current_stream(self._device)
+            if cur.cuda_stream == 0:
+                # the legacy default stream cannot be captured into a CUDA graph: run the engine on a side stream that is
+                # ordered after / before the caller's stream (two event waits), so small batches get graph replay
+                if self._side is None:
+                    self._side = torch.cuda.Stream(self._device)
+                self._side.wait_stream(cur)
+                for t in (x, org, kp, idx, hm):
+                    if t is not None:
+                        t.record_stream(self._side)
+                st = C.c_void_p(self._side.cuda_stream)
+            else:
+                st = C.c_void_p(cur.cuda_stream)
             _lib.check(_lib.lib().vpb_infer(self._handle, C.c_void_p(x.data_ptr()), C.c_void_p(org.data_ptr()), B,
                                             C.c_void_p(kp.data_ptr()), C.c_void_p(idx.data_ptr()),
-                                            C.c_void_p(hm.data_ptr()) if hm is not None else None, self._stream()))
+                                            C.c_void_p(hm.data_ptr()) if hm is not None else None, st))
+            if cur.cuda_stream == 0:
+                cur.wait_stream(self._side)
         return (kp, idx, hm) if return_heatmaps else (kp, idx)
 
     def infer_host(self, crops: np.ndarray, org_wh: np.ndarray, kpts_out: np.ndarray | None = None,
