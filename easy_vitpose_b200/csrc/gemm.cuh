@@ -47,6 +47,14 @@ struct GemmParams {
   int up_h, up_w;         // EPI_BF16_RELU_UP: input grid (H, W); W * up_tr == 96 rows per M tile
   int up_tr;              // EPI_BF16_RELU_UP: image rows per M tile
   int up_c;               // EPI_BF16_RELU_UP: input channels (K = 4 taps * up_c)
+  // Fused LayerNorm tail (EPI_F32_ADD / EPI_F32_RESID, ln_out != nullptr): the CTA that completes the LAST column tile of a
+  // 128-row block of the fp32 stream (atomic counter per block) normalises those rows out of L2 and writes the bf16 rows
+  // the next GEMM consumes -- no separate LayerNorm launch, no second trip of x through HBM.
+  const float* ln_gamma;  // [N]
+  const float* ln_beta;   // [N]
+  __nv_bfloat16* ln_out;  // [M, N] or nullptr
+  int* ln_counters;       // [ceil(M/128)] zero before the first launch; the last arriver resets its entry
+  float ln_eps;
   int stages_limit;       // debug: use at most this many ring stages (0 = all)
   int dbg_flags;          // debug (results become wrong!): 1 = every pair loads the SAME A rows, 2 = the same W rows
                           //        (probes whether L2 reads or SM-side delivery bound the loop); 4 = m-fastest tile order
@@ -90,6 +98,43 @@ __device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + 
 __device__ __forceinline__ float gelu_fast(float x) { return gelu_tanh_fit(x); }
 #endif
 
+// One warp normalises one row of the fp32 stream (D = 128*V columns) straight out of L2 (ld.global.cg: the row was just
+// written by other SMs' TMA reduce-adds / stores) -> bf16.  nn.LayerNorm(eps), biased variance (backbone/vit.py:190,198,304).
+template <int V>
+__device__ __forceinline__ void ln_row_l2(const float* __restrict__ xrow, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                          __nv_bfloat16* __restrict__ yrow, float eps, int lane) {
+  constexpr int D = 128 * V;
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = __ldcg(reinterpret_cast<const float4*>(xrow) + i * 32 + lane);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.0f / D) + eps);
+  uint2* yr = reinterpret_cast<uint2*>(yrow);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+    uint2 o;
+    o.x = pack_bf16(v[i].x * rstd * g.x + b.x, v[i].y * rstd * g.y + b.y);
+    o.y = pack_bf16(v[i].z * rstd * g.z + b.z, v[i].w * rstd * g.w + b.w);
+    yr[i * 32 + lane] = o;
+  }
+}
+
 template <int BN, int EPI>
 __global__ void __cluster_dims__(GEMM_CL, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
@@ -104,6 +149,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* acc_full = empty_bar + Cfg::STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;               // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  volatile int* ln_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);   // "this CTA finishes the row block" broadcast
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -366,6 +412,43 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);   // the leader's MMA thread waits for both CTAs' epilogues
+
+      if constexpr (EPI == EPI_F32_ADD || EPI == EPI_F32_RESID) {
+        if (p.ln_out != nullptr && mt < num_m) {
+          // ---- fused LayerNorm tail
+          if constexpr (EPI == EPI_F32_ADD) {
+            if (lane == 0) tma_store_wait_all<0>();         // this warp's reduce-adds have been performed in L2
+          } else {
+            __threadfence();                                // this thread's stores are visible device-wide
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");    // all 8 epilogue warps of this CTA are done with the tile
+          if (threadIdx.x == 0) {
+            __threadfence();
+            const int old = atomicAdd(p.ln_counters + mt, 1);
+            const int last = (old == num_n - 1);
+            if (last) p.ln_counters[mt] = 0;                // every column tile has arrived: reset for the next launch
+            *ln_flag = last;
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (*ln_flag) {
+            __threadfence();                                // acquire side of the counter hand-off
+            const int r_end = min(GEMM_BM, p.M - m0);
+            const float* xb = reinterpret_cast<const float*>(p.out) + static_cast<size_t>(m0) * p.N;
+            __nv_bfloat16* yb = p.ln_out + static_cast<size_t>(m0) * p.N;
+            for (int r = ew; r < r_end; r += GEMM_EPI_WARPS) {
+              const float* xr = xb + static_cast<size_t>(r) * p.N;
+              __nv_bfloat16* yr = yb + static_cast<size_t>(r) * p.N;
+              switch (p.N) {
+                case 384: ln_row_l2<3>(xr, p.ln_gamma, p.ln_beta, yr, p.ln_eps, lane); break;
+                case 768: ln_row_l2<6>(xr, p.ln_gamma, p.ln_beta, yr, p.ln_eps, lane); break;
+                case 1024: ln_row_l2<8>(xr, p.ln_gamma, p.ln_beta, yr, p.ln_eps, lane); break;
+                default: ln_row_l2<10>(xr, p.ln_gamma, p.ln_beta, yr, p.ln_eps, lane); break;   // 1280
+              }
+            }
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");    // ln_flag is rewritten at the next tile
+        }
+      }
     }
     if constexpr (epi_uses_tma(EPI)) {
       if (lane == 0) tma_store_wait_all<0>();         // staging must stay alive until the last store has drained

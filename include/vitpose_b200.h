@@ -88,7 +88,7 @@ void vpb_host_free(void* p);
 
 /* Introspection used by bench.py / tests. */
 int vpb_kernel_launches(const vpb_engine* e, int32_t batch);          /* kernels one vpb_infer enqueues */
-int vpb_set_option(vpb_engine* e, const char* name, int32_t value);   /* "stop_after", "profile", "pdl", "graph" */
+int vpb_set_option(vpb_engine* e, const char* name, int32_t value);   /* "stop_after", "profile", "pdl", "graph", "ln_fused" */
 /* With option "profile"=1 every launch is bracketed by a CUDA-event pair on its stream; collect() synchronises,
  * sums elapsed ms and launch counts per kernel class (arrays of vpb_profile_classes() entries) and resets. */
 int vpb_profile_classes(void);

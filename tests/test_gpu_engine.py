@@ -140,3 +140,19 @@ def test_ragged_video_stream_batches():
             first = (x, org, kp.cpu().numpy())
     kp_again, _ = m.infer_crops(first[0], torch.from_numpy(first[1]))
     assert np.array_equal(kp_again.cpu().numpy(), first[2])
+
+
+def test_fused_layernorm_tail_is_bit_identical(golden_dir):
+    """LayerNorm fused into the tail of the residual GEMMs (last-arriving column tile of a row block normalises it) against
+    the standalone LayerNorm kernel: same arithmetic order -> identical heatmaps, for a full and a ragged batch."""
+    g = np.load(os.path.join(golden_dir, "fwd_b_coco.npz"))
+    m, _ = _engine(g, max_batch=5)
+    x = torch.from_numpy(O.make_crops(5, 321)).cuda()
+    outs = {}
+    for fused in (1, 0, 1):
+        m.set_option("ln_fused", fused)
+        outs.setdefault(fused, []).append((m(x).cpu().numpy(), m(x[:3]).cpu().numpy()))
+    for a, b in zip(outs[1][0], outs[0][0]):
+        assert np.array_equal(a, b)
+    for a, b in zip(outs[1][0], outs[1][1]):
+        assert np.array_equal(a, b)                                  # counters were reset: a second fused run repeats exactly
