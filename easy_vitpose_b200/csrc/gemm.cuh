@@ -451,7 +451,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
     if constexpr (epi_uses_tma(EPI)) {
-      if (lane == 0) tma_store_wait_all<0>();         // staging must stay alive until the last store has drained
+      if (lane == 0) tma_store_wait_read<0>();        // staging must stay alive until the TMA engine has read it; the
+                                                      // writes themselves complete before the grid does
     }
     if (p.dbg && warp == 0 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 6] = t_wfull; }
   }
