@@ -57,7 +57,6 @@ __global__ void __launch_bounds__(256) decode_heatmaps(const DecodeParams p) {
   int bi = 0x7fffffff;
   {
     const float4* h4 = reinterpret_cast<const float4*>(hm);
-    bool have = false;
 #pragma unroll 6
     for (int j = 0; j < HM_PIX / 128; ++j) {
       const float4 v = __ldg(h4 + j * 32 + lane);
@@ -65,7 +64,7 @@ __global__ void __launch_bounds__(256) decode_heatmaps(const DecodeParams p) {
       const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        if (!have || arg_better(vv[e], base + e, bv, bi)) { bv = vv[e]; bi = base + e; have = true; }
+        if (arg_better(vv[e], base + e, bv, bi)) { bv = vv[e]; bi = base + e; }   // bi starts at INT_MAX: the first element always wins
       }
     }
   }

@@ -77,13 +77,13 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
   return VPB_OK;
 }
 
-// bf16 NHWC feature map [B,H,W,C] as a 4-D tensor (C, W, H, B); box = 64 channels x W x box_h rows x 1 image, 128B-swizzled:
+// bf16 NHWC feature map [B,H,W,C] as a 4-D tensor (C, W, H, B); box = 64 channels x box_w x box_h positions x 1 image, 128B-swizzled:
 // the A operand of the implicit-GEMM deconv (shifted boxes, zero fill outside the map).
-static int make_map_nhwc(CUtensorMap* m, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t box_h) {
+static int make_map_nhwc(CUtensorMap* m, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t box_h, uint32_t box_w) {
   VPB_TRY(load_driver_api());
   cuuint64_t dims[4] = {C, W, H, B};
   cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(W), box_h, 1};
+  cuuint32_t box[4] = {64, box_w, box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -128,7 +128,7 @@ static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, const CUt
     attr = true;
   }
   const bool deconv = (EPI == EPI_BF16_RELU_UP);
-  const int num_m = deconv ? p.M / 96 : (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int num_m = deconv ? p.M / (p.up_tr * p.up_tw) : (p.M + GEMM_BM - 1) / GEMM_BM;
   const int pairs = ((num_m + GEMM_CL - 1) / GEMM_CL) * (deconv ? 4 : (p.N + BN - 1) / BN);
   const int max_clusters = g_num_sms / GEMM_CL;
   const int grid = GEMM_CL * (pairs < max_clusters ? pairs : max_clusters);
@@ -144,7 +144,6 @@ static int gemm_launch(int bn, int epi, const CUtensorMap& ta, const CUtensorMap
   VPB_CASE(256, EPI_BF16) VPB_CASE(128, EPI_BF16)
   VPB_CASE(256, EPI_BF16_GELU) VPB_CASE(128, EPI_BF16_GELU)
   VPB_CASE(256, EPI_F32_ADD) VPB_CASE(128, EPI_F32_ADD)
-  VPB_CASE(256, EPI_F32_RESID) VPB_CASE(128, EPI_F32_RESID)
   VPB_CASE(256, EPI_BF16_RELU_UP)
   VPB_CASE(32, EPI_F32_NCHW) VPB_CASE(144, EPI_F32_NCHW)
 #undef VPB_CASE
@@ -468,8 +467,8 @@ extern "C" int vpb_finalize(vpb_engine* e) {
   VPB_TRY(make_map(&e->m_xn, e->xn, M, D, D, 128));
   VPB_TRY(make_map(&e->m_attn, e->attn, M, D, D, 128));
   VPB_TRY(make_map(&e->m_hid, e->hid, M, 4 * D, 4 * D, 128));
-  VPB_TRY(make_map_nhwc(&e->m_feat_nhwc, e->xn, B, 16, 12, D, 8));     // 8 rows x 12 = 96 positions per M tile
-  VPB_TRY(make_map_nhwc(&e->m_d1_nhwc, e->d1, B, 32, 24, 256, 4));    // 4 rows x 24 = 96 positions per M tile
+  VPB_TRY(make_map_nhwc(&e->m_feat_nhwc, e->xn, B, 16, 12, D, 8, 12));   // 8 x 12 = 96 positions per M tile (12 is not a multiple of 8)
+  VPB_TRY(make_map_nhwc(&e->m_d1_nhwc, e->d1, B, 32, 24, 256, 16, 8));  // 16 x 8 = 128 positions per M tile: full UMMA tiles
   VPB_TRY(make_map(&e->m_d2, e->d2, B * 3072, 256, 256, 128));
   VPB_TRY(make_attn_maps(&e->m_qkv_att, &e->m_qkv_att_tail, e->qkv, M, D, D / e->heads));
   VPB_TRY(make_map(&e->o_qkv, e->qkv, M, 3 * D, 3 * D, 32));
@@ -517,7 +516,8 @@ static GemmParams gp(int M, int N, int K, const float* bias, void* out, int ldc)
 // 7 first fc1, 8 first block, 9 all blocks, 10 last norm, 11 deconv1, 12 deconv2
 static int patch_gather(vpb_engine* e, const float* d_crops, int B, cudaStream_t st) {
   e->prof.begin(KC_PATCH_IM2COL, st);
-  CU_TRY(launch_k(patch_im2col, dim3(cdiv(static_cast<long long>(B) * 3 * 256 * 24, 256)), dim3(256), 0, st, d_crops, e->patch_rows, B));
+  CU_TRY(launch_k(patch_im2col, dim3(cdiv(static_cast<long long>(B) * 3 * 256 * 24, 256)), dim3(256), 0, st, d_crops, e->patch_rows, B,
+                  reinterpret_cast<const float4*>(e->pos_bias), reinterpret_cast<float4*>(e->x), e->D));
   e->prof.end(st);
   return VPB_OK;
 }
@@ -538,12 +538,11 @@ static int backbone(vpb_engine* e, int B, cudaStream_t st) {
     e->prof.end(st);
     return VPB_OK;
   };
-  {  // tokens = rows * Wpatch^T + (pos_embed[1+t] + pos_embed[0] + conv bias)   [+ norm1 of block 0]
-    GemmParams p = gp(M, D, 768, nullptr, e->x, D);
-    p.resid = e->pos_bias; p.resid_mod = 192;
+  {  // tokens += rows * Wpatch^T; the stream was seeded with pos_embed[1+t] + pos_embed[0] + conv bias by the gather
+    GemmParams p = gp(M, D, 768, e->patch.b, e->x, D);   // patch.b is a zero vector (the conv bias lives in pos_bias)
     fuse_ln(p, e->blocks[0].ln1_g, e->blocks[0].ln1_b);
     e->prof.begin(KC_GEMM_PATCH, st);
-    VPB_TRY(gemm_launch(e->patch.bn, EPI_F32_RESID, e->m_patch_rows, e->patch.map, e->m_patch_rows, p, st));
+    VPB_TRY(gemm_launch(e->patch.bn, EPI_F32_ADD, e->m_patch_rows, e->patch.map, e->o_x, p, st));
     e->prof.end(st);
   }
   if (stop == 2) return VPB_OK;
@@ -595,7 +594,7 @@ static int head(vpb_engine* e, int B, float* d_heat, cudaStream_t st) {
   const int stop = e->stop_after;
   {  // deconv 1: tokens as NHWC 16x12xD -> d1 NHWC 32x24x256, all four sub-pixel phases in one implicit-GEMM launch
     GemmParams p = gp(B * 192, 256, 4 * D, e->dc1.b, e->d1, 256);
-    p.up_h = 16; p.up_w = 12; p.up_tr = 8; p.up_c = D;
+    p.up_h = 16; p.up_w = 12; p.up_tr = 8; p.up_tw = 12; p.up_c = D;
     e->prof.begin(KC_GEMM_DECONV, st);
     VPB_TRY(gemm_launch(256, EPI_BF16_RELU_UP, e->m_feat_nhwc, e->dc1.map, e->m_xn, p, st));
     e->prof.end(st);
@@ -603,7 +602,7 @@ static int head(vpb_engine* e, int B, float* d_heat, cudaStream_t st) {
   if (stop == 11) return VPB_OK;
   {  // deconv 2: d1 -> d2 NHWC 64x48x256
     GemmParams p = gp(B * 768, 256, 1024, e->dc2.b, e->d2, 256);
-    p.up_h = 32; p.up_w = 24; p.up_tr = 4; p.up_c = 256;
+    p.up_h = 32; p.up_w = 24; p.up_tr = 16; p.up_tw = 8; p.up_c = 256;
     e->prof.begin(KC_GEMM_DECONV, st);
     VPB_TRY(gemm_launch(256, EPI_BF16_RELU_UP, e->m_d1_nhwc, e->dc2.map, e->m_xn, p, st));
     e->prof.end(st);
@@ -833,10 +832,12 @@ extern "C" int vpb_gemm(const void* d_a, const void* d_w, const float* d_bias, v
   if (epilogue == EPI_F32_NCHW && n != bn) return fail(VPB_ERR_ARG, "vpb_gemm: NCHW epilogue wants W padded to %d rows", bn);
   CUtensorMap ta, tw, tout;
   if (epilogue == EPI_BF16_RELU_UP) {
-    // d_a: NHWC input [m / (H*W), H, W, C] with H = aux0, W = aux1, rows per tile aux2 (W * aux2 == 96), C = aux3 = k / 4;
-    // d_w: the four phase matrices stacked [4*256, 4*C]
-    if (aux1 * aux2 != 96 || aux3 * 4 != k || aux0 % aux2 != 0 || m % (aux0 * aux1) != 0) return fail(VPB_ERR_ARG, "vpb_gemm: bad deconv geometry");
-    VPB_TRY(make_map_nhwc(&ta, d_a, m / (aux0 * aux1), aux0, aux1, aux3, aux2));
+    // d_a: NHWC input [m / (H*W), H, W, C] with H = aux0, W = aux1, tile = aux2 rows x (aux3 >> 16) columns (96 or 128
+    // positions), C = aux3 & 0xffff = k / 4; d_w: the four phase matrices stacked [4*256, 4*C]
+    const int tile_w = aux3 >> 16, cin = aux3 & 0xffff;
+    if ((tile_w * aux2 != 96 && tile_w * aux2 != 128) || cin * 4 != k || aux0 % aux2 != 0 || aux1 % tile_w != 0 || m % (aux0 * aux1) != 0)
+      return fail(VPB_ERR_ARG, "vpb_gemm: bad deconv geometry");
+    VPB_TRY(make_map_nhwc(&ta, d_a, m / (aux0 * aux1), aux0, aux1, cin, aux2, tile_w));
     VPB_TRY(make_map(&tw, d_w, 4 * n, k, k, bn / GEMM_CL));
   } else {
     VPB_TRY(make_map(&ta, d_a, m, k, k, 128));
@@ -846,9 +847,9 @@ extern "C" int vpb_gemm(const void* d_a, const void* d_w, const float* d_bias, v
   if (epilogue == EPI_BF16 || epilogue == EPI_BF16_GELU) VPB_TRY(make_map(&tout, d_out, m, n, n, 32));
   if (epilogue == EPI_F32_ADD) VPB_TRY(make_map(&tout, d_out, m, n, n, 32, /*f32=*/true));
   GemmParams p = gp(m, n, k, d_bias, d_out, n);
-  p.resid = d_resid; p.resid_mod = resid_mod;
+  (void)d_resid; (void)resid_mod;
   if (epilogue == EPI_F32_NCHW) { p.n_valid = aux0; p.pix = aux1; }
-  if (epilogue == EPI_BF16_RELU_UP) { p.up_h = aux0; p.up_w = aux1; p.up_tr = aux2; p.up_c = aux3; }
+  if (epilogue == EPI_BF16_RELU_UP) { p.up_h = aux0; p.up_w = aux1; p.up_tr = aux2; p.up_tw = aux3 >> 16; p.up_c = aux3 & 0xffff; }
   return gemm_launch(bn, epilogue, ta, tw, tout, p, static_cast<cudaStream_t>(stream));
 }
 

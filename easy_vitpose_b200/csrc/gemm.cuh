@@ -30,9 +30,8 @@ enum Epilogue : int {
   EPI_BF16_GELU = 1,    // out bf16 [M,ldc]   = gelu_erf(acc + bias)                    (fc1)            TMA store
   EPI_BF16_RELU_UP = 2, // implicit-GEMM deconv: A = shifted NHWC boxes (4-D TMA), all 4 sub-pixel phases in one launch,
                         // out bf16 NHWC (b,2y+py,2x+px) = relu(acc + bias)                                direct
-  EPI_F32_RESID = 3,    // out f32 [M,ldc]    = resid[row % mod] + acc + bias           (patch embed)    direct
   EPI_F32_NCHW = 4,     // out f32 [b,n,pix]  = acc + bias for n < n_valid              (1x1 conv)       direct
-  EPI_F32_ADD = 5,      // out f32 [M,ldc]   += acc + bias                              (proj, fc2)      TMA reduce-add
+  EPI_F32_ADD = 5,      // out f32 [M,ldc]   += acc + bias                 (patch embed, proj, fc2)      TMA reduce-add
 };
 
 struct GemmParams {
@@ -40,14 +39,12 @@ struct GemmParams {
   const float* bias;      // [N] (padded to the N tile) or nullptr
   void* out;              // direct epilogues only
   int ldc;                // row pitch of out in elements (direct row-major epilogues)
-  const float* resid;     // EPI_F32_RESID: residual source
-  int resid_mod;          // 0: resid row = row; >0: resid row = row % resid_mod (position embedding)
   int n_valid;            // EPI_F32_NCHW: number of real output channels
   int pix;                // EPI_F32_NCHW: pixels per image (rows per batch item)
-  int up_h, up_w;         // EPI_BF16_RELU_UP: input grid (H, W); W * up_tr == 96 rows per M tile
-  int up_tr;              // EPI_BF16_RELU_UP: image rows per M tile
+  int up_h, up_w;         // EPI_BF16_RELU_UP: input grid (H, W)
+  int up_tr, up_tw;       // EPI_BF16_RELU_UP: an M tile is a up_tr x up_tw patch of positions (96 = 8x12 or 128 = 16x8)
   int up_c;               // EPI_BF16_RELU_UP: input channels (K = 4 taps * up_c)
-  // Fused LayerNorm tail (EPI_F32_ADD / EPI_F32_RESID, ln_out != nullptr): the CTA that completes the LAST column tile of a
+  // Fused LayerNorm tail (EPI_F32_ADD, ln_out != nullptr): the CTA that completes the LAST column tile of a
   // 128-row block of the fp32 stream (atomic counter per block) normalises those rows out of L2 and writes the bf16 rows
   // the next GEMM consumes -- no separate LayerNorm launch, no second trip of x through HBM.
   const float* ln_gamma;  // [N]
@@ -157,8 +154,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int cluster = static_cast<int>(cluster_id_x());
   const int num_clusters = static_cast<int>(cluster_count_x());
   constexpr bool kDeconv = (EPI == EPI_BF16_RELU_UP);
-  // deconv: an M tile is up_tr image rows (96 positions) of one crop, p.M counts positions; the 4 phases play the n-blocks
-  const int num_m = kDeconv ? p.M / 96 : (p.M + GEMM_BM - 1) / GEMM_BM;
+  // deconv: an M tile is a up_tr x up_tw patch (96 or 128 positions) of one crop, p.M counts positions; the 4 phases play the n-blocks
+  const int up_pos = kDeconv ? p.up_tr * p.up_tw : GEMM_BM;
+  const int num_m = kDeconv ? p.M / up_pos : (p.M + GEMM_BM - 1) / GEMM_BM;
   const int num_mp = (num_m + GEMM_CL - 1) / GEMM_CL;               // m-block pairs
   const int num_n = kDeconv ? 4 : (p.N + BN - 1) / BN;
   const int num_pairs = num_mp * num_n;
@@ -205,7 +203,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int nb = (p.dbg_flags & 4) ? pair / num_mp : pair % num_n;   // n-block (deconv: sub-pixel phase)
       const int m0 = (p.dbg_flags & 1) ? cta_rank * GEMM_BM : mt * GEMM_BM;   // may lie past M: TMA zero-fills
       const int n0 = (p.dbg_flags & 2) ? 0 : nb * BN;
-      const int tiles_per_img = kDeconv ? p.up_h / p.up_tr : 1;
+      const int tiles_x = kDeconv ? p.up_w / p.up_tw : 1;
+      const int tiles_per_img = kDeconv ? (p.up_h / p.up_tr) * tiles_x : 1;
       const int kb_per_tap = kDeconv ? p.up_c / GEMM_BK : 1;
       for (int kb = 0; kb < num_kb; ++kb) {
         const long long w0 = clock64();
@@ -213,15 +212,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         t_wait += clock64() - w0;
         uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
         if constexpr (kDeconv) {
-          // A tile = 96 positions (up_tr rows x W) of the input map shifted by the tap's (dy, dx); the 4-D box is zero
-          // filled outside the map (= the transposed conv's border).  Rows 96..127 of the smem tile are never written:
-          // they only feed accumulator rows nobody stores.
+          // A tile = a up_tr x up_tw patch of the input map shifted by the tap's (dy, dx); the 4-D box is zero filled
+          // outside the map (= the transposed conv's border).  With 96-position tiles rows 96..127 of the smem tile are
+          // never written: they only feed accumulator rows nobody stores.
           const int tap = kb / kb_per_tap, c0 = (kb % kb_per_tap) * GEMM_BK;
           const int py = nb >> 1, px = nb & 1, iy = tap >> 1, ix = tap & 1;
           const int dy = py ? (iy ? 0 : 1) : (iy ? -1 : 0);
           const int dx = px ? (ix ? 0 : 1) : (ix ? -1 : 0);
-          if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], GEMM_CL * (96 * 128 + Cfg::B_SLICE));
-          tma_load_4d_pair(sa, &tmap_a, &full_bar[stage], c0, dx, (mt % tiles_per_img) * p.up_tr + dy, mt / tiles_per_img);
+          if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], GEMM_CL * (up_pos * 128 + Cfg::B_SLICE));
+          const int ti = mt % tiles_per_img;
+          tma_load_4d_pair(sa, &tmap_a, &full_bar[stage], c0, (ti % tiles_x) * p.up_tw + dx, (ti / tiles_x) * p.up_tr + dy,
+                           mt / tiles_per_img);
         } else {
           if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], GEMM_CL * Cfg::STAGE_BYTES);   // bytes of both CTAs land here
           tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
@@ -285,7 +286,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int nb = (p.dbg_flags & 4) ? pair / num_mp : pair % num_n;
       const int n0 = kDeconv ? 0 : nb * BN;
       const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = kDeconv ? (quarter * 32 + lane < 96 && mt < num_m) : (row < p.M);
+      const bool row_ok = kDeconv ? (quarter * 32 + lane < up_pos && mt < num_m) : (row < p.M);
       const long long w0 = clock64();
       mbar_wait(&acc_full[acc], acc_phase);
       t_wfull += clock64() - w0;
@@ -345,15 +346,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         // ---- direct epilogues (scattered / transposed outputs)
         size_t out_row = static_cast<size_t>(row);
         if constexpr (EPI == EPI_BF16_RELU_UP) {
-          const int tiles_per_img = p.up_h / p.up_tr;
-          const int r = quarter * 32 + lane;                              // position inside the tile (valid < 96)
-          const int b = mt / tiles_per_img;
-          const int y = (mt % tiles_per_img) * p.up_tr + r / p.up_w, x = r % p.up_w;
+          const int tiles_x = p.up_w / p.up_tw;
+          const int tiles_per_img = (p.up_h / p.up_tr) * tiles_x;
+          const int r = quarter * 32 + lane;                              // position inside the tile (valid < up_pos)
+          const int b = mt / tiles_per_img, ti = mt % tiles_per_img;
+          const int y = (ti / tiles_x) * p.up_tr + r / p.up_tw, x = (ti % tiles_x) * p.up_tw + r % p.up_tw;
           out_row = (static_cast<size_t>(b) * (2 * p.up_h) + (2 * y + (nb >> 1))) * (2 * p.up_w) + (2 * x + (nb & 1));
-        }
-        size_t res_row = static_cast<size_t>(row);
-        if constexpr (EPI == EPI_F32_RESID) {
-          if (p.resid_mod > 0) res_row = static_cast<size_t>(row % p.resid_mod);
         }
 #pragma unroll 1
         for (int c = 0; c < Cfg::HALF; c += Cfg::CH) {
@@ -385,18 +383,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 *reinterpret_cast<uint4*>(o + j) = q;
               }
             }
-          } else if constexpr (EPI == EPI_F32_RESID) {
-            if (row_ok && n < p.N) {
-              const float* rs = p.resid + res_row * p.ldc + n;
-              float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldc + n;
-#pragma unroll
-              for (int j = 0; j < Cfg::CH; j += 4) {
-                const float4 r4 = *reinterpret_cast<const float4*>(rs + j);
-                float4 w4;
-                w4.x = v[j] + r4.x; w4.y = v[j + 1] + r4.y; w4.z = v[j + 2] + r4.z; w4.w = v[j + 3] + r4.w;
-                *reinterpret_cast<float4*>(o + j) = w4;
-              }
-            }
           } else {  // EPI_F32_NCHW: a warp's 32 lanes are 32 consecutive pixels -> coalesced per channel
             if (row_ok) {
               const int b = row / p.pix, pix = row % p.pix;
@@ -413,14 +399,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);   // the leader's MMA thread waits for both CTAs' epilogues
 
-      if constexpr (EPI == EPI_F32_ADD || EPI == EPI_F32_RESID) {
+      if constexpr (EPI == EPI_F32_ADD) {
         if (p.ln_out != nullptr && mt < num_m) {
           // ---- fused LayerNorm tail
-          if constexpr (EPI == EPI_F32_ADD) {
-            if (lane == 0) tma_store_wait_all<0>();         // this warp's reduce-adds have been performed in L2
-          } else {
-            __threadfence();                                // this thread's stores are visible device-wide
-          }
+          if (lane == 0) tma_store_wait_all<0>();           // this warp's reduce-adds have been performed in L2
           asm volatile("bar.sync 2, 256;" ::: "memory");    // all 8 epilogue warps of this CTA are done with the tile
           if (threadIdx.x == 0) {
             __threadfence();

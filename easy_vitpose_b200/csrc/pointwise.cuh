@@ -58,11 +58,17 @@ __global__ void __launch_bounds__(256) layernorm_f32_to_bf16(const float* __rest
 //   row (b, py, px), col c*256 + ky*16 + kx  =  x[b, c, 16py-2+ky, 16px-2+kx]   (0 outside the image)
 // Conv2d(k16,s16,p2) geometry from backbone/vit.py:222.  One thread = 8 consecutive kx of one patch
 // row: reads 32 B of the image (8-byte aligned: columns start at -2), writes 16 B.
-__global__ void __launch_bounds__(256) patch_im2col(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int batch) {
+// The same launch seeds the fp32 token stream with  pos_embed[1+t] + pos_embed[0] + conv bias  (vit.py:382), so that the
+// patch GEMM can add its product into it with the TMA reduce-add epilogue like every other residual GEMM.
+__global__ void __launch_bounds__(256) patch_im2col(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int batch,
+                                                    const float4* __restrict__ pos_bias, float4* __restrict__ stream, int D) {
   const int total = batch * 3 * 256 * 24;                  // (b, c, y', xchunk)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   pdl_launch_dependents();
-  pdl_wait();            // the previous step may still be reading patch rows through its first GEMM
+  pdl_wait();            // the previous step may still be reading patch rows / the stream
+  const int per_crop4 = 192 * D / 4;                       // float4 per crop in the stream
+  for (long long j = i; j < static_cast<long long>(batch) * per_crop4; j += static_cast<long long>(gridDim.x) * blockDim.x)
+    stream[j] = __ldg(pos_bias + j % per_crop4);
   if (i >= total) return;
   const int xc = i % 24;
   const int yp = (i / 24) % 256;                           // y' = 16*py + ky

@@ -97,7 +97,9 @@ int vpb_profile_collect(vpb_engine* e, float* ms_per_class, int32_t* launches_pe
 int vpb_read_buffer(vpb_engine* e, const char* name, void* host_dst, int64_t bytes);  /* synchronous debug read */
 
 /* Kernel-level entry points (unit tests / profiling).  All pointers are device pointers.
- * vpb_gemm: out = epilogue(A[M,K] bf16 * W[N,K]^T bf16 + bias);  epilogue ids as in csrc/gemm.cuh. */
+ * vpb_gemm: out = epilogue(A[M,K] bf16 * W[N,K]^T bf16 + bias);  epilogue ids as in csrc/gemm.cuh (0 bias->bf16, 1 bias+GELU->bf16,
+ * 2 implicit-GEMM deconv: aux = H, W, tile rows, (tile cols << 16) | Cin, 4 bias->f32 NCHW: aux0 = channels, aux1 = pixels,
+ * 5 f32 out += ...).  d_resid / resid_mod are reserved (pass NULL / 0). */
 int vpb_gemm(const void* d_a, const void* d_w, const float* d_bias, void* d_out, int32_t m, int32_t n, int32_t k,
              int32_t epilogue, const float* d_resid, int32_t resid_mod, int32_t aux0, int32_t aux1, int32_t aux2,
              int32_t aux3, void* stream);
