@@ -388,7 +388,8 @@ def run_gpu(args) -> None:
             "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"ViT-{args.model.upper()} COCO-{K} bf16, batch={B} synthetic 256x192 crops per GPU (BASELINE configs[1])",
+            "config": {"workload": f"ViT-{args.model.upper()} K={K} bf16, batch={B} synthetic 256x192 crops per GPU"
+                                   + (" (BASELINE configs[1]: ViT-B COCO-17, batch 64)" if (args.model, K, B) == ("b", 17, 64) else ""),
                        "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world} (crops sharded, weights replicated)",
                        "l2": f"inputs rotate over {NBUF} device batches ({NBUF * B * 589824 / 1e6:.0f} MB > 126 MB L2); "
                              "weights + activations touched per step exceed L2 several times over",
