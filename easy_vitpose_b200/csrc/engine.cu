@@ -180,7 +180,7 @@ static int make_attn_maps(CUtensorMap* main, CUtensorMap* tail, const void* qkv,
 }
 static int attention_launch(int hd, const CUtensorMap& main, const CUtensorMap& tail, const AttnParams& ap, cudaStream_t st) {
   const int items = ap.batch * ap.heads;
-  const dim3 grid(items < 2 * g_num_sms ? items : 2 * g_num_sms);
+  const dim3 grid(items < g_num_sms ? items : g_num_sms);      // one CTA per SM (512 TMEM columns each)
   cudaError_t err;
   switch (hd) {
     case 32: err = launch_k(attention_tcgen05<32>, grid, dim3(ATT_THREADS), AttCfg<32>::SMEM, st, main, tail, ap); break;

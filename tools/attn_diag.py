@@ -22,7 +22,7 @@ for heads, hd, B in ((12, 64, 64), (16, 80, 32), (12, 32, 64)):
         _lib.check(L.vpb_attention(C.c_void_p(qkv.data_ptr()), B, heads, hd, C.c_void_p(out.data_ptr()), None))
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 100
-    n = min(B * heads, 296)
+    n = min(B * heads, 148)
     dbg = torch.zeros(n * 8, dtype=torch.int64, device=dev)
     L.vpb_debug_gemm(0, C.c_void_p(dbg.data_ptr()))
     attention(qkv, B, heads, hd)
@@ -30,4 +30,4 @@ for heads, hd, B in ((12, 64, 64), (16, 80, 32), (12, 32, 64)):
     m = dbg.cpu().reshape(n, 8).double().mean(0)
     steps = 2 * B * heads / n
     print(f"hd={hd} B={B} heads={heads}: {us:.1f} us/launch; per CTA: lifetime {m[0]:.0f} cyc, {steps:.1f} tile steps -> {m[0]/steps:.0f} cyc/step")
-    print(f"   worker0: wait S {m[1]/steps:.0f}  softmax {m[2]/steps:.0f}  wait O {m[3]/steps:.0f}  epilogue {m[4]/steps:.0f}   | ctl: wait P {m[5]/steps:.0f}  wait O {m[6]/steps:.0f}  wait loads {m[7]/steps:.0f}  (cycles per tile step)")
+    print(f"   softmax warp 0: wait S {m[1]/steps:.0f}  busy {m[2]/steps:.0f}   | epilogue warp 4: wait {m[3]/steps:.0f}  busy {m[4]/steps:.0f}  (cycles per tile step)")
