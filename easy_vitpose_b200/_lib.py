@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from .build import LIB
+from .build import LIB, build, is_stale
 
 _lib = None
 
@@ -52,9 +52,13 @@ def lib():
     """Loads the shared library once.  Raises if it has not been built (python -m easy_vitpose_b200.build)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            raise RuntimeError(f"{LIB} is missing: build it with `python -m easy_vitpose_b200.build` "
-                               "(or __graft_entry__.build()); there is no fallback implementation")
+        if not os.path.exists(LIB) or is_stale():
+            try:
+                build()                              # nvcc cross-compiles sm_100a anywhere; seconds
+            except Exception as exc:
+                if not os.path.exists(LIB):
+                    raise RuntimeError(f"{LIB} is missing and could not be built ({exc}); build it with "
+                                       "`python -m easy_vitpose_b200.build`; there is no fallback implementation") from exc
         handle = C.CDLL(LIB)
         for name, (res, args) in EXPORTS.items():
             fn = getattr(handle, name)          # AttributeError here = header and library disagree

@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -149,7 +150,7 @@ static int gemm_launch(int bn, int epi, const CUtensorMap& ta, const CUtensorMap
 #undef VPB_CASE
   return fail(VPB_ERR_ARG, "gemm: no kernel for BN=%d epilogue=%d", bn, epi);
 }
-static int bn_for(int n) { return (n % 256 == 0) ? 256 : 128; }
+static int bn_for(int n) { return (n % 256 == 0 && !(g_dbg_flags & 8)) ? 256 : 128; }   // debug flag 8: force 128-wide tiles
 
 static int device_check(int device) {
   static int checked_device = -1;
@@ -242,6 +243,12 @@ struct vpb_engine {
   struct GraphEntry { int batch; int seen; cudaGraphExec_t exec; };
   std::vector<GraphEntry> graphs;
   bool use_graph = true;
+  // L2 residency: the fp32 token stream x (37.7 MB at B=64) is read-modify-written by every residual GEMM and read by every
+  // LayerNorm, but the per-layer working set (~220 MB) would evict it from the 126 MB L2 in between; an access-policy window
+  // marks it persisting on every stream the engine launches on.
+  bool l2_persist = true;
+  size_t l2_window_bytes = 0;
+  std::vector<cudaStream_t> l2_streams;
   float* g_kpts = nullptr;      // graph-owned outputs / decode inputs: the captured chain only touches engine memory
   int32_t *g_idx = nullptr, *g_org = nullptr;
   std::map<std::string, std::pair<float*, int64_t>> staged;   // fp32 state_dict tensors on device until finalize
@@ -474,6 +481,19 @@ extern "C" int vpb_finalize(vpb_engine* e) {
   VPB_TRY(make_map(&e->o_qkv, e->qkv, M, 3 * D, 3 * D, 32));
   VPB_TRY(make_map(&e->o_hid, e->hid, M, 4 * D, 4 * D, 32));
   VPB_TRY(make_map(&e->o_x, e->x, M, D, D, 32, /*f32=*/true));
+  {
+    const char* env = getenv("VPB_L2_PERSIST");
+    if (env && env[0] == '0') e->l2_persist = false;
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, e->cfg.device));
+    size_t want = M * D * sizeof(float);
+    if (want > static_cast<size_t>(prop.accessPolicyMaxWindowSize)) want = prop.accessPolicyMaxWindowSize;
+    if (want > static_cast<size_t>(prop.persistingL2CacheMaxSize)) want = prop.persistingL2CacheMaxSize;
+    if (e->l2_persist && want > 0) {
+      CU_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+      e->l2_window_bytes = want;
+    }
+  }
   CU_TRY(cudaDeviceSynchronize());
   for (auto& kv : e->staged) cudaFree(kv.second.first);
   e->staged.clear();
@@ -618,6 +638,21 @@ static int head(vpb_engine* e, int B, float* d_heat, cudaStream_t st) {
   return VPB_OK;
 }
 
+static int apply_l2_policy(vpb_engine* e, cudaStream_t st) {
+  if (!e->l2_persist || e->l2_window_bytes == 0) return VPB_OK;
+  for (cudaStream_t s : e->l2_streams) if (s == st) return VPB_OK;
+  cudaStreamAttrValue v;
+  memset(&v, 0, sizeof(v));
+  v.accessPolicyWindow.base_ptr = e->x;
+  v.accessPolicyWindow.num_bytes = e->l2_window_bytes;
+  v.accessPolicyWindow.hitRatio = 1.0f;
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  CU_TRY(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v));
+  e->l2_streams.push_back(st);
+  return VPB_OK;
+}
+
 static int check_ready(vpb_engine* e, int batch) {
   if (!e) return fail(VPB_ERR_ARG, "null engine");
   if (!e->finalized) return fail(VPB_ERR_STATE, "weights not finalized: call vpb_finalize first");
@@ -629,6 +664,7 @@ extern "C" int vpb_forward(vpb_engine* e, const float* d_crops, int32_t batch, f
   VPB_TRY(check_ready(e, batch));
   if (!d_crops || !d_heatmaps) return fail(VPB_ERR_ARG, "vpb_forward: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VPB_TRY(apply_l2_policy(e, st));
   VPB_TRY(patch_gather(e, d_crops, batch, st));
   VPB_TRY(backbone(e, batch, st));
   if (e->stop_after && e->stop_after <= 10) return VPB_OK;
@@ -675,6 +711,7 @@ extern "C" int vpb_infer(vpb_engine* e, const float* d_crops, const int32_t* d_o
   if (!d_crops || !d_org_wh || !d_kpts) return fail(VPB_ERR_ARG, "vpb_infer: null pointer");
   float* heat = d_heatmaps ? d_heatmaps : e->heat;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VPB_TRY(apply_l2_policy(e, st));
   if (!e->use_graph || e->prof.on || e->stop_after || st == nullptr)      // the legacy default stream cannot be captured
     return infer_enqueue(e, d_crops, d_org_wh, batch, d_kpts, d_idx, heat, stream);
   vpb_engine::GraphEntry* g = nullptr;

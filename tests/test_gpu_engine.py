@@ -156,3 +156,45 @@ def test_fused_layernorm_tail_is_bit_identical(golden_dir):
         assert np.array_equal(a, b)
     for a, b in zip(outs[1][0], outs[1][1]):
         assert np.array_equal(a, b)                                  # counters were reset: a second fused run repeats exactly
+
+
+def test_install_rebinds_a_vitinference_like_object():
+    """easy_vitpose_b200.install() performs the two assignments VitInference.__init__ makes (inference.py:156,172) on an
+    object that looks like a constructed VitInference; `_inference(img)` must then honour the reference contract:
+    uint8 RGB crop -> float32 [1,K,3] rows (y, x, score) in crop pixels, equal to pre_img -> forward -> postprocess."""
+    import types
+
+    import cv2
+
+    from easy_vitpose_b200 import install
+    from easy_vitpose_b200.inference import MEAN, STD
+    D, depth, heads, K = 768, 12, 12, 17
+    sd = O.make_state_dict(D, depth, K, 77, peaky=0.1, bumps=True)
+
+    class FakeRefModel(torch.nn.Module):           # just enough of the reference ViTPose: state_dict() + num_heads
+        def __init__(self):
+            super().__init__()
+            for k, v in sd.items():
+                self.register_buffer(k.replace(".", "__"), torch.from_numpy(np.asarray(v)))
+            self.backbone = types.SimpleNamespace(blocks=[types.SimpleNamespace(attn=types.SimpleNamespace(num_heads=heads))])
+
+        def state_dict(self, *a, **kw):
+            return {k.replace("__", "."): v for k, v in super().state_dict(*a, **kw).items()}
+
+    vi = types.SimpleNamespace(_vit_pose=FakeRefModel(), _inference=None, postprocess=None)
+    backend = install(vi, max_batch=4)
+    rs = np.random.RandomState(3)
+    img = rs.randint(0, 256, size=(301, 207, 3), dtype=np.uint8)
+    out = vi._inference(img)
+    assert out.shape == (1, K, 3) and out.dtype == np.float32
+    # the same thing step by step: reference pre_img arithmetic, engine heatmaps, oracle decode
+    x = cv2.resize(img, (192, 256), interpolation=cv2.INTER_LINEAR) / 255
+    x = ((x - MEAN) / STD).transpose(2, 0, 1)[None].astype(np.float32)
+    hm = vi._vit_pose(torch.from_numpy(x).cuda()).cpu().numpy()
+    okp, _ = O.decode_maps(hm, np.array([[207, 301]], np.int32), wrap="crop")
+    assert np.array_equal(out[..., 2], okp[..., 2])
+    vis = okp[..., 2] > 0.3
+    assert np.abs(out - okp)[vis].max() < 5e-3 * 301 / 64
+    assert np.array_equal(vi.postprocess(hm, 207, 301)[..., 2], okp[..., 2])
+    many = backend.inference_batch([img, img[:200, :150], img[50:, 20:]])
+    assert many.shape == (3, K, 3) and np.array_equal(many[:1], out)
