@@ -504,7 +504,8 @@ extern "C" int vpb_finalize(vpb_engine* e) {
 // ------------------------------------------------------------------------------------------------ forward
 template <int D>
 static void ln_launch(const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, float eps, cudaStream_t st) {
-  launch_k(layernorm_f32_to_bf16<D>, dim3(cdiv(rows, 8)), dim3(256), 0, st, x, g, b, y, rows, eps);
+  const int want = cdiv(rows, 4), cap = g_num_sms * 4;     // 4 warps per CTA, at most 4 CTAs per SM (persistent, row stride)
+  launch_k(layernorm_f32_to_bf16<D>, dim3(want < cap ? want : cap), dim3(128), 0, st, x, g, b, y, rows, eps);
 }
 static int layernorm(const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, int D, float eps, cudaStream_t st) {
   switch (D) {
@@ -906,5 +907,8 @@ extern "C" int vpb_attention(const void* d_qkv, int32_t batch, int32_t heads, in
 extern "C" int vpb_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_y, int32_t rows, int32_t dim, float eps,
                              void* stream) {
   if (!d_x || !d_gamma || !d_beta || !d_y) return fail(VPB_ERR_ARG, "vpb_layernorm: null pointer");
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  VPB_TRY(device_check(dev));
   return layernorm(d_x, d_gamma, d_beta, reinterpret_cast<__nv_bfloat16*>(d_y), rows, dim, eps, static_cast<cudaStream_t>(stream));
 }

@@ -7,49 +7,63 @@
 namespace vpb {
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm(eps) over the last dim of x f32 [rows, D] -> bf16 [rows, D].  One warp per row, the row
-// lives in registers (D/128 float4 per lane), mean and biased variance by warp shuffles in fp32.
+// LayerNorm(eps) over the last dim of x f32 [rows, D] -> bf16 [rows, D].  Persistent warps (grid = a few CTAs per SM)
+// walk rows with stride; a row lives in registers (D/128 float4 per lane) and the NEXT row's loads are already in flight
+// while the current row is reduced (fp32 mean and biased variance by warp shuffles) and written.
 // Reference: nn.LayerNorm(eps=1e-6) at backbone/vit.py:190,198,304.
 template <int D>
-__global__ void __launch_bounds__(256) layernorm_f32_to_bf16(const float* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(128) layernorm_f32_to_bf16(const float* __restrict__ x, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                                                              int rows, float eps) {
   static_assert(D % 128 == 0, "row must split into float4 per lane");
   constexpr int V = D / 128;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   pdl_launch_dependents();
   pdl_wait();
   if (row >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
-  float4 v[V];
-  float s = 0.f;
+  float4 nxt[V];
+  {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    v[i] = xr[i * 32 + lane];
-    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    for (int i = 0; i < V; ++i) nxt[i] = xr[i * 32 + lane];
   }
+  for (; row < rows; row += warps_total) {
+    float4 v[V];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s * (1.0f / D);
-  float q = 0.f;
+    for (int i = 0; i < V; ++i) v[i] = nxt[i];
+    const int nrow = row + warps_total;
+    if (nrow < rows) {
+      const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(nrow) * D);
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-  }
+      for (int i = 0; i < V; ++i) nxt[i] = xr[i * 32 + lane];
+    }
+    float s = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q * (1.0f / D) + eps);
-  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+    for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
-    uint2 o;
-    o.x = pack_bf16(v[i].x * rstd * g.x + b.x, v[i].y * rstd * g.y + b.y);
-    o.y = pack_bf16(v[i].z * rstd * g.z + b.z, v[i].w * rstd * g.w + b.w);
-    yr[i * 32 + lane] = o;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / D) + eps);
+    uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * D);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+      uint2 o;
+      o.x = pack_bf16(v[i].x * rstd * g.x + b.x, v[i].y * rstd * g.y + b.y);
+      o.y = pack_bf16(v[i].z * rstd * g.z + b.z, v[i].w * rstd * g.w + b.w);
+      yr[i * 32 + lane] = o;
+    }
   }
 }
 
