@@ -204,6 +204,81 @@ def torch_cuda_eager(model: str, K: int, B: int, dev) -> dict:
     return out
 
 
+def bench_frame_path(model, B: int, K: int, steps: int, dev) -> dict:
+    """the reference's whole per-person loop (box pad/clip, crop, pad_image, cv2 resize,
+    normalise, model, decode, offset back) as one engine call per frame.  HOST uint8 1080p frames + B boxes in, HOST
+    keypoints out, two frames in flight (vpb_submit_frame_host / vpb_wait_host); plus the device time of the
+    pre-processing kernel alone and the reference's own CPU pre-processing (cv2) on the same boxes."""
+    import torch
+    rs = np.random.RandomState(5)
+    FH, FW = 1080, 1920
+    frames = [torch.from_numpy(rs.randint(0, 256, size=(FH, FW, 3), dtype=np.uint8)).pin_memory() for _ in range(2)]
+    w = rs.randint(90, 420, size=B); h = (w * rs.uniform(1.6, 2.6, size=B)).astype(np.int64)
+    x0 = rs.randint(0, FW - 100, size=B); y0 = rs.randint(0, FH - 200, size=B)
+    boxes = np.ascontiguousarray(np.stack([x0, y0, x0 + w, y0 + h], 1).astype(np.int32))
+    hk = [torch.empty((B, K, 3), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+    hi = [torch.empty((B, K), dtype=torch.int32).pin_memory().numpy() for _ in range(2)]
+    fr = [f.numpy() for f in frames]
+    for _ in range(3):
+        model.infer_frame_host(fr[0], boxes)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    model.submit_frame_host(fr[0], boxes, hk[0], hi[0], 0)
+    for i in range(1, steps):
+        model.submit_frame_host(fr[i % 2], boxes, hk[i % 2], hi[i % 2], i % 2)
+        model.wait_host((i - 1) % 2)
+    model.wait_host((steps - 1) % 2)
+    dt = time.perf_counter() - t0
+    # the pre-processing kernel alone, CUDA events on its stream, frame resident
+    d_frame = frames[0].to(dev); d_boxes = torch.from_numpy(boxes).to(dev)
+    import ctypes as C
+
+    from easy_vitpose_b200 import _lib
+    crops = torch.empty((B, 3, 256, 192), dtype=torch.float32, device=dev)
+    org = torch.empty((B, 2), dtype=torch.int32, device=dev); offs = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    side = torch.cuda.Stream(dev)
+
+    def pp():
+        _lib.check(_lib.lib().vpb_preprocess(C.c_void_p(d_frame.data_ptr()), FH, FW, 0, C.c_void_p(d_boxes.data_ptr()), B, 10,
+                                             C.c_void_p(crops.data_ptr()), C.c_void_p(org.data_ptr()), C.c_void_p(offs.data_ptr()),
+                                             None, C.c_void_p(side.cuda_stream)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 50
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        for _ in range(5):
+            pp()
+        e0.record(side)
+        for _ in range(reps):
+            pp()
+        e1.record(side)
+    torch.cuda.synchronize()
+    pp_ms = e0.elapsed_time(e1) / reps                 # back-to-back launches on one stream, frame resident in L2/HBM
+    out_bytes = B * 3 * 256 * 192 * 4
+    res = {"workload": f"{FH}x{FW} uint8 RGB frame + {B} person boxes per step, host in / host out",
+           "value": B * steps / dt, "unit": "crops/s", "frames_per_s": steps / dt, "steps": steps,
+           "api": "vpb_submit_frame_host / vpb_wait_host (C ABI), 2 frames in flight, pinned host buffers",
+           "h2d_bytes_per_step": FH * FW * 3 + B * 16, "d2h_bytes_per_step": B * K * 3 * 4 + B * K * 4,
+           "preprocess_kernel": {"ms_per_call": pp_ms, "bytes_written": out_bytes, "GBps_written": out_bytes / (pp_ms * 1e-3) / 1e9,
+                                 "note": "vpb_preprocess, CUDA events around 50 back-to-back launches"}}
+    try:
+        import cv2
+        from oracle import preproc_oracle as PO              # geometry helpers only; the resize below is cv2 itself
+        MEAN, STD = np.array(PO.MEAN), np.array(PO.STD)
+        n_cpu = min(B, 32)
+        t0 = time.perf_counter()
+        for b in boxes[:n_cpu]:
+            canvas, _ = PO.crop_canvas(fr[0], b)
+            x = cv2.resize(canvas, (192, 256), interpolation=cv2.INTER_LINEAR) / 255
+            x = ((x - MEAN) / STD).transpose(2, 0, 1)[None].astype(np.float32)
+        cdt = time.perf_counter() - t0
+        res["cpu_preprocess_reference"] = {"value": n_cpu / cdt, "unit": "crops/s", "cores": 1,
+                                           "sample": f"{n_cpu} boxes: numpy crop + pad, cv2.resize, float64 normalise (inference.py:259-265,314-318)"}
+    except Exception as exc:                                  # cv2 missing on the box: report, do not fail the bench
+        res["cpu_preprocess_reference"] = {"unavailable": repr(exc)}
+    return res
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -353,6 +428,10 @@ def run_gpu(args) -> None:
     e2e_value = world * B * e_steps / float(te[0].item())
     e2e_sync_value = world * B * e_steps / float(te[1].item())
 
+    frame_path = None
+    if world == 1:
+        frame_path = bench_frame_path(model, B, K, max(5, args.steps // 4), dev)
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
         fl = flops_per_crop(D, depth, heads, K)
@@ -410,6 +489,7 @@ def run_gpu(args) -> None:
                 "value": cpu_val, "unit": "crops/s", "cores": cores, "kind": "port",
                 "sample": f"{args.cpu_sample} crops x 3 steps, torch CPU fp32 forward + numpy decode (oracle/)"},
             "torch_cuda_eager": eager,
+            "frame_path": frame_path,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

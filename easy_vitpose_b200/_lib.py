@@ -32,6 +32,12 @@ EXPORTS = {
     "vpb_infer_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vpb_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
     "vpb_wait_host": (C.c_int, [C.c_void_p, C.c_int32]),
+    "vpb_preprocess": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vpb_decode_frame": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vpb_infer_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vpb_infer_frame_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vpb_submit_frame_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
     "vpb_host_alloc": (C.c_void_p, [C.c_int64]),
     "vpb_host_free": (None, [C.c_void_p]),
     "vpb_kernel_launches": (C.c_int, [C.c_void_p, C.c_int32]),
@@ -71,3 +77,11 @@ def lib():
 def check(code: int) -> None:
     if code != 0:
         raise RuntimeError(f"vitpose_b200 error {code}: {lib().vpb_last_error().decode()}")
+
+
+def check_value(code: int) -> None:
+    """Like check(), but a bad ARGUMENT (code 1: e.g. a box that is empty after clipping, where the reference raises from
+    pad_image / cv2.resize) surfaces as ValueError."""
+    if code == 1:
+        raise ValueError(lib().vpb_last_error().decode())
+    check(code)

@@ -7,6 +7,7 @@
 //                                                                 7-point Taylor step with a float64 2x2 inverse
 //   transform_preds(use_udp)  vit_utils/post_processing/post_transforms.py:183-192
 //   VitInference.postprocess  easy_ViTPose/inference.py:187-205   centre = org // 2, output order (y, x, score)
+//   VitInference.inference    easy_ViTPose/inference.py:270       optional integer (y, x) offset back to the frame
 // The blur is only evaluated at the (at most) 7 stencil points the Taylor step reads, with cv2's exact
 // float32 accumulation order (row pass: sequential fmaf left to right; column pass: centre tap then
 // fmaf of symmetric pairs), so blurred values are bit-identical to cv2 4.13 (oracle/make_golden.py).
@@ -38,6 +39,7 @@ struct DecodeParams {
   const int* org_wh;       // [N,2] crop (width, height)
   float* kpts;             // [N,K,3]
   int* idx;                // [N,K] (may be nullptr)
+  const int* offs_yx;      // [N,2] integer (y, x) added to the keypoints: crop -> frame coordinates (inference.py:270); may be nullptr
   int n, k;
   int wrap_batch;          // sentinel quirk: 0 = previous map wraps inside the crop, 1 = inside the whole call
 };
@@ -159,7 +161,15 @@ __global__ void __launch_bounds__(256) decode_heatmaps(const DecodeParams p) {
     const float X = static_cast<float>(static_cast<double>(xr) * (ow / (HM_W - 1.0)) + static_cast<double>(ow / 2) - ow * 0.5);
     const float Y = static_cast<float>(static_cast<double>(yr) * (oh / (HM_H - 1.0)) + static_cast<double>(oh / 2) - oh * 0.5);
     float* o = p.kpts + static_cast<size_t>(g) * 3;
-    o[0] = Y; o[1] = X; o[2] = mx;
+    float Yf = Y, Xf = X;
+    if (p.offs_yx != nullptr) {
+      // numpy adds the int64 offsets in float64 and casts back: one rounding of an exact sum, which is what a float32
+      // add of an exactly representable integer does.  Zero offsets are skipped so that -0.0 survives.
+      const int oy = p.offs_yx[2 * n_i], ox = p.offs_yx[2 * n_i + 1];
+      if (oy != 0) Yf = __fadd_rn(Y, static_cast<float>(oy));
+      if (ox != 0) Xf = __fadd_rn(X, static_cast<float>(ox));
+    }
+    o[0] = Yf; o[1] = Xf; o[2] = mx;
     if (p.idx != nullptr) p.idx[g] = amax;
   }
 }

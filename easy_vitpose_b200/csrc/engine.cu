@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +20,7 @@
 #include "decode.cuh"
 #include "gemm.cuh"
 #include "pointwise.cuh"
+#include "preprocess.cuh"
 
 using namespace vpb;
 
@@ -197,9 +199,9 @@ static int attention_launch(int hd, const CUtensorMap& main, const CUtensorMap& 
 // Optional ("profile" option): a CUDA-event pair around every launch, on the launch stream, summed per kernel
 // class by vpb_profile_collect.  bench.py uses it to report the dominant kernel's achieved FLOP/s live.
 enum KClass : int { KC_PATCH_IM2COL, KC_GEMM_PATCH, KC_LN, KC_GEMM_QKV, KC_ATTN, KC_GEMM_PROJ, KC_GEMM_FC1, KC_GEMM_FC2,
-                    KC_GEMM_DECONV, KC_GEMM_FINAL, KC_DECODE, KC_COUNT };
+                    KC_GEMM_DECONV, KC_GEMM_FINAL, KC_DECODE, KC_PREPROCESS, KC_COUNT };
 static const char* kclass_names[KC_COUNT] = {"patch_im2col", "gemm_patch_embed", "layernorm", "gemm_qkv", "attention", "gemm_proj",
-                                             "gemm_fc1_gelu", "gemm_fc2", "gemm_deconv", "gemm_final_conv", "decode"};
+                                             "gemm_fc1_gelu", "gemm_fc2", "gemm_deconv", "gemm_final_conv", "decode", "crop_preprocess"};
 struct ProfRec { int cls; cudaEvent_t a, b; };
 struct Profiler {
   bool on = false;
@@ -250,7 +252,14 @@ struct vpb_engine {
   size_t l2_window_bytes = 0;
   std::vector<cudaStream_t> l2_streams;
   float* g_kpts = nullptr;      // graph-owned outputs / decode inputs: the captured chain only touches engine memory
-  int32_t *g_idx = nullptr, *g_org = nullptr;
+  int32_t *g_idx = nullptr, *g_org = nullptr, *g_offs = nullptr;
+  // frame-level entry points (crop pre-processing on the GPU): crops / canvas sizes / frame offsets produced by
+  // crop_resize_normalise, the status word it flags empty boxes in, and per-slot frame + box staging for the host variants
+  float* pp_crops = nullptr;
+  int32_t *pp_org = nullptr, *pp_offs = nullptr, *pp_status = nullptr;
+  uint8_t* frame_stage[2] = {nullptr, nullptr};
+  size_t frame_cap[2] = {0, 0};
+  int32_t* bbox_stage[2] = {nullptr, nullptr};
   std::map<std::string, std::pair<float*, int64_t>> staged;   // fp32 state_dict tensors on device until finalize
   std::vector<void*> allocs;
   // packed weights
@@ -348,6 +357,7 @@ extern "C" void vpb_destroy(vpb_engine* e) {
   }
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->compute_stream) cudaStreamDestroy(e->compute_stream);
+  for (int s = 0; s < 2; ++s) if (e->frame_stage[s]) cudaFree(e->frame_stage[s]);
   delete e;
 }
 
@@ -468,6 +478,13 @@ extern "C" int vpb_finalize(vpb_engine* e) {
   VPB_TRY(dev_alloc(e, &e->g_kpts, B * e->K * 3));
   VPB_TRY(dev_alloc(e, &e->g_idx, B * e->K));
   VPB_TRY(dev_alloc(e, &e->g_org, B * 2));
+  VPB_TRY(dev_alloc(e, &e->g_offs, B * 2));
+  VPB_TRY(dev_alloc(e, &e->pp_crops, B * 3 * 256 * 192));
+  VPB_TRY(dev_alloc(e, &e->pp_org, B * 2));
+  VPB_TRY(dev_alloc(e, &e->pp_offs, B * 2));
+  VPB_TRY(dev_alloc(e, &e->pp_status, 1));
+  CU_TRY(cudaMemset(e->pp_status, 0, sizeof(int32_t)));
+  for (int s = 0; s < 2; ++s) VPB_TRY(dev_alloc(e, &e->bbox_stage[s], B * 4));
   CU_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   CU_TRY(cudaStreamCreateWithFlags(&e->compute_stream, cudaStreamNonBlocking));
   VPB_TRY(make_map(&e->m_patch_rows, e->patch_rows, M, 768, 768, 128));
@@ -684,52 +701,62 @@ extern "C" int vpb_forward_features(vpb_engine* e, const float* d_crops, int32_t
   return VPB_OK;
 }
 
-extern "C" int vpb_decode(const float* d_heatmaps, int32_t n, int32_t k, const int32_t* d_org_wh, float* d_kpts, int32_t* d_idx,
-                          int32_t wrap_batch, void* stream) {
+static int decode_launch(const float* d_heatmaps, int32_t n, int32_t k, const int32_t* d_org_wh, const int32_t* d_offs_yx, float* d_kpts,
+                         int32_t* d_idx, int32_t wrap_batch, void* stream) {
   if (!d_heatmaps || !d_org_wh || !d_kpts) return fail(VPB_ERR_ARG, "vpb_decode: null pointer");
   if (n < 0 || k < 1) return fail(VPB_ERR_ARG, "vpb_decode: n=%d k=%d", n, k);
   if (n == 0) return VPB_OK;
   DecodeParams p;
   p.heatmaps = d_heatmaps; p.org_wh = d_org_wh; p.kpts = d_kpts; p.idx = d_idx; p.n = n; p.k = k; p.wrap_batch = wrap_batch;
+  p.offs_yx = d_offs_yx;
   launch_k(decode_heatmaps, dim3(cdiv(static_cast<long long>(n) * k, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   CU_TRY(cudaGetLastError());
   return VPB_OK;
 }
+extern "C" int vpb_decode(const float* d_heatmaps, int32_t n, int32_t k, const int32_t* d_org_wh, float* d_kpts, int32_t* d_idx,
+                          int32_t wrap_batch, void* stream) {
+  return decode_launch(d_heatmaps, n, k, d_org_wh, nullptr, d_kpts, d_idx, wrap_batch, stream);
+}
+extern "C" int vpb_decode_frame(const float* d_heatmaps, int32_t n, int32_t k, const int32_t* d_org_wh, const int32_t* d_offs_yx,
+                                float* d_kpts, int32_t* d_idx, int32_t wrap_batch, void* stream) {
+  return decode_launch(d_heatmaps, n, k, d_org_wh, d_offs_yx, d_kpts, d_idx, wrap_batch, stream);
+}
 
-static int infer_enqueue(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, int32_t batch, float* d_kpts, int32_t* d_idx,
-                         float* heat, void* stream) {
+static int infer_enqueue(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, const int32_t* d_offs_yx, int32_t batch,
+                         float* d_kpts, int32_t* d_idx, float* heat, void* stream) {
   VPB_TRY(vpb_forward(e, d_crops, batch, heat, stream));
   if (e->stop_after) return VPB_OK;
   e->prof.begin(KC_DECODE, static_cast<cudaStream_t>(stream));
-  VPB_TRY(vpb_decode(heat, batch, e->K, d_org_wh, d_kpts, d_idx, 0, stream));
+  VPB_TRY(decode_launch(heat, batch, e->K, d_org_wh, d_offs_yx, d_kpts, d_idx, 0, stream));
   e->prof.end(static_cast<cudaStream_t>(stream));
   return VPB_OK;
 }
 
-extern "C" int vpb_infer(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, int32_t batch, float* d_kpts, int32_t* d_idx,
-                         float* d_heatmaps, void* stream) {
-  VPB_TRY(check_ready(e, batch));
-  if (!d_crops || !d_org_wh || !d_kpts) return fail(VPB_ERR_ARG, "vpb_infer: null pointer");
+// crops -> keypoints; d_offs_yx (nullable) moves the keypoints from crop to frame coordinates inside the decode kernel
+static int infer_core(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, const int32_t* d_offs_yx, int32_t batch,
+                      float* d_kpts, int32_t* d_idx, float* d_heatmaps, void* stream) {
   float* heat = d_heatmaps ? d_heatmaps : e->heat;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VPB_TRY(apply_l2_policy(e, st));
   if (!e->use_graph || e->prof.on || e->stop_after || st == nullptr)      // the legacy default stream cannot be captured
-    return infer_enqueue(e, d_crops, d_org_wh, batch, d_kpts, d_idx, heat, stream);
+    return infer_enqueue(e, d_crops, d_org_wh, d_offs_yx, batch, d_kpts, d_idx, heat, stream);
   vpb_engine::GraphEntry* g = nullptr;
   for (auto& c : e->graphs)
     if (c.batch == batch) g = &c;
   if (!g) {                                                               // first use of this batch size: run eagerly
     e->graphs.push_back({batch, 1, nullptr});
-    return infer_enqueue(e, d_crops, d_org_wh, batch, d_kpts, d_idx, heat, stream);
+    return infer_enqueue(e, d_crops, d_org_wh, d_offs_yx, batch, d_kpts, d_idx, heat, stream);
   }
   VPB_TRY(patch_gather(e, d_crops, batch, st));
   CU_TRY(cudaMemcpyAsync(e->g_org, d_org_wh, static_cast<size_t>(batch) * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  if (d_offs_yx) CU_TRY(cudaMemcpyAsync(e->g_offs, d_offs_yx, static_cast<size_t>(batch) * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  else CU_TRY(cudaMemsetAsync(e->g_offs, 0, static_cast<size_t>(batch) * 2 * sizeof(int32_t), st));
   if (!g->exec) {                                                         // second use: capture, instantiate
     cudaGraph_t graph = nullptr;
     CU_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int rc = backbone(e, batch, st);
     if (rc == VPB_OK) rc = head(e, batch, e->heat, st);
-    if (rc == VPB_OK) rc = vpb_decode(e->heat, batch, e->K, e->g_org, e->g_kpts, e->g_idx, 0, stream);
+    if (rc == VPB_OK) rc = decode_launch(e->heat, batch, e->K, e->g_org, e->g_offs, e->g_kpts, e->g_idx, 0, stream);
     const cudaError_t ce = cudaStreamEndCapture(st, &graph);
     if (rc != VPB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (ce != cudaSuccess) return fail(VPB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
@@ -742,6 +769,106 @@ extern "C" int vpb_infer(vpb_engine* e, const float* d_crops, const int32_t* d_o
   if (d_idx) CU_TRY(cudaMemcpyAsync(d_idx, e->g_idx, static_cast<size_t>(batch) * e->K * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   if (d_heatmaps)
     CU_TRY(cudaMemcpyAsync(d_heatmaps, e->heat, static_cast<size_t>(batch) * e->K * 3072 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return VPB_OK;
+}
+
+extern "C" int vpb_infer(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, int32_t batch, float* d_kpts, int32_t* d_idx,
+                         float* d_heatmaps, void* stream) {
+  VPB_TRY(check_ready(e, batch));
+  if (!d_crops || !d_org_wh || !d_kpts) return fail(VPB_ERR_ARG, "vpb_infer: null pointer");
+  return infer_core(e, d_crops, d_org_wh, nullptr, batch, d_kpts, d_idx, d_heatmaps, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ frame-level entry points
+extern "C" int vpb_preprocess(const uint8_t* d_frame, int32_t frame_h, int32_t frame_w, int64_t pitch_bytes, const int32_t* d_bboxes,
+                              int32_t n, int32_t pad_bbox, float* d_crops, int32_t* d_org_wh, int32_t* d_offs_yx, int32_t* d_status,
+                              void* stream) {
+  if (!d_frame || !d_bboxes || !d_crops || !d_org_wh || !d_offs_yx) return fail(VPB_ERR_ARG, "vpb_preprocess: null pointer");
+  if (frame_h < 1 || frame_w < 1 || n < 0 || pad_bbox < 0) return fail(VPB_ERR_ARG, "vpb_preprocess: frame %dx%d n=%d pad=%d", frame_h, frame_w, n, pad_bbox);
+  if (pitch_bytes == 0) pitch_bytes = static_cast<int64_t>(frame_w) * 3;
+  if (pitch_bytes < static_cast<int64_t>(frame_w) * 3) return fail(VPB_ERR_ARG, "vpb_preprocess: pitch %lld < 3 * width", static_cast<long long>(pitch_bytes));
+  if (n == 0) return VPB_OK;
+  PreprocParams p;
+  p.frame = d_frame; p.pitch = pitch_bytes; p.fh = frame_h; p.fw = frame_w; p.bboxes = d_bboxes; p.n = n; p.pad = pad_bbox;
+  p.crops = d_crops; p.org_wh = d_org_wh; p.offs_yx = d_offs_yx; p.status = d_status;
+  crop_resize_normalise<<<dim3(n, PP_H / PP_ROWS), PP_W, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  CU_TRY(cudaGetLastError());
+  return VPB_OK;
+}
+
+static int infer_frame_enqueue(vpb_engine* e, const uint8_t* d_frame, int32_t frame_h, int32_t frame_w, const int32_t* d_bboxes,
+                               int32_t n, float* d_kpts, int32_t* d_idx, cudaStream_t st) {
+  e->prof.begin(KC_PREPROCESS, st);
+  VPB_TRY(vpb_preprocess(d_frame, frame_h, frame_w, 0, d_bboxes, n, 10, e->pp_crops, e->pp_org, e->pp_offs, e->pp_status, st));
+  e->prof.end(st);
+  return infer_core(e, e->pp_crops, e->pp_org, e->pp_offs, n, d_kpts, d_idx, nullptr, st);
+}
+
+extern "C" int vpb_infer_frame(vpb_engine* e, const uint8_t* d_frame, int32_t frame_h, int32_t frame_w, const int32_t* d_bboxes,
+                               int32_t n, float* d_kpts, int32_t* d_idx, void* stream) {
+  VPB_TRY(check_ready(e, n));
+  if (!d_frame || !d_bboxes || !d_kpts) return fail(VPB_ERR_ARG, "vpb_infer_frame: null pointer");
+  return infer_frame_enqueue(e, d_frame, frame_h, frame_w, d_bboxes, n, d_kpts, d_idx, static_cast<cudaStream_t>(stream));
+}
+
+// host boxes are checked here, where the reference raises (ZeroDivisionError in pad_image / cv2.resize on an empty crop)
+static int check_boxes_host(const int32_t* bb, int32_t n, int32_t fh, int32_t fw) {
+  for (int i = 0; i < n; ++i) {
+    const int x0 = std::min(std::max(bb[4 * i] - 10, 0), fw), x1 = std::min(std::max(bb[4 * i + 2] + 10, 0), fw);
+    const int y0 = std::min(std::max(bb[4 * i + 1] - 10, 0), fh), y1 = std::min(std::max(bb[4 * i + 3] + 10, 0), fh);
+    if (x1 - x0 <= 0 || y1 - y0 <= 0)
+      return fail(VPB_ERR_ARG, "box %d (%d,%d,%d,%d) is empty after padding and clipping to the %dx%d frame", i, bb[4 * i], bb[4 * i + 1],
+                  bb[4 * i + 2], bb[4 * i + 3], fw, fh);
+  }
+  return VPB_OK;
+}
+static int frame_stage_reserve(vpb_engine* e, int slot, size_t bytes) {
+  if (e->frame_cap[slot] >= bytes) return VPB_OK;
+  if (e->frame_stage[slot]) { CU_TRY(cudaDeviceSynchronize()); CU_TRY(cudaFree(e->frame_stage[slot])); e->frame_stage[slot] = nullptr; e->frame_cap[slot] = 0; }
+  void* q = nullptr;
+  CU_TRY(cudaMalloc(&q, bytes + 256));
+  e->frame_stage[slot] = static_cast<uint8_t*>(q);
+  e->frame_cap[slot] = bytes;
+  return VPB_OK;
+}
+
+extern "C" int vpb_infer_frame_host(vpb_engine* e, const uint8_t* h_frame, int32_t frame_h, int32_t frame_w, const int32_t* h_bboxes,
+                                    int32_t n, float* h_kpts, int32_t* h_idx, void* stream) {
+  VPB_TRY(check_ready(e, n));
+  if (!h_frame || !h_bboxes || !h_kpts || frame_h < 1 || frame_w < 1) return fail(VPB_ERR_ARG, "vpb_infer_frame_host: bad argument");
+  VPB_TRY(check_boxes_host(h_bboxes, n, frame_h, frame_w));
+  const size_t fbytes = static_cast<size_t>(frame_h) * frame_w * 3;
+  VPB_TRY(frame_stage_reserve(e, 0, fbytes));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU_TRY(cudaMemcpyAsync(e->frame_stage[0], h_frame, fbytes, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(e->bbox_stage[0], h_bboxes, static_cast<size_t>(n) * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  VPB_TRY(infer_frame_enqueue(e, e->frame_stage[0], frame_h, frame_w, e->bbox_stage[0], n, e->kpts[0], e->idx[0], st));
+  CU_TRY(cudaMemcpyAsync(h_kpts, e->kpts[0], static_cast<size_t>(n) * e->K * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (h_idx) CU_TRY(cudaMemcpyAsync(h_idx, e->idx[0], static_cast<size_t>(n) * e->K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return VPB_OK;
+}
+
+// Pipelined frames (video): same slots, events and vpb_wait_host as vpb_submit_host; the H2D per step is the uint8 frame and
+// 16 B per box instead of 589 824 B per crop.
+extern "C" int vpb_submit_frame_host(vpb_engine* e, const uint8_t* h_frame, int32_t frame_h, int32_t frame_w, const int32_t* h_bboxes,
+                                     int32_t n, float* h_kpts, int32_t* h_idx, int32_t slot) {
+  VPB_TRY(check_ready(e, n));
+  if (!h_frame || !h_bboxes || !h_kpts || frame_h < 1 || frame_w < 1 || slot < 0 || slot > 1)
+    return fail(VPB_ERR_ARG, "vpb_submit_frame_host: bad argument");
+  VPB_TRY(check_boxes_host(h_bboxes, n, frame_h, frame_w));
+  CU_TRY(cudaSetDevice(e->cfg.device));
+  const size_t fbytes = static_cast<size_t>(frame_h) * frame_w * 3;
+  VPB_TRY(frame_stage_reserve(e, slot, fbytes));
+  CU_TRY(cudaStreamWaitEvent(e->copy_stream, e->ev_done[slot], 0));
+  CU_TRY(cudaMemcpyAsync(e->frame_stage[slot], h_frame, fbytes, cudaMemcpyHostToDevice, e->copy_stream));
+  CU_TRY(cudaMemcpyAsync(e->bbox_stage[slot], h_bboxes, static_cast<size_t>(n) * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, e->copy_stream));
+  CU_TRY(cudaEventRecord(e->ev_h2d[slot], e->copy_stream));
+  CU_TRY(cudaStreamWaitEvent(e->compute_stream, e->ev_h2d[slot], 0));
+  VPB_TRY(infer_frame_enqueue(e, e->frame_stage[slot], frame_h, frame_w, e->bbox_stage[slot], n, e->kpts[slot], e->idx[slot], e->compute_stream));
+  CU_TRY(cudaMemcpyAsync(h_kpts, e->kpts[slot], static_cast<size_t>(n) * e->K * 3 * sizeof(float), cudaMemcpyDeviceToHost, e->compute_stream));
+  if (h_idx) CU_TRY(cudaMemcpyAsync(h_idx, e->idx[slot], static_cast<size_t>(n) * e->K * sizeof(int32_t), cudaMemcpyDeviceToHost, e->compute_stream));
+  CU_TRY(cudaEventRecord(e->ev_done[slot], e->compute_stream));
   return VPB_OK;
 }
 

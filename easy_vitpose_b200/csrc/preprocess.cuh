@@ -1,0 +1,116 @@
+// Crop pre-processing: frame uint8 RGB [H,W,3] + int boxes [n,4]  ->  normalised crops
+// f32 [n,3,256,192], canvas sizes [n,2] (w,h) and frame offsets [n,2] (y,x), one launch for all people of a frame.
+// HBM/L2-bound: 589 824 B written per crop; the gather side re-reads frame pixels that stay in L2.
+//
+// Restates, per box, what VitInference.inference does on the CPU:
+//   easy_ViTPose/inference.py:259-261   box +-10 px, clipped to the frame
+//   easy_ViTPose/inference.py:264-265   crop, then pad_image(crop, 3/4): zero-pad to a 3:4 canvas (vit_utils/inference.py:41-70);
+//                                       the canvas is never materialised here, out-of-crop taps read 0
+//   easy_ViTPose/inference.py:314-318   pre_img: cv2.resize(.., (192,256), INTER_LINEAR) on uint8, /255, (x-MEAN)/STD in
+//                                       float64, HWC -> CHW, astype(float32)
+//   easy_ViTPose/inference.py:270       offset (y0 - top_pad, x0 - left_pad) that maps crop keypoints back to the frame
+// cv2's uint8 bilinear resize is fixed-point; the arithmetic below is its exact integer pipeline (oracle/preproc_oracle.py
+// documents and pins it): int16 coefficients rint(frac * 2048), horizontal sums in int32, vertical
+// (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.  The horizontal pass clamps (index, fraction) at the
+// borders, the vertical pass clamps only the row indices.  Normalisation is a 3x256 table computed in float64, so the
+// crops are bit-identical to the reference's.
+#pragma once
+#include <cstdint>
+
+#include "ptx.cuh"
+
+namespace vpb {
+
+constexpr int PP_W = 192, PP_H = 256, PP_ROWS = 16;     // one CTA: 192 columns x 16 output rows of one crop
+
+struct PreprocParams {
+  const uint8_t* frame;       // [fh, fw, 3] RGB, row pitch `pitch` bytes
+  long long pitch;
+  int fh, fw;
+  const int* bboxes;          // [n,4] (x0, y0, x1, y1), already rounded to int (inference.py:253)
+  int n, pad;
+  float* crops;               // [n,3,256,192]
+  int* org_wh;                // [n,2] canvas (w, h)
+  int* offs_yx;               // [n,2] (y0 - top_pad, x0 - left_pad)
+  int* status;                // bit 0 set if any box is empty after clipping (may be nullptr)
+};
+
+struct PpAxis { int i0, i1, a0, a1; };
+
+// destination index d of `dn` -> the two source indices and int16 weights over a source of `sn` samples
+__device__ __forceinline__ PpAxis pp_axis(int d, int dn, int sn, bool clamp_fraction) {
+  const double scale = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(dn), static_cast<double>(sn)));
+  const float f = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(d) + 0.5, scale), -0.5));
+  int s = __float2int_rd(f);
+  float fr = __fsub_rn(f, static_cast<float>(s));
+  if (clamp_fraction) {
+    if (s < 0) { s = 0; fr = 0.f; }
+    if (s >= sn - 1) { s = sn - 1; fr = 0.f; }
+  }
+  PpAxis a;
+  a.a1 = __float2int_rn(__fmul_rn(fr, 2048.f));
+  a.a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fr), 2048.f));
+  a.i0 = min(max(s, 0), sn - 1);
+  a.i1 = min(max(s + 1, 0), sn - 1);
+  return a;
+}
+
+__global__ void __launch_bounds__(PP_W) crop_resize_normalise(const PreprocParams p) {
+  __shared__ float s_lut[3][256];
+  const int crop = blockIdx.x, dx = threadIdx.x, dy0 = blockIdx.y * PP_ROWS;
+  {
+    const double mean[3] = {0.485, 0.456, 0.406}, stdv[3] = {0.229, 0.224, 0.225};   // inference.py:32-33
+    for (int i = dx; i < 768; i += PP_W) {
+      const int c = i >> 8, v = i & 255;
+      s_lut[c][v] = static_cast<float>(__ddiv_rn(__dsub_rn(__ddiv_rn(static_cast<double>(v), 255.0), mean[c]), stdv[c]));
+    }
+  }
+  const int* bb = p.bboxes + 4 * crop;
+  const int x0 = min(max(bb[0] - p.pad, 0), p.fw), x1 = min(max(bb[2] + p.pad, 0), p.fw);
+  const int y0 = min(max(bb[1] - p.pad, 0), p.fh), y1 = min(max(bb[3] + p.pad, 0), p.fh);
+  const int w = x1 - x0, h = y1 - y0;
+  __syncthreads();
+  float* out = p.crops + static_cast<size_t>(crop) * 3 * PP_H * PP_W;
+  if (w <= 0 || h <= 0) {                                   // the reference raises here; flag it, emit a black crop
+    if (dx == 0 && blockIdx.y == 0) {
+      if (p.status) atomicOr(p.status, 1);
+      p.org_wh[2 * crop] = 0; p.org_wh[2 * crop + 1] = 0;
+      p.offs_yx[2 * crop] = y0; p.offs_yx[2 * crop + 1] = x0;
+    }
+    for (int r = 0; r < PP_ROWS; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) out[(c * PP_H + dy0 + r) * PP_W + dx] = s_lut[c][0];
+    return;
+  }
+  // pad_image: w / h < 3 / 4  <=>  4w < 3h;  int(0.75 * h) = 3h / 4,  int(w / 0.75) = 4w / 3
+  int cw = w, ch = h, left = 0, top = 0;
+  if (4 * w < 3 * h) { cw = (3 * h) / 4; left = (cw - w) / 2; }
+  else { ch = (4 * w) / 3; top = (ch - h) / 2; }
+  if (dx == 0 && blockIdx.y == 0) {
+    p.org_wh[2 * crop] = cw; p.org_wh[2 * crop + 1] = ch;
+    p.offs_yx[2 * crop] = y0 - top; p.offs_yx[2 * crop + 1] = x0 - left;
+  }
+  const PpAxis ax = pp_axis(dx, PP_W, cw, true);
+  const int cx0 = ax.i0 - left, cx1 = ax.i1 - left;          // canvas column -> crop column
+  const bool vx0 = cx0 >= 0 && cx0 < w, vx1 = cx1 >= 0 && cx1 < w;
+  const uint8_t* col0 = p.frame + static_cast<size_t>(vx0 ? x0 + cx0 : 0) * 3;   // only dereferenced when valid
+  const uint8_t* col1 = p.frame + static_cast<size_t>(vx1 ? x0 + cx1 : 0) * 3;
+  for (int r = 0; r < PP_ROWS; ++r) {
+    const int dy = dy0 + r;
+    const PpAxis ay = pp_axis(dy, PP_H, ch, false);
+    const int cy0 = ay.i0 - top, cy1 = ay.i1 - top;
+    const bool vy0 = cy0 >= 0 && cy0 < h, vy1 = cy1 >= 0 && cy1 < h;
+    const size_t r0 = static_cast<size_t>(vy0 ? y0 + cy0 : 0) * p.pitch, r1 = static_cast<size_t>(vy1 ? y0 + cy1 : 0) * p.pitch;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int p00 = (vy0 && vx0) ? col0[r0 + c] : 0, p01 = (vy0 && vx1) ? col1[r0 + c] : 0;
+      const int p10 = (vy1 && vx0) ? col0[r1 + c] : 0, p11 = (vy1 && vx1) ? col1[r1 + c] : 0;
+      const int s0 = p00 * ax.a0 + p01 * ax.a1, s1 = p10 * ax.a0 + p11 * ax.a1;
+      int v = (((ay.a0 * (s0 >> 4)) >> 16) + ((ay.a1 * (s1 >> 4)) >> 16) + 2) >> 2;
+      v = min(max(v, 0), 255);
+      out[(c * PP_H + dy) * PP_W + dx] = s_lut[c][v];
+    }
+  }
+}
+
+}  // namespace vpb

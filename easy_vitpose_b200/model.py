@@ -201,6 +201,23 @@ class ViTPose:
         return out
 
     @torch.no_grad()
+    def _call_on_stream(self, tensors, call) -> None:
+        """Runs `call(stream)` on the caller's current stream; on the legacy default stream (which cannot be captured into a
+        CUDA graph) on a side stream ordered after / before it by two event waits, so small batches get graph replay."""
+        with torch.cuda.device(self._device):
+            cur = torch.cuda.current_stream(self._device)
+            if cur.cuda_stream == 0:
+                if self._side is None:
+                    self._side = torch.cuda.Stream(self._device)
+                self._side.wait_stream(cur)
+                for t in tensors:
+                    if t is not None:
+                        t.record_stream(self._side)
+                _lib.check(call(C.c_void_p(self._side.cuda_stream)))
+                cur.wait_stream(self._side)
+            else:
+                _lib.check(call(C.c_void_p(cur.cuda_stream)))
+
     def infer_crops(self, x: torch.Tensor, org_wh: torch.Tensor, return_heatmaps: bool = False):
         """Batched crops -> keypoints [B,K,3] (y, x, score) in crop pixels + flat argmax [B,K].
         org_wh int32 [B,2] = each crop's (width, height) before the resize to 192x256."""
@@ -212,25 +229,9 @@ class ViTPose:
         kp = torch.empty((B, self.num_keypoints, 3), dtype=torch.float32, device=x.device)
         idx = torch.empty((B, self.num_keypoints), dtype=torch.int32, device=x.device)
         hm = torch.empty((B, self.num_keypoints, HM_H, HM_W), dtype=torch.float32, device=x.device) if return_heatmaps else None
-        with torch.cuda.device(self._device):
-            cur = torch.cuda.current_stream(self._device)
-            if cur.cuda_stream == 0:
-                # the legacy default stream cannot be captured into a CUDA graph: run the engine on a side stream that is
-                # ordered after / before the caller's stream (two event waits), so small batches get graph replay
-                if self._side is None:
-                    self._side = torch.cuda.Stream(self._device)
-                self._side.wait_stream(cur)
-                for t in (x, org, kp, idx, hm):
-                    if t is not None:
-                        t.record_stream(self._side)
-                st = C.c_void_p(self._side.cuda_stream)
-            else:
-                st = C.c_void_p(cur.cuda_stream)
-            _lib.check(_lib.lib().vpb_infer(self._handle, C.c_void_p(x.data_ptr()), C.c_void_p(org.data_ptr()), B,
-                                            C.c_void_p(kp.data_ptr()), C.c_void_p(idx.data_ptr()),
-                                            C.c_void_p(hm.data_ptr()) if hm is not None else None, st))
-            if cur.cuda_stream == 0:
-                cur.wait_stream(self._side)
+        self._call_on_stream((x, org, kp, idx, hm), lambda st: _lib.lib().vpb_infer(
+            self._handle, C.c_void_p(x.data_ptr()), C.c_void_p(org.data_ptr()), B, C.c_void_p(kp.data_ptr()),
+            C.c_void_p(idx.data_ptr()), C.c_void_p(hm.data_ptr()) if hm is not None else None, st))
         return (kp, idx, hm) if return_heatmaps else (kp, idx)
 
     def infer_host(self, crops: np.ndarray, org_wh: np.ndarray, kpts_out: np.ndarray | None = None,
@@ -262,6 +263,100 @@ class ViTPose:
         with torch.cuda.device(self._device):
             _lib.check(_lib.lib().vpb_submit_host(self._handle, crops.ctypes.data_as(C.c_void_p), org_wh.ctypes.data_as(C.c_void_p), B,
                                                   kpts_out.ctypes.data_as(C.c_void_p), idx_out.ctypes.data_as(C.c_void_p), int(slot)))
+
+    # ---------------------------------------------------------------------------------------- frame-level calls
+    def _check_frame(self, frame: torch.Tensor, bboxes) -> "tuple[torch.Tensor, torch.Tensor]":
+        self._ensure()
+        if not isinstance(frame, torch.Tensor) or frame.dtype != torch.uint8 or frame.dim() != 3 or frame.shape[2] != 3:
+            raise ValueError("frame must be a uint8 RGB tensor [H,W,3]")
+        dev = torch.device("cuda", self._device)
+        if not frame.is_cuda:
+            frame = frame.to(dev, non_blocking=True)
+        if frame.device.index != self._device:
+            raise ValueError(f"frame lives on {frame.device}, the engine on cuda:{self._device}")
+        bb = torch.as_tensor(bboxes)
+        if bb.is_floating_point():
+            bb = bb.round()                                  # easy_ViTPose/inference.py:253 (round half to even, like numpy)
+        bb = bb.to(device=dev, dtype=torch.int32).reshape(-1, 4).contiguous()
+        if bb.shape[0] > self.max_batch:
+            raise ValueError(f"{bb.shape[0]} boxes exceed max_batch={self.max_batch}")
+        return frame.contiguous(), bb
+
+    def preprocess(self, frame: torch.Tensor, bboxes, pad_bbox: int = 10):
+        """uint8 RGB frame [H,W,3] (CUDA) + boxes [n,4] (x0,y0,x1,y1) -> (crops f32 [n,3,256,192], org_wh i32 [n,2],
+        offs_yx i32 [n,2]): box padding/clipping, pad_image and pre_img of the reference in one kernel
+        (easy_ViTPose/inference.py:259-265,314-318).  Raises ValueError for a box that is empty after clipping."""
+        frame, bb = self._check_frame(frame, bboxes)
+        n = bb.shape[0]
+        dev = frame.device
+        crops = torch.empty((n, 3, IMG_H, IMG_W), dtype=torch.float32, device=dev)
+        org = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        offs = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        if n:
+            with torch.cuda.device(self._device):
+                _lib.check(_lib.lib().vpb_preprocess(C.c_void_p(frame.data_ptr()), frame.shape[0], frame.shape[1], 0,
+                                                     C.c_void_p(bb.data_ptr()), n, int(pad_bbox), C.c_void_p(crops.data_ptr()),
+                                                     C.c_void_p(org.data_ptr()), C.c_void_p(offs.data_ptr()),
+                                                     C.c_void_p(status.data_ptr()), self._stream()))
+            if int(status.item()) & 1:
+                raise ValueError("a box is empty after padding and clipping to the frame")
+        return crops, org, offs
+
+    def infer_frame(self, frame: torch.Tensor, bboxes):
+        """uint8 RGB frame [H,W,3] (CUDA) + boxes [n,4] -> (kpts f32 [n,K,3] (y, x, score) in FRAME pixels, idx i32 [n,K]):
+        the whole per-person loop of VitInference.inference (easy_ViTPose/inference.py:258-272) as one enqueue, no host sync.
+        Boxes that are empty after clipping are not detected here (that would need a sync); use infer_frame_host or
+        preprocess() when the boxes are untrusted."""
+        frame, bb = self._check_frame(frame, bboxes)
+        n = bb.shape[0]
+        kp = torch.empty((n, self.num_keypoints, 3), dtype=torch.float32, device=frame.device)
+        idx = torch.empty((n, self.num_keypoints), dtype=torch.int32, device=frame.device)
+        if n:
+            self._call_on_stream((frame, bb, kp, idx), lambda st: _lib.lib().vpb_infer_frame(
+                self._handle, C.c_void_p(frame.data_ptr()), frame.shape[0], frame.shape[1], C.c_void_p(bb.data_ptr()), n,
+                C.c_void_p(kp.data_ptr()), C.c_void_p(idx.data_ptr()), st))
+        return kp, idx
+
+    @staticmethod
+    def _host_frame_args(frame: np.ndarray, bboxes: np.ndarray):
+        if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3:
+            raise ValueError("frame must be a uint8 RGB array [H,W,3]")
+        bb = np.asarray(bboxes)
+        if bb.dtype.kind == "f":
+            bb = bb.round()
+        return np.ascontiguousarray(frame), np.ascontiguousarray(bb.reshape(-1, 4), np.int32)
+
+    def infer_frame_host(self, frame: np.ndarray, bboxes: np.ndarray):
+        """HOST frame + boxes in, HOST keypoints out (vpb_infer_frame_host): H2D of the uint8 frame, the path, D2H, sync.
+        More than max_batch boxes are processed in chunks."""
+        self._ensure()
+        frame, bb = self._host_frame_args(frame, bboxes)
+        n = bb.shape[0]
+        kp = np.empty((n, self.num_keypoints, 3), np.float32)
+        idx = np.empty((n, self.num_keypoints), np.int32)
+        with torch.cuda.device(self._device):
+            for s in range(0, n, self.max_batch):
+                m = min(self.max_batch, n - s)
+                _lib.check_value(_lib.lib().vpb_infer_frame_host(
+                    self._handle, frame.ctypes.data_as(C.c_void_p), frame.shape[0], frame.shape[1], bb[s:s + m].ctypes.data_as(C.c_void_p), m,
+                    kp[s:s + m].ctypes.data_as(C.c_void_p), idx[s:s + m].ctypes.data_as(C.c_void_p), self._stream()))
+        return kp, idx
+
+    def submit_frame_host(self, frame: np.ndarray, bboxes: np.ndarray, kpts_out: np.ndarray, idx_out: np.ndarray, slot: int) -> None:
+        """Asynchronous vpb_submit_frame_host (wait with wait_host(slot)): uint8 frame [H,W,3], int32 boxes [n,4] (already
+        rounded), float32 kpts_out [n,K,3], int32 idx_out [n,K]; all C-contiguous, alive and unmodified until the wait."""
+        self._ensure()
+        n = bboxes.shape[0]
+        if frame.dtype != np.uint8 or bboxes.dtype != np.int32 or kpts_out.dtype != np.float32 or idx_out.dtype != np.int32:
+            raise TypeError("submit_frame_host takes a uint8 frame, int32 boxes / idx and float32 keypoints")
+        if frame.ndim != 3 or frame.shape[2] != 3 or bboxes.shape != (n, 4) or kpts_out.shape != (n, self.num_keypoints, 3) \
+                or idx_out.shape != (n, self.num_keypoints) or not all(a.flags.c_contiguous for a in (frame, bboxes, kpts_out, idx_out)):
+            raise ValueError("submit_frame_host: wrong shapes or non-contiguous arrays")
+        with torch.cuda.device(self._device):
+            _lib.check_value(_lib.lib().vpb_submit_frame_host(
+                self._handle, frame.ctypes.data_as(C.c_void_p), frame.shape[0], frame.shape[1], bboxes.ctypes.data_as(C.c_void_p), n,
+                kpts_out.ctypes.data_as(C.c_void_p), idx_out.ctypes.data_as(C.c_void_p), int(slot)))
 
     def wait_host(self, slot: int) -> None:
         _lib.check(_lib.lib().vpb_wait_host(self._handle, int(slot)))

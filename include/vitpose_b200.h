@@ -86,6 +86,34 @@ int vpb_wait_host(vpb_engine* e, int32_t slot);
 void* vpb_host_alloc(int64_t bytes);   /* cudaHostAlloc; NULL on failure */
 void vpb_host_free(void* p);
 
+/* ---- frame-level entry points: the per-person loop of VitInference.inference
+ * (easy_ViTPose/inference.py:258-272) as one batched call.
+ *
+ * vpb_preprocess replaces, for all n boxes of a frame at once: the +-pad_bbox box padding and clipping (:259-261), the
+ * crop (:264), pad_image(crop, 3/4) (vit_utils/inference.py:41-70) and VitInference.pre_img (:314-318: cv2 uint8
+ * INTER_LINEAR resize to 192x256, /255, (x-MEAN)/STD in float64, CHW float32).  Bit-exact with cv2 4.13.
+ *   d_frame u8 [frame_h, frame_w, 3] RGB, row pitch pitch_bytes (0 = packed);  d_bboxes i32 [n,4] (x0,y0,x1,y1), already
+ *   rounded as `res_pd[:, :4].round().astype(int)` (:253);  d_crops f32 [n,3,256,192];  d_org_wh i32 [n,2] padded canvas
+ *   (w,h) = what pre_img returns as (org_w, org_h);  d_offs_yx i32 [n,2] = (y0 - top_pad, x0 - left_pad), the offset :270
+ *   adds;  d_status i32 [1] or NULL: bit 0 is OR-ed in when a box is empty after clipping (the reference raises there;
+ *   the kernel emits a black crop with org_wh = 0). */
+int vpb_preprocess(const uint8_t* d_frame, int32_t frame_h, int32_t frame_w, int64_t pitch_bytes, const int32_t* d_bboxes,
+                   int32_t n, int32_t pad_bbox, float* d_crops, int32_t* d_org_wh, int32_t* d_offs_yx, int32_t* d_status,
+                   void* stream);
+/* vpb_decode with the :270 offsets applied in the same kernel: keypoints come out in FRAME pixels. */
+int vpb_decode_frame(const float* d_heatmaps, int32_t n, int32_t k, const int32_t* d_org_wh, const int32_t* d_offs_yx,
+                     float* d_kpts, int32_t* d_idx, int32_t wrap_batch, void* stream);
+/* frame + boxes on the device -> d_kpts f32 [n,K,3] (y, x, score) in frame pixels, d_idx i32 [n,K] or NULL; n <= max_batch.
+ * pad_bbox is the reference's 10. */
+int vpb_infer_frame(vpb_engine* e, const uint8_t* d_frame, int32_t frame_h, int32_t frame_w, const int32_t* d_bboxes,
+                    int32_t n, float* d_kpts, int32_t* d_idx, void* stream);
+/* Same with HOST buffers (H2D of the packed uint8 frame + 16 B per box, D2H of the keypoints, stream sync); empty boxes
+ * return VPB_ERR_ARG where the reference raises.  The pipelined form shares its slots and vpb_wait_host with vpb_submit_host. */
+int vpb_infer_frame_host(vpb_engine* e, const uint8_t* h_frame, int32_t frame_h, int32_t frame_w, const int32_t* h_bboxes,
+                         int32_t n, float* h_kpts, int32_t* h_idx, void* stream);
+int vpb_submit_frame_host(vpb_engine* e, const uint8_t* h_frame, int32_t frame_h, int32_t frame_w, const int32_t* h_bboxes,
+                          int32_t n, float* h_kpts, int32_t* h_idx, int32_t slot);
+
 /* Introspection used by bench.py / tests. */
 int vpb_kernel_launches(const vpb_engine* e, int32_t batch);          /* kernels one vpb_infer enqueues */
 int vpb_set_option(vpb_engine* e, const char* name, int32_t value);   /* "stop_after", "profile", "pdl", "graph", "ln_fused" */

@@ -59,3 +59,37 @@ def postprocess(ns, heatmaps, org_w, org_h):
             heatmaps=heatmaps, center=np.array([[org_w // 2, org_h // 2]]),
             scale=np.array([[org_w, org_h]]), unbiased=True, use_udp=True)
     return np.concatenate([points[:, :, ::-1], prob], axis=2)
+
+
+class _Permissive(types.ModuleType):
+    """Stand-in for an absent third-party module: any attribute is `object` (enough for `from x import Y` at import time)."""
+    __path__: list = []
+
+    def __getattr__(self, k):
+        if k.startswith("__"):
+            raise AttributeError(k)
+        return object
+
+
+def load_vitinference():
+    """The UNMODIFIED `easy_ViTPose.inference` module (VitInference, pad_image, MEAN, STD).  Its import chain needs
+    ultralytics, matplotlib, skimage, filterpy, ffmpeg (inference.py:10, sort.py:22-29, visualization.py) -- none is
+    touched by the per-person pose loop, so permissive stubs are enough.  The detector is supplied by the caller
+    (oracle/make_golden_frames.py uses a stub that returns fixed boxes)."""
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REF_ROOT}")
+    sys.dont_write_bytecode = True
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "ffmpeg", "ultralytics", "skimage", "skimage.io",
+                 "filterpy", "filterpy.kalman", "lap"):
+        if name not in sys.modules or not hasattr(sys.modules[name], "__path__") and name in ("matplotlib", "skimage", "filterpy"):
+            try:
+                if isinstance(sys.modules.get(name), types.ModuleType) and not getattr(sys.modules[name], "__file__", None):
+                    raise ImportError(name)                      # an empty stub left by load(): replace it
+                importlib.import_module(name)
+            except Exception:
+                sys.modules[name] = _Permissive(name)
+    if hasattr(sys.modules["matplotlib"], "__path__") and not getattr(sys.modules["matplotlib"], "__file__", None):
+        sys.modules["matplotlib"].use = lambda *a, **k: None
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    return importlib.import_module("easy_ViTPose.inference")
