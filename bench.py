@@ -255,12 +255,26 @@ def bench_frame_path(model, B: int, K: int, steps: int, dev) -> dict:
     torch.cuda.synchronize()
     pp_ms = e0.elapsed_time(e1) / reps                 # back-to-back launches on one stream, frame resident in L2/HBM
     out_bytes = B * 3 * 256 * 192 * 4
+    # the fused kernel the frame path actually runs (frame -> bf16 patch rows + token-stream seed), engine profiler events
+    model.set_option("profile", 1)
+    model.profile_collect()
+    with torch.cuda.stream(side):
+        for _ in range(10):
+            model.infer_frame(d_frame, d_boxes)
+    torch.cuda.synchronize()
+    fused_ms, fused_n = model.profile_collect()["crop_preprocess"]
+    model.set_option("profile", 0)
+    D = model.embed_dim
+    fused_bytes = B * 192 * 768 * 2 + B * 192 * D * 4          # bf16 patch rows + fp32 token-stream seed written
     res = {"workload": f"{FH}x{FW} uint8 RGB frame + {B} person boxes per step, host in / host out",
            "value": B * steps / dt, "unit": "crops/s", "frames_per_s": steps / dt, "steps": steps,
            "api": "vpb_submit_frame_host / vpb_wait_host (C ABI), 2 frames in flight, pinned host buffers",
            "h2d_bytes_per_step": FH * FW * 3 + B * 16, "d2h_bytes_per_step": B * K * 3 * 4 + B * K * 4,
            "preprocess_kernel": {"ms_per_call": pp_ms, "bytes_written": out_bytes, "GBps_written": out_bytes / (pp_ms * 1e-3) / 1e9,
-                                 "note": "vpb_preprocess, CUDA events around 50 back-to-back launches"}}
+                                 "note": "vpb_preprocess (f32 crops), CUDA events around 50 back-to-back launches"},
+           "fused_gather_kernel": {"ms_per_call": fused_ms / max(1, fused_n), "bytes_written": fused_bytes,
+                                   "GBps_written": fused_bytes / (fused_ms / max(1, fused_n) * 1e-3) / 1e9,
+                                   "note": "frame_to_patch_rows inside vpb_infer_frame: replaces crop_resize_normalise + patch_im2col"}}
     try:
         import cv2
         from oracle import preproc_oracle as PO              # geometry helpers only; the resize below is cv2 itself
@@ -430,7 +444,7 @@ def run_gpu(args) -> None:
 
     frame_path = None
     if world == 1:
-        frame_path = bench_frame_path(model, B, K, max(5, args.steps // 4), dev)
+        frame_path = bench_frame_path(model, B, K, max(5, args.steps // 2), dev)
 
     if rank == 0:
         peaks, peak_src = measured_peaks()

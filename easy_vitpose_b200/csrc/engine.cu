@@ -253,9 +253,8 @@ struct vpb_engine {
   std::vector<cudaStream_t> l2_streams;
   float* g_kpts = nullptr;      // graph-owned outputs / decode inputs: the captured chain only touches engine memory
   int32_t *g_idx = nullptr, *g_org = nullptr, *g_offs = nullptr;
-  // frame-level entry points (crop pre-processing on the GPU): crops / canvas sizes / frame offsets produced by
-  // crop_resize_normalise, the status word it flags empty boxes in, and per-slot frame + box staging for the host variants
-  float* pp_crops = nullptr;
+  // frame-level entry points (crop pre-processing on the GPU): canvas sizes / frame offsets produced by frame_to_patch_rows,
+  // the status word it flags empty boxes in, and per-slot frame + box staging for the host variants
   int32_t *pp_org = nullptr, *pp_offs = nullptr, *pp_status = nullptr;
   uint8_t* frame_stage[2] = {nullptr, nullptr};
   size_t frame_cap[2] = {0, 0};
@@ -479,7 +478,6 @@ extern "C" int vpb_finalize(vpb_engine* e) {
   VPB_TRY(dev_alloc(e, &e->g_idx, B * e->K));
   VPB_TRY(dev_alloc(e, &e->g_org, B * 2));
   VPB_TRY(dev_alloc(e, &e->g_offs, B * 2));
-  VPB_TRY(dev_alloc(e, &e->pp_crops, B * 3 * 256 * 192));
   VPB_TRY(dev_alloc(e, &e->pp_org, B * 2));
   VPB_TRY(dev_alloc(e, &e->pp_offs, B * 2));
   VPB_TRY(dev_alloc(e, &e->pp_status, 1));
@@ -558,6 +556,27 @@ static int patch_gather(vpb_engine* e, const float* d_crops, int B, cudaStream_t
                   reinterpret_cast<const float4*>(e->pos_bias), reinterpret_cast<float4*>(e->x), e->D));
   e->prof.end(st);
   return VPB_OK;
+}
+// Where a batch of patch rows comes from: normalised f32 crops (patch_im2col) or a uint8 frame + boxes (frame_to_patch_rows:
+// crop pre-processing fused with the im2col; it also fills pp_org / pp_offs for the decode).
+struct Source {
+  const float* crops = nullptr;
+  const uint8_t* frame = nullptr;
+  int fh = 0, fw = 0;
+  const int32_t* bboxes = nullptr;
+};
+static int frame_gather(vpb_engine* e, const Source& src, int B, cudaStream_t st) {
+  FramePatchParams q;
+  q.pp.frame = src.frame; q.pp.pitch = static_cast<long long>(src.fw) * 3; q.pp.fh = src.fh; q.pp.fw = src.fw; q.pp.bboxes = src.bboxes;
+  q.pp.n = B; q.pp.pad = 10; q.pp.crops = nullptr; q.pp.org_wh = e->pp_org; q.pp.offs_yx = e->pp_offs; q.pp.status = e->pp_status;
+  q.rows = e->patch_rows; q.pos_bias = reinterpret_cast<const float4*>(e->pos_bias); q.stream = reinterpret_cast<float4*>(e->x); q.D = e->D;
+  e->prof.begin(KC_PREPROCESS, st);
+  CU_TRY(launch_k(frame_to_patch_rows, dim3(B, 16), dim3(384), 0, st, q));
+  e->prof.end(st);
+  return VPB_OK;
+}
+static int gather(vpb_engine* e, const Source& src, int B, cudaStream_t st) {
+  return src.crops ? patch_gather(e, src.crops, B, st) : frame_gather(e, src, B, st);
 }
 // everything after the patch gather, up to last_norm
 static int backbone(vpb_engine* e, int B, cudaStream_t st) {
@@ -722,9 +741,13 @@ extern "C" int vpb_decode_frame(const float* d_heatmaps, int32_t n, int32_t k, c
   return decode_launch(d_heatmaps, n, k, d_org_wh, d_offs_yx, d_kpts, d_idx, wrap_batch, stream);
 }
 
-static int infer_enqueue(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, const int32_t* d_offs_yx, int32_t batch,
+static int infer_enqueue(vpb_engine* e, const Source& src, const int32_t* d_org_wh, const int32_t* d_offs_yx, int32_t batch,
                          float* d_kpts, int32_t* d_idx, float* heat, void* stream) {
-  VPB_TRY(vpb_forward(e, d_crops, batch, heat, stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VPB_TRY(gather(e, src, batch, st));
+  VPB_TRY(backbone(e, batch, st));
+  if (e->stop_after && e->stop_after <= 10) return VPB_OK;
+  VPB_TRY(head(e, batch, heat, st));
   if (e->stop_after) return VPB_OK;
   e->prof.begin(KC_DECODE, static_cast<cudaStream_t>(stream));
   VPB_TRY(decode_launch(heat, batch, e->K, d_org_wh, d_offs_yx, d_kpts, d_idx, 0, stream));
@@ -733,21 +756,21 @@ static int infer_enqueue(vpb_engine* e, const float* d_crops, const int32_t* d_o
 }
 
 // crops -> keypoints; d_offs_yx (nullable) moves the keypoints from crop to frame coordinates inside the decode kernel
-static int infer_core(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, const int32_t* d_offs_yx, int32_t batch,
+static int infer_core(vpb_engine* e, const Source& src, const int32_t* d_org_wh, const int32_t* d_offs_yx, int32_t batch,
                       float* d_kpts, int32_t* d_idx, float* d_heatmaps, void* stream) {
   float* heat = d_heatmaps ? d_heatmaps : e->heat;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VPB_TRY(apply_l2_policy(e, st));
   if (!e->use_graph || e->prof.on || e->stop_after || st == nullptr)      // the legacy default stream cannot be captured
-    return infer_enqueue(e, d_crops, d_org_wh, d_offs_yx, batch, d_kpts, d_idx, heat, stream);
+    return infer_enqueue(e, src, d_org_wh, d_offs_yx, batch, d_kpts, d_idx, heat, stream);
   vpb_engine::GraphEntry* g = nullptr;
   for (auto& c : e->graphs)
     if (c.batch == batch) g = &c;
   if (!g) {                                                               // first use of this batch size: run eagerly
     e->graphs.push_back({batch, 1, nullptr});
-    return infer_enqueue(e, d_crops, d_org_wh, d_offs_yx, batch, d_kpts, d_idx, heat, stream);
+    return infer_enqueue(e, src, d_org_wh, d_offs_yx, batch, d_kpts, d_idx, heat, stream);
   }
-  VPB_TRY(patch_gather(e, d_crops, batch, st));
+  VPB_TRY(gather(e, src, batch, st));
   CU_TRY(cudaMemcpyAsync(e->g_org, d_org_wh, static_cast<size_t>(batch) * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   if (d_offs_yx) CU_TRY(cudaMemcpyAsync(e->g_offs, d_offs_yx, static_cast<size_t>(batch) * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   else CU_TRY(cudaMemsetAsync(e->g_offs, 0, static_cast<size_t>(batch) * 2 * sizeof(int32_t), st));
@@ -776,7 +799,9 @@ extern "C" int vpb_infer(vpb_engine* e, const float* d_crops, const int32_t* d_o
                          float* d_heatmaps, void* stream) {
   VPB_TRY(check_ready(e, batch));
   if (!d_crops || !d_org_wh || !d_kpts) return fail(VPB_ERR_ARG, "vpb_infer: null pointer");
-  return infer_core(e, d_crops, d_org_wh, nullptr, batch, d_kpts, d_idx, d_heatmaps, stream);
+  Source src;
+  src.crops = d_crops;
+  return infer_core(e, src, d_org_wh, nullptr, batch, d_kpts, d_idx, d_heatmaps, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ frame-level entry points
@@ -798,16 +823,16 @@ extern "C" int vpb_preprocess(const uint8_t* d_frame, int32_t frame_h, int32_t f
 
 static int infer_frame_enqueue(vpb_engine* e, const uint8_t* d_frame, int32_t frame_h, int32_t frame_w, const int32_t* d_bboxes,
                                int32_t n, float* d_kpts, int32_t* d_idx, cudaStream_t st) {
-  e->prof.begin(KC_PREPROCESS, st);
-  VPB_TRY(vpb_preprocess(d_frame, frame_h, frame_w, 0, d_bboxes, n, 10, e->pp_crops, e->pp_org, e->pp_offs, e->pp_status, st));
-  e->prof.end(st);
-  return infer_core(e, e->pp_crops, e->pp_org, e->pp_offs, n, d_kpts, d_idx, nullptr, st);
+  Source src;                   // the crops are never materialised: frame_to_patch_rows writes the bf16 patch rows directly
+  src.frame = d_frame; src.fh = frame_h; src.fw = frame_w; src.bboxes = d_bboxes;
+  VPB_TRY(apply_l2_policy(e, st));
+  return infer_core(e, src, e->pp_org, e->pp_offs, n, d_kpts, d_idx, nullptr, st);
 }
 
 extern "C" int vpb_infer_frame(vpb_engine* e, const uint8_t* d_frame, int32_t frame_h, int32_t frame_w, const int32_t* d_bboxes,
                                int32_t n, float* d_kpts, int32_t* d_idx, void* stream) {
   VPB_TRY(check_ready(e, n));
-  if (!d_frame || !d_bboxes || !d_kpts) return fail(VPB_ERR_ARG, "vpb_infer_frame: null pointer");
+  if (!d_frame || !d_bboxes || !d_kpts || frame_h < 1 || frame_w < 1) return fail(VPB_ERR_ARG, "vpb_infer_frame: bad argument");
   return infer_frame_enqueue(e, d_frame, frame_h, frame_w, d_bboxes, n, d_kpts, d_idx, static_cast<cudaStream_t>(stream));
 }
 

@@ -15,6 +15,8 @@
 // borders, the vertical pass clamps only the row indices.  Normalisation is a 3x256 table computed in float64, so the
 // crops are bit-identical to the reference's.
 #pragma once
+#include <cuda_bf16.h>
+
 #include <cstdint>
 
 #include "ptx.cuh"
@@ -37,9 +39,12 @@ struct PreprocParams {
 
 struct PpAxis { int i0, i1, a0, a1; };
 
-// destination index d of `dn` -> the two source indices and int16 weights over a source of `sn` samples
-__device__ __forceinline__ PpAxis pp_axis(int d, int dn, int sn, bool clamp_fraction) {
-  const double scale = __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(dn), static_cast<double>(sn)));
+// cv2: scale = 1 / (dst / src) in double
+__device__ __forceinline__ double pp_scale(int dn, int sn) {
+  return __ddiv_rn(1.0, __ddiv_rn(static_cast<double>(dn), static_cast<double>(sn)));
+}
+// destination index d -> the two source indices and int16 weights over a source of `sn` samples
+__device__ __forceinline__ PpAxis pp_axis(int d, double scale, int sn, bool clamp_fraction) {
   const float f = static_cast<float>(__dadd_rn(__dmul_rn(static_cast<double>(d) + 0.5, scale), -0.5));
   int s = __float2int_rd(f);
   float fr = __fsub_rn(f, static_cast<float>(s));
@@ -57,13 +62,12 @@ __device__ __forceinline__ PpAxis pp_axis(int d, int dn, int sn, bool clamp_frac
 
 __global__ void __launch_bounds__(PP_W) crop_resize_normalise(const PreprocParams p) {
   __shared__ float s_lut[3][256];
+  __shared__ PpAxis s_ay[PP_ROWS];
   const int crop = blockIdx.x, dx = threadIdx.x, dy0 = blockIdx.y * PP_ROWS;
-  {
-    const double mean[3] = {0.485, 0.456, 0.406}, stdv[3] = {0.229, 0.224, 0.225};   // inference.py:32-33
-    for (int i = dx; i < 768; i += PP_W) {
-      const int c = i >> 8, v = i & 255;
-      s_lut[c][v] = static_cast<float>(__ddiv_rn(__dsub_rn(__ddiv_rn(static_cast<double>(v), 255.0), mean[c]), stdv[c]));
-    }
+  for (int i = dx; i < 768; i += PP_W) {                   // inference.py:32-33 MEAN / STD, float64 as in pre_img
+    const int c = i >> 8, v = i & 255;
+    const double mean = c == 0 ? 0.485 : (c == 1 ? 0.456 : 0.406), stdv = c == 0 ? 0.229 : (c == 1 ? 0.224 : 0.225);
+    s_lut[c][v] = static_cast<float>(__ddiv_rn(__dsub_rn(__ddiv_rn(static_cast<double>(v), 255.0), mean), stdv));
   }
   const int* bb = p.bboxes + 4 * crop;
   const int x0 = min(max(bb[0] - p.pad, 0), p.fw), x1 = min(max(bb[2] + p.pad, 0), p.fw);
@@ -90,14 +94,17 @@ __global__ void __launch_bounds__(PP_W) crop_resize_normalise(const PreprocParam
     p.org_wh[2 * crop] = cw; p.org_wh[2 * crop + 1] = ch;
     p.offs_yx[2 * crop] = y0 - top; p.offs_yx[2 * crop + 1] = x0 - left;
   }
-  const PpAxis ax = pp_axis(dx, PP_W, cw, true);
+  if (dx < PP_ROWS) s_ay[dx] = pp_axis(dy0 + dx, pp_scale(PP_H, ch), ch, false);   // the row weights are shared by the CTA
+  const PpAxis ax = pp_axis(dx, pp_scale(PP_W, cw), cw, true);
+  __syncthreads();
   const int cx0 = ax.i0 - left, cx1 = ax.i1 - left;          // canvas column -> crop column
   const bool vx0 = cx0 >= 0 && cx0 < w, vx1 = cx1 >= 0 && cx1 < w;
   const uint8_t* col0 = p.frame + static_cast<size_t>(vx0 ? x0 + cx0 : 0) * 3;   // only dereferenced when valid
   const uint8_t* col1 = p.frame + static_cast<size_t>(vx1 ? x0 + cx1 : 0) * 3;
+#pragma unroll 4
   for (int r = 0; r < PP_ROWS; ++r) {
     const int dy = dy0 + r;
-    const PpAxis ay = pp_axis(dy, PP_H, ch, false);
+    const PpAxis ay = s_ay[r];
     const int cy0 = ay.i0 - top, cy1 = ay.i1 - top;
     const bool vy0 = cy0 >= 0 && cy0 < h, vy1 = cy1 >= 0 && cy1 < h;
     const size_t r0 = static_cast<size_t>(vy0 ? y0 + cy0 : 0) * p.pitch, r1 = static_cast<size_t>(vy1 ? y0 + cy1 : 0) * p.pitch;
@@ -111,6 +118,96 @@ __global__ void __launch_bounds__(PP_W) crop_resize_normalise(const PreprocParam
       out[(c * PP_H + dy) * PP_W + dx] = s_lut[c][v];
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same pre-processing fused with the patch-embedding im2col (pointwise.cuh: patch_im2col): frame + boxes -> bf16 patch
+// rows [n*192, 768] directly, so the f32 crops (589 824 B each) are never written or re-read.  Values are bf16(table[v]),
+// i.e. exactly what patch_im2col produces from crop_resize_normalise's output.  One CTA = one crop x one patch row (16 image
+// rows incl. the conv's 2-pixel zero border); thread (ky, xchunk) = 8 consecutive kx for the 3 channels -> three 16 B stores.
+// Like patch_im2col, the launch also seeds the fp32 token stream with pos_embed + conv bias (vit.py:382).
+struct FramePatchParams {
+  PreprocParams pp;             // crops / status unused
+  __nv_bfloat16* rows;          // [n*192, 768]
+  const float4* pos_bias;       // [192*D/4]
+  float4* stream;               // [n*192*D/4]
+  int D;
+};
+
+__global__ void __launch_bounds__(384) frame_to_patch_rows(const FramePatchParams q) {
+  __shared__ uint16_t s_lut[3][256];
+  __shared__ PpAxis s_ay[16];
+  __shared__ PpAxis s_ax[PP_W];
+  const PreprocParams& p = q.pp;
+  const int crop = blockIdx.x, py = blockIdx.y, tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();                                               // the previous step may still be reading patch rows / the stream
+  {
+    const int per_crop4 = 192 * q.D / 4, per_cta4 = per_crop4 / 16;      // this CTA seeds 1/16 of its crop's tokens
+    const float4* src = q.pos_bias + py * per_cta4;
+    float4* dst = q.stream + static_cast<size_t>(crop) * per_crop4 + py * per_cta4;
+    for (int j = tid; j < per_cta4; j += 384) dst[j] = __ldg(src + j);
+  }
+  for (int i = tid; i < 768; i += 384) {
+    const int c = i >> 8, v = i & 255;
+    const double mean = c == 0 ? 0.485 : (c == 1 ? 0.456 : 0.406), stdv = c == 0 ? 0.229 : (c == 1 ? 0.224 : 0.225);
+    const float f = static_cast<float>(__ddiv_rn(__dsub_rn(__ddiv_rn(static_cast<double>(v), 255.0), mean), stdv));
+    s_lut[c][v] = __bfloat16_as_ushort(__float2bfloat16_rn(f));
+  }
+  const int* bb = p.bboxes + 4 * crop;
+  const int x0 = min(max(bb[0] - p.pad, 0), p.fw), x1 = min(max(bb[2] + p.pad, 0), p.fw);
+  const int y0 = min(max(bb[1] - p.pad, 0), p.fh), y1 = min(max(bb[3] + p.pad, 0), p.fh);
+  int w = x1 - x0, h = y1 - y0;
+  const bool empty = w <= 0 || h <= 0;
+  if (empty) { w = 0; h = 0; }
+  int cw = max(w, 1), ch = max(h, 1), left = 0, top = 0;    // an empty box reads nothing: a black crop, as in crop_resize_normalise
+  if (!empty) {
+    if (4 * w < 3 * h) { cw = (3 * h) / 4; left = (cw - w) / 2; }
+    else { ch = (4 * w) / 3; top = (ch - h) / 2; }
+  }
+  if (tid == 0 && py == 0) {
+    if (empty && p.status) atomicOr(p.status, 1);
+    p.org_wh[2 * crop] = empty ? 0 : cw; p.org_wh[2 * crop + 1] = empty ? 0 : ch;
+    p.offs_yx[2 * crop] = y0 - top; p.offs_yx[2 * crop + 1] = x0 - left;
+  }
+  if (tid < PP_W) s_ax[tid] = pp_axis(tid, pp_scale(PP_W, cw), cw, true);
+  else if (tid < PP_W + 16) {
+    const int dy = 16 * py - 2 + (tid - PP_W);
+    if (dy >= 0) s_ay[tid - PP_W] = pp_axis(dy, pp_scale(PP_H, ch), ch, false);
+  }
+  __syncthreads();
+  const int ky = tid / 24, xc = tid % 24;
+  const int dy = 16 * py - 2 + ky, dx0 = xc * 8 - 2;
+  uint32_t o[3][4] = {};
+  if (dy >= 0) {
+    const PpAxis ay = s_ay[ky];
+    const int cy0 = ay.i0 - top, cy1 = ay.i1 - top;
+    const bool vy0 = cy0 >= 0 && cy0 < h, vy1 = cy1 >= 0 && cy1 < h;
+    const uint8_t* r0 = p.frame + static_cast<size_t>(vy0 ? y0 + cy0 : 0) * p.pitch;
+    const uint8_t* r1 = p.frame + static_cast<size_t>(vy1 ? y0 + cy1 : 0) * p.pitch;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int dx = dx0 + j;
+      if (dx < 0 || dx >= PP_W) continue;                    // conv zero padding: stays 0
+      const PpAxis ax = s_ax[dx];
+      const int cx0 = ax.i0 - left, cx1 = ax.i1 - left;
+      const bool vx0 = cx0 >= 0 && cx0 < w, vx1 = cx1 >= 0 && cx1 < w;
+      const int f0 = (vx0 ? x0 + cx0 : 0) * 3, f1 = (vx1 ? x0 + cx1 : 0) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int p00 = (vy0 && vx0) ? r0[f0 + c] : 0, p01 = (vy0 && vx1) ? r0[f1 + c] : 0;
+        const int p10 = (vy1 && vx0) ? r1[f0 + c] : 0, p11 = (vy1 && vx1) ? r1[f1 + c] : 0;
+        const int s0 = p00 * ax.a0 + p01 * ax.a1, s1 = p10 * ax.a0 + p11 * ax.a1;
+        int v = (((ay.a0 * (s0 >> 4)) >> 16) + ((ay.a1 * (s1 >> 4)) >> 16) + 2) >> 2;
+        v = min(max(v, 0), 255);
+        o[c][j >> 1] |= static_cast<uint32_t>(s_lut[c][v]) << ((j & 1) * 16);
+      }
+    }
+  }
+  const int px = xc >> 1, kx0 = (xc & 1) * 8;
+  __nv_bfloat16* dst = q.rows + ((static_cast<size_t>(crop) * 16 + py) * 12 + px) * 768 + ky * 16 + kx0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) *reinterpret_cast<uint4*>(dst + c * 256) = make_uint4(o[c][0], o[c][1], o[c][2], o[c][3]);
 }
 
 }  // namespace vpb

@@ -88,9 +88,13 @@ def test_infer_frame_vs_reference_loop(golden_dir, name):
     kp = kp.cpu().numpy()
     ref = g["kpts"]
     assert kp.shape == ref.shape
-    # the same thing in two steps is bit-identical: preprocess -> infer_crops -> + offsets
+    # infer_frame never materialises the crops (frame_to_patch_rows writes the bf16 patch rows directly); the two-step way
+    # -- preprocess (crop_resize_normalise) -> infer_crops (patch_im2col) -> + offsets -- must be bit-identical
+    n = len(boxes)
+    rows_fused = m.read_buffer("patch_rows", (n * 192, 768), "bf16").view(torch.int16).numpy().copy()
     crops, org, offs = m.preprocess(fr, boxes)
     kp2, idx2 = m.infer_crops(crops, org)
+    assert np.array_equal(m.read_buffer("patch_rows", (n * 192, 768), "bf16").view(torch.int16).numpy(), rows_fused)
     assert np.array_equal(idx2.cpu().numpy(), idx.cpu().numpy())
     assert np.array_equal(P.to_frame_coords(kp2.cpu().numpy(), offs.cpu().numpy()), kp)
     # against the fp32 reference: deviation in pixels of the 256x192 model input, visible keypoints only
