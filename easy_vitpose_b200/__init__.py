@@ -10,4 +10,4 @@ from . import distributed  # noqa: F401
 from .configs import data_cfg, dyn_model_import, model_cfg  # noqa: F401
 from .inference import B200PoseBackend, install  # noqa: F401
 from .model import ViTPose  # noqa: F401
-from .top_down_eval import decode_heatmaps, keypoints_from_heatmaps  # noqa: F401
+from .top_down_eval import decode_heatmaps, decode_topdown, keypoints_from_heatmaps  # noqa: F401

@@ -42,7 +42,31 @@ struct DecodeParams {
   const int* offs_yx;      // [N,2] integer (y, x) added to the keypoints: crop -> frame coordinates (inference.py:270); may be nullptr
   int n, k;
   int wrap_batch;          // sentinel quirk: 0 = previous map wraps inside the crop, 1 = inside the whole call
+  // general transform_preds (post_transforms.py:150-194) for callers other than VitInference.postprocess: per crop
+  // (centre_x, centre_y, scale_x, scale_y) either as float32 (numpy keeps the whole expression in float32) or as float64
+  // (int64 / float64 arrays promote it to float64); both null = the VitInference form above (scale = org, centre = org // 2)
+  const float* cs32 = nullptr;
+  const double* cs64 = nullptr;
 };
+
+// coords (heatmap pixels) -> image pixels: x * (scale / (W-1 or W)) + centre - scale * 0.5, evaluated left to right with one
+// rounding per operation in the type numpy would use (no FMA contraction)
+__device__ __forceinline__ void transform_cs(float xr, float yr, int n_i, const float* cs32, const double* cs64, bool use_udp,
+                                             float& X, float& Y) {
+  if (cs32 != nullptr) {
+    const float cx = cs32[4 * n_i], cy = cs32[4 * n_i + 1], sx = cs32[4 * n_i + 2], sy = cs32[4 * n_i + 3];
+    const float kx = __fdiv_rn(sx, use_udp ? HM_W - 1.0f : static_cast<float>(HM_W));
+    const float ky = __fdiv_rn(sy, use_udp ? HM_H - 1.0f : static_cast<float>(HM_H));
+    X = __fsub_rn(__fadd_rn(__fmul_rn(xr, kx), cx), __fmul_rn(sx, 0.5f));
+    Y = __fsub_rn(__fadd_rn(__fmul_rn(yr, ky), cy), __fmul_rn(sy, 0.5f));
+  } else {
+    const double cx = cs64[4 * n_i], cy = cs64[4 * n_i + 1], sx = cs64[4 * n_i + 2], sy = cs64[4 * n_i + 3];
+    const double kx = __ddiv_rn(sx, use_udp ? HM_W - 1.0 : static_cast<double>(HM_W));
+    const double ky = __ddiv_rn(sy, use_udp ? HM_H - 1.0 : static_cast<double>(HM_H));
+    X = static_cast<float>(__dsub_rn(__dadd_rn(__dmul_rn(static_cast<double>(xr), kx), cx), __dmul_rn(sx, 0.5)));
+    Y = static_cast<float>(__dsub_rn(__dadd_rn(__dmul_rn(static_cast<double>(yr), ky), cy), __dmul_rn(sy, 0.5)));
+  }
+}
 
 __global__ void __launch_bounds__(256) decode_heatmaps(const DecodeParams p) {
   __shared__ float s_rowpass[8][7][11];
@@ -157,9 +181,14 @@ __global__ void __launch_bounds__(256) decode_heatmaps(const DecodeParams p) {
     const float xr = static_cast<float>(static_cast<double>(x) - offx);
     const float yr = static_cast<float>(static_cast<double>(y) - offy);
     const int n_i = g / p.k;
-    const int ow = p.org_wh[2 * n_i], oh = p.org_wh[2 * n_i + 1];
-    const float X = static_cast<float>(static_cast<double>(xr) * (ow / (HM_W - 1.0)) + static_cast<double>(ow / 2) - ow * 0.5);
-    const float Y = static_cast<float>(static_cast<double>(yr) * (oh / (HM_H - 1.0)) + static_cast<double>(oh / 2) - oh * 0.5);
+    float X, Y;
+    if (p.cs32 != nullptr || p.cs64 != nullptr) {
+      transform_cs(xr, yr, n_i, p.cs32, p.cs64, true, X, Y);
+    } else {
+      const int ow = p.org_wh[2 * n_i], oh = p.org_wh[2 * n_i + 1];
+      X = static_cast<float>(static_cast<double>(xr) * (ow / (HM_W - 1.0)) + static_cast<double>(ow / 2) - ow * 0.5);
+      Y = static_cast<float>(static_cast<double>(yr) * (oh / (HM_H - 1.0)) + static_cast<double>(oh / 2) - oh * 0.5);
+    }
     float* o = p.kpts + static_cast<size_t>(g) * 3;
     float Yf = Y, Xf = X;
     if (p.offs_yx != nullptr) {
@@ -172,6 +201,136 @@ __global__ void __launch_bounds__(256) decode_heatmaps(const DecodeParams p) {
     o[0] = Yf; o[1] = Xf; o[2] = mx;
     if (p.idx != nullptr) p.idx[g] = amax;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The decode modes VitInference never selects, for mmpose-style callers of
+// keypoints_from_heatmaps (vit_utils/top_down_eval.py:493-641) with use_udp=False:
+//   mode 0  post_process=None       argmax only                                           :598
+//   mode 1  'default'               +-0.25 px towards the higher neighbour                  :617-631
+//   mode 2  'unbiased'              zero-padded Gaussian modulation + log + _taylor          :600-607, :315-350, :416-456
+//   mode 3  'megvii'                modulation first, argmax of the modulated map, +-0.25 + 0.5, score / 255 + 0.5   :573-574,:629-639
+// One CTA per map (the modulation needs every pixel and the global maximum of the blurred map); the map lives in shared memory.
+// The blur is cv2's with a zero border (what `_gaussian_blur`'s padding amounts to), same accumulation order as above.
+enum : int { DECODE_NONE = 0, DECODE_DEFAULT = 1, DECODE_UNBIASED = 2, DECODE_MEGVII = 3, DECODE_DARK_UDP = 4 };
+
+struct DecodeModesParams {
+  const float* heatmaps;   // [N,K,64,48]
+  const float* cs32;       // [N,4] (centre_x, centre_y, scale_x, scale_y) float32, or
+  const double* cs64;      // the same as float64 (exactly one of the two is non-null)
+  float* kpts;             // [N,K,3] (y, x, score)
+  int* idx;                // [N,K] flat argmax of the map the coordinates were read from (may be nullptr)
+  int n, k, mode;
+};
+
+// np.argmax / np.amax over the 3072 values in shared memory; result broadcast to every thread
+__device__ __forceinline__ void block_argmax(const float* s_map, float* s_rv, int* s_ri, float& bv, int& bi) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  bv = -INFINITY; bi = 0x7fffffff;
+  for (int i = tid; i < HM_PIX; i += 256)
+    if (arg_better(s_map[i], i, bv, bi)) { bv = s_map[i]; bi = i; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (arg_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  __syncthreads();                                         // previous users of s_rv / s_ri are done
+  if (lane == 0) { s_rv[w] = bv; s_ri[w] = bi; }
+  __syncthreads();
+  bv = s_rv[0]; bi = s_ri[0];
+#pragma unroll
+  for (int j = 1; j < 8; ++j)
+    if (arg_better(s_rv[j], s_ri[j], bv, bi)) { bv = s_rv[j]; bi = s_ri[j]; }
+}
+
+__global__ void __launch_bounds__(256) decode_modes(const DecodeModesParams p) {
+  __shared__ float s_a[HM_PIX];
+  __shared__ float s_b[HM_PIX];
+  __shared__ float s_rv[8];
+  __shared__ int s_ri[8];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  {
+    const float4* h4 = reinterpret_cast<const float4*>(p.heatmaps + static_cast<size_t>(g) * HM_PIX);
+    for (int i = tid; i < HM_PIX / 4; i += 256) reinterpret_cast<float4*>(s_a)[i] = __ldg(h4 + i);
+  }
+  __syncthreads();
+  float mx; int amax;
+  block_argmax(s_a, s_rv, s_ri, mx, amax);                  // raw map: np.argmax, np.amax (= np.max: NaN wins both)
+  if (p.mode == DECODE_UNBIASED || p.mode == DECODE_MEGVII) {
+    // _gaussian_blur (:416-456): zero-padded 11x11 blur, then *= origin_max / max(blurred)
+    for (int i = tid; i < HM_PIX; i += 256) {
+      const int y = i / HM_W, x = i % HM_W;
+      float acc = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 11; ++j) {
+        const int xx = x - 5 + j;
+        acc = __fmaf_rn(c_gauss11[j < 6 ? j : 10 - j], (xx >= 0 && xx < HM_W) ? s_a[y * HM_W + xx] : 0.0f, acc);
+      }
+      s_b[i] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < HM_PIX; i += 256) {
+      const int y = i / HM_W, x = i % HM_W;
+      float acc = __fmul_rn(c_gauss11[5], s_b[i]);
+#pragma unroll
+      for (int d = 1; d <= 5; ++d) {
+        const float lo = y - d >= 0 ? s_b[(y - d) * HM_W + x] : 0.0f, hi = y + d < HM_H ? s_b[(y + d) * HM_W + x] : 0.0f;
+        acc = __fmaf_rn(c_gauss11[5 - d], __fadd_rn(hi, lo), acc);
+      }
+      s_a[i] = acc;                                          // the raw map is no longer needed
+    }
+    __syncthreads();
+    float bmax; int bidx;
+    block_argmax(s_a, s_rv, s_ri, bmax, bidx);
+    const float ratio = __fdiv_rn(mx, bmax);
+    for (int i = tid; i < HM_PIX; i += 256) {
+      float v = __fmul_rn(s_a[i], ratio);
+      if (p.mode == DECODE_UNBIASED) v = logf(v != v ? v : fmaxf(v, 1e-10f));      // np.log(np.maximum(., 1e-10)), NaN propagates
+      s_a[i] = v;
+    }
+    __syncthreads();
+    if (p.mode == DECODE_MEGVII) block_argmax(s_a, s_rv, s_ri, mx, amax);          // megvii reads everything from the modulated map
+  }
+  if (tid != 0) return;
+  float cx = -1.0f, cy = -1.0f;
+  if (mx > 0.0f) { cx = static_cast<float>(amax % HM_W); cy = static_cast<float>(amax / HM_W); }
+  const int px = static_cast<int>(cx), py = static_cast<int>(cy);
+  auto at = [&](int yy, int xx) { return s_a[yy * HM_W + xx]; };
+  if (p.mode == DECODE_DEFAULT || p.mode == DECODE_MEGVII) {
+    if (1 < px && px < HM_W - 1 && 1 < py && py < HM_H - 1) {
+      const float dx = __fsub_rn(at(py, px + 1), at(py, px - 1)), dy = __fsub_rn(at(py + 1, px), at(py - 1, px));
+      const float sx = dx != dx ? dx : (dx > 0.f ? 1.f : (dx < 0.f ? -1.f : 0.f));      // np.sign (NaN stays NaN)
+      const float sy = dy != dy ? dy : (dy > 0.f ? 1.f : (dy < 0.f ? -1.f : 0.f));
+      cx = __fadd_rn(cx, __fmul_rn(sx, 0.25f)); cy = __fadd_rn(cy, __fmul_rn(sy, 0.25f));
+      if (p.mode == DECODE_MEGVII) { cx = __fadd_rn(cx, 0.5f); cy = __fadd_rn(cy, 0.5f); }
+    }
+  } else if (p.mode == DECODE_UNBIASED) {
+    if (1 < px && px < HM_W - 2 && 1 < py && py < HM_H - 2) {                           // _taylor (:315-350), float32 derivatives
+      const float c2 = __fmul_rn(2.0f, at(py, px));
+      const float dx = __fmul_rn(0.5f, __fsub_rn(at(py, px + 1), at(py, px - 1)));
+      const float dy = __fmul_rn(0.5f, __fsub_rn(at(py + 1, px), at(py - 1, px)));
+      const float dxx = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(at(py, px + 2), c2), at(py, px - 2)));
+      const float dyy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(at(py + 2, px), c2), at(py - 2, px)));
+      const float dxy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(__fsub_rn(at(py + 1, px + 1), at(py - 1, px + 1)), at(py + 1, px - 1)),
+                                                   at(py - 1, px - 1)));
+      if (__fsub_rn(__fmul_rn(dxx, dyy), __fmul_rn(dxy, dxy)) != 0.0f) {
+        // the reference inverts the float32 2x2 with LAPACK; closed form in float64 here (tolerance stated in the tests)
+        const double a = dxx, b = dxy, d = dyy, det = a * d - b * b;
+        cx = static_cast<float>(static_cast<double>(cx) - (d * dx - b * dy) / det);
+        cy = static_cast<float>(static_cast<double>(cy) - (a * dy - b * dx) / det);
+      }
+    }
+  }
+  float X, Y;
+  transform_cs(cx, cy, g / p.k, p.cs32, p.cs64, false, X, Y);
+  float score = mx;
+  if (p.mode == DECODE_MEGVII) score = __fadd_rn(__fdiv_rn(mx, 255.0f), 0.5f);
+  float* o = p.kpts + static_cast<size_t>(g) * 3;
+  o[0] = Y; o[1] = X; o[2] = score;
+  if (p.idx != nullptr) p.idx[g] = amax;
 }
 
 }  // namespace vpb

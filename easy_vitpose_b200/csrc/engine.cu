@@ -736,6 +736,26 @@ extern "C" int vpb_decode(const float* d_heatmaps, int32_t n, int32_t k, const i
                           int32_t wrap_batch, void* stream) {
   return decode_launch(d_heatmaps, n, k, d_org_wh, nullptr, d_kpts, d_idx, wrap_batch, stream);
 }
+extern "C" int vpb_decode_modes(const float* d_heatmaps, int32_t n, int32_t k, int32_t mode, const float* d_cs32, const double* d_cs64,
+                                float* d_kpts, int32_t* d_idx, void* stream) {
+  if (!d_heatmaps || !d_kpts || (d_cs32 == nullptr) == (d_cs64 == nullptr))
+    return fail(VPB_ERR_ARG, "vpb_decode_modes: null pointer, or not exactly one of d_cs32 / d_cs64");
+  if (n < 0 || k < 1 || mode < DECODE_NONE || mode > DECODE_DARK_UDP) return fail(VPB_ERR_ARG, "vpb_decode_modes: n=%d k=%d mode=%d", n, k, mode);
+  if (n == 0) return VPB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == DECODE_DARK_UDP) {                            // one reference call on the whole array: wrap_batch = 1
+    DecodeParams p;
+    p.heatmaps = d_heatmaps; p.org_wh = nullptr; p.kpts = d_kpts; p.idx = d_idx; p.n = n; p.k = k; p.wrap_batch = 1; p.offs_yx = nullptr;
+    p.cs32 = d_cs32; p.cs64 = d_cs64;
+    CU_TRY(launch_k(decode_heatmaps, dim3(cdiv(static_cast<long long>(n) * k, 8)), dim3(256), 0, st, p));
+  } else {
+    DecodeModesParams p;
+    p.heatmaps = d_heatmaps; p.cs32 = d_cs32; p.cs64 = d_cs64; p.kpts = d_kpts; p.idx = d_idx; p.n = n; p.k = k; p.mode = mode;
+    CU_TRY(launch_k(decode_modes, dim3(n * k), dim3(256), 0, st, p));
+  }
+  CU_TRY(cudaGetLastError());
+  return VPB_OK;
+}
 extern "C" int vpb_decode_frame(const float* d_heatmaps, int32_t n, int32_t k, const int32_t* d_org_wh, const int32_t* d_offs_yx,
                                 float* d_kpts, int32_t* d_idx, int32_t wrap_batch, void* stream) {
   return decode_launch(d_heatmaps, n, k, d_org_wh, d_offs_yx, d_kpts, d_idx, wrap_batch, stream);

@@ -1,9 +1,10 @@
 """keypoints_from_heatmaps on the GPU (the branch VitInference takes), same call shape as the
 reference function at easy_ViTPose/vit_utils/top_down_eval.py:493-641.
 
-Only `unbiased=True, use_udp=True, target_type='GaussianHeatmap', kernel=11` is built -- the branch
-at :586-589 that easy_ViTPose/inference.py:200-203 selects; every other combination raises instead of
-silently computing something else.
+`decode_heatmaps` is the fast form of the branch VitInference takes (unbiased=True, use_udp=True: DARK/UDP with
+centre = scale // 2, easy_ViTPose/inference.py:200-203).  `keypoints_from_heatmaps` covers every GaussianHeatmap
+branch of the reference function with general centre / scale; `decode_topdown` is
+TopdownHeatmapBaseHead.decode on top of it.  CombinedTarget and modulation kernels other than 11 raise.
 """
 from __future__ import annotations
 
@@ -14,7 +15,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["keypoints_from_heatmaps", "decode_heatmaps"]
+__all__ = ["keypoints_from_heatmaps", "decode_heatmaps", "decode_topdown"]
 
 
 def decode_heatmaps(heatmaps: torch.Tensor, org_wh: torch.Tensor, wrap_batch: bool = False):
@@ -37,25 +38,94 @@ def decode_heatmaps(heatmaps: torch.Tensor, org_wh: torch.Tensor, wrap_batch: bo
     return kp, idx
 
 
-def keypoints_from_heatmaps(heatmaps, center, scale, unbiased=False, post_process="default", kernel=11,
-                            valid_radius_factor=0.0546875, use_udp=False, target_type="GaussianHeatmap"):
-    """Reference signature; returns (preds [N,K,2] (x,y) float32, maxvals [N,K,1] float32) as numpy arrays.
+_MODES = {None: 0, "default": 1, "unbiased": 2, "megvii": 3}
 
-    `center` must be scale//2-style integers and `scale` the crop (w,h) exactly as VitInference.postprocess
-    passes them (inference.py:200-203): the kernel derives the centre as scale // 2.
-    """
-    if not (unbiased and use_udp) or str(target_type).lower() != "gaussianheatmap" or kernel != 11 \
-            or post_process not in ("default", "unbiased", True):
-        raise NotImplementedError("only unbiased=True, use_udp=True, GaussianHeatmap, kernel=11 is implemented on the GPU path")
+
+def _centre_scale(center, scale, n: int, device):
+    """-> (cs32 | None, cs64 | None): [n,4] (cx, cy, sx, sy) in the dtype numpy's transform_preds arithmetic would run in
+    (numpy >= 2: two float32 arrays stay float32; int64 / float64 promote to float64)."""
+    center = np.asarray(center); scale = np.asarray(scale)
+    if center.shape != (n, 2) or scale.shape != (n, 2):
+        raise ValueError("center and scale must be [N,2]")
+    if center.dtype == np.float32 and scale.dtype == np.float32:
+        return torch.from_numpy(np.ascontiguousarray(np.concatenate([center, scale], 1))).to(device), None
+    cs = np.concatenate([center.astype(np.float64), scale.astype(np.float64)], 1)
+    return None, torch.from_numpy(np.ascontiguousarray(cs)).to(device)
+
+
+def keypoints_from_heatmaps(heatmaps, center, scale, unbiased=False, post_process="default", kernel=11,
+                            valid_radius_factor=0.0546875, use_udp=False, target_type="GaussianHeatmap", return_idx=False):
+    """Reference signature and semantics (vit_utils/top_down_eval.py:493-641) on the GPU; returns
+    (preds [N,K,2] (x,y) float32, maxvals [N,K,1] float32) as numpy arrays.  `heatmaps` may be a numpy array or a CUDA tensor
+    [N,K,64,48] and is never modified (the reference works on a copy, :545).
+
+    Every GaussianHeatmap branch is built: post_process None / 'default' / 'unbiased' / 'megvii' with use_udp=False, and the
+    DARK/UDP branch (use_udp=True; the one VitInference.postprocess takes).  `kernel` must be 11 (what every reference config
+    uses: the tap table is compiled in); target_type='CombinedTarget' (:580-593) is not built and raises."""
+    # the reference's conflict checks (:548-553) and config normalisation (:556-579), deprecation warnings dropped
+    if unbiased:
+        assert post_process not in [False, None, "megvii"]
+    if post_process in ["megvii", "unbiased"]:
+        assert kernel > 0
+    if use_udp:
+        assert not post_process == "megvii"
+    if post_process is False:
+        post_process = None
+    elif post_process is True:
+        post_process = "unbiased" if unbiased is True else "default"
+    elif post_process == "default" and unbiased is True:
+        post_process = "unbiased"
+    if str(target_type).lower() == "combinedtarget" and use_udp:
+        raise NotImplementedError("target_type='CombinedTarget' is not built (no reference config uses it)")
+    if use_udp and str(target_type).lower() != "gaussianheatmap":
+        raise ValueError("target_type should be either 'GaussianHeatmap' or 'CombinedTarget'")
+    if post_process not in _MODES:
+        raise ValueError(f"unknown post_process {post_process!r}")
+    if kernel != 11 and (use_udp or post_process in ("unbiased", "megvii")):
+        raise NotImplementedError("only the 11x11 modulation kernel (every reference config: modulate_kernel=11) is built")
+
     hm = heatmaps if isinstance(heatmaps, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(heatmaps, np.float32))
     if not hm.is_cuda:
         hm = hm.cuda()
-    scale = np.asarray(scale)
-    center = np.asarray(center)
-    if scale.shape != (hm.shape[0], 2) or center.shape != scale.shape:
-        raise ValueError("center and scale must be [N,2]")
-    if not np.array_equal(center, scale // 2):
-        raise NotImplementedError("center must equal scale // 2 (what VitInference.postprocess passes)")
-    kp, _ = decode_heatmaps(hm, torch.from_numpy(scale.astype(np.int32)), wrap_batch=True)
+    if hm.dim() != 4 or tuple(hm.shape[2:]) != (64, 48):
+        raise ValueError(f"expected [N,K,64,48], got {tuple(hm.shape)}")
+    hm = hm.to(torch.float32).contiguous()
+    N, K = hm.shape[:2]
+    cs32, cs64 = _centre_scale(center, scale, N, hm.device)
+    kp = torch.empty((N, K, 3), dtype=torch.float32, device=hm.device)
+    idx = torch.empty((N, K), dtype=torch.int32, device=hm.device)
+    mode = 4 if use_udp else _MODES[post_process]
+    with torch.cuda.device(hm.device):
+        st = C.c_void_p(torch.cuda.current_stream(hm.device).cuda_stream)
+        _lib.check(_lib.lib().vpb_decode_modes(C.c_void_p(hm.data_ptr()), N, K, mode,
+                                               C.c_void_p(cs32.data_ptr()) if cs32 is not None else None,
+                                               C.c_void_p(cs64.data_ptr()) if cs64 is not None else None,
+                                               C.c_void_p(kp.data_ptr()), C.c_void_p(idx.data_ptr()), st))
     kp = kp.cpu().numpy()
-    return np.ascontiguousarray(kp[:, :, 1::-1]), kp[:, :, 2:3].copy()
+    out = (np.ascontiguousarray(kp[:, :, 1::-1]), kp[:, :, 2:3].copy())
+    return out + (idx.cpu().numpy(),) if return_idx else out
+
+
+def decode_topdown(img_metas, output, test_cfg: "dict | None" = None) -> dict:
+    """TopdownHeatmapBaseHead.decode (vit_models/head/topdown_heatmap_base_head.py:40-103): per-image centre / scale /
+    bbox score from `img_metas`, keypoints_from_heatmaps configured by `test_cfg` (configs/ViTPose_common.py:123-129), and the
+    mmpose result dict: preds [N,K,3] (x, y, score), boxes [N,6] (centre, scale, area = prod(scale * 200), score),
+    image_paths, bbox_ids."""
+    cfg = test_cfg or {}
+    n = len(img_metas)
+    c = np.zeros((n, 2), np.float32); s = np.zeros((n, 2), np.float32)
+    score = np.ones(n)
+    for i, meta in enumerate(img_metas):
+        c[i, :] = meta["center"]; s[i, :] = meta["scale"]
+        if "bbox_score" in meta:
+            score[i] = np.array(meta["bbox_score"]).reshape(-1)[0]
+    preds, maxvals = keypoints_from_heatmaps(
+        output, c, s, unbiased=cfg.get("unbiased_decoding", False), post_process=cfg.get("post_process", "default"),
+        kernel=cfg.get("modulate_kernel", 11), valid_radius_factor=cfg.get("valid_radius_factor", 0.0546875),
+        use_udp=cfg.get("use_udp", False), target_type=cfg.get("target_type", "GaussianHeatmap"))
+    all_preds = np.zeros((n, preds.shape[1], 3), np.float32)
+    all_preds[:, :, 0:2] = preds; all_preds[:, :, 2:3] = maxvals
+    boxes = np.zeros((n, 6), np.float32)
+    boxes[:, 0:2] = c; boxes[:, 2:4] = s; boxes[:, 4] = np.prod(s * 200.0, axis=1); boxes[:, 5] = score
+    return {"preds": all_preds, "boxes": boxes, "image_paths": [m["image_file"] for m in img_metas],
+            "bbox_ids": [m["bbox_id"] for m in img_metas] if n and "bbox_id" in img_metas[0] else None}

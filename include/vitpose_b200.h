@@ -68,6 +68,21 @@ int vpb_forward_features(vpb_engine* e, const float* d_crops, int32_t batch, flo
 int vpb_decode(const float* d_heatmaps, int32_t n, int32_t k, const int32_t* d_org_wh, float* d_kpts, int32_t* d_idx,
                int32_t wrap_batch, void* stream);
 
+/* The other modes of keypoints_from_heatmaps (vit_utils/top_down_eval.py:493-641), with the
+ * general transform_preds (post_processing/post_transforms.py:150-194).  mode: 0 post_process=None (:598), 1 'default' (+-0.25 px,
+ * :617-631), 2 'unbiased' (Gaussian modulation + log + _taylor, :600-607), 3 'megvii' (:573-574,:629-639) -- all use_udp=False --
+ * and 4 = use_udp=True DARK (:576-579) with arbitrary centre / scale.  Exactly one of d_cs32 (f32 [n,4]) / d_cs64 (f64 [n,4]) holds
+ * (centre_x, centre_y, scale_x, scale_y) per crop: float32 arrays keep numpy's arithmetic in float32, int64 / float64 arrays
+ * promote it to float64.  Output layout as vpb_decode: d_kpts f32 [n,k,3] (y, x, score), d_idx i32 [n,k] or NULL.
+ * CombinedTarget (:580-593) is not built: no reference config uses it. */
+#define VPB_DECODE_NONE 0
+#define VPB_DECODE_DEFAULT 1
+#define VPB_DECODE_UNBIASED 2
+#define VPB_DECODE_MEGVII 3
+#define VPB_DECODE_DARK_UDP 4
+int vpb_decode_modes(const float* d_heatmaps, int32_t n, int32_t k, int32_t mode, const float* d_cs32, const double* d_cs64,
+                     float* d_kpts, int32_t* d_idx, void* stream);
+
 /* Replaces the model + postprocess part of VitInference._inference_torch (easy_ViTPose/inference.py:320-328)
  * for a whole batch of crops resident on the device.  d_heatmaps may be NULL. */
 int vpb_infer(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, int32_t batch, float* d_kpts,

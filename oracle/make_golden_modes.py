@@ -1,0 +1,60 @@
+"""Generate tests/golden/decode_modes.npz from the UNMODIFIED reference keypoints_from_heatmaps  --  TEST INFRASTRUCTURE ONLY.
+
+Run here:  python oracle/make_golden_modes.py      
+Maps regenerate from the seed (vitpose_oracle.make_decode_maps); stored: centre/scale in both dtypes and the reference's
+(preds, maxvals) for every mode x use_udp x dtype combination the reference accepts.  Also asserts here that the oracle's
+zero-padded blur equals `_gaussian_blur` bit for bit on every pixel.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import decode_modes_oracle as M, ref_import, vitpose_oracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+N, K, SEED = 4, 17, 401
+COMBOS = [(None, False), ("default", False), ("unbiased", False), ("megvii", False), ("default", True), ("unbiased", True)]
+
+
+def main() -> None:
+    import importlib
+    ns = ref_import.load()
+    tde = importlib.import_module("vit_utils.top_down_eval")
+    maps = O.make_decode_maps(N, K, SEED)
+    taps = O.gaussian_taps(11)
+    blurred = tde._gaussian_blur(maps.copy(), 11)
+    for n in range(N):
+        for k in range(K):
+            mine = M.gaussian_modulate(maps[n, k], taps)
+            assert np.array_equal(mine, blurred[n, k], equal_nan=True), (n, k, float(np.nanmax(np.abs(mine - blurred[n, k]))))
+    print("zero-padded blur + renormalisation: bit-exact vs _gaussian_blur")
+    rs = np.random.RandomState(SEED + 1)
+    center32 = np.stack([rs.uniform(50, 600, N), rs.uniform(50, 400, N)], 1).astype(np.float32)
+    scale32 = np.stack([rs.uniform(60, 400, N), rs.uniform(80, 520, N)], 1).astype(np.float32)
+    scale64 = np.stack([rs.randint(64, 513, N), rs.randint(64, 513, N)], 1).astype(np.int64)
+    center64 = np.stack([rs.randint(0, 900, N), rs.randint(0, 700, N)], 1).astype(np.int64)
+    out = {"meta": np.array([N, K, SEED], np.int64), "center32": center32, "scale32": scale32, "center64": center64, "scale64": scale64}
+    for pp, udp in COMBOS:
+        for tag, (c, s) in {"f32": (center32, scale32), "i64": (center64, scale64)}.items():
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                preds, maxvals = ns.keypoints_from_heatmaps(maps.copy(), c, s, unbiased=False, post_process=pp, kernel=11, use_udp=udp)
+            key = f"{pp}_{'udp' if udp else 'std'}_{tag}"
+            out[key + "_preds"] = preds.astype(np.float32)
+            out[key + "_maxvals"] = maxvals.astype(np.float32)
+            opreds, omax, _ = M.keypoints_from_heatmaps(maps, c, s, post_process=pp, use_udp=udp)
+            ok_max = np.array_equal(omax, maxvals.astype(np.float32), equal_nan=True)
+            dev = np.nanmax(np.abs(opreds - preds))
+            print(key, "oracle maxvals equal:", ok_max, "preds max |diff|:", float(dev), "dtype", preds.dtype)
+    np.savez_compressed(os.path.join(OUT, "decode_modes.npz"), **out)
+    print("written", os.path.getsize(os.path.join(OUT, "decode_modes.npz")), "bytes")
+
+
+if __name__ == "__main__":
+    main()

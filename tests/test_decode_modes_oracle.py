@@ -1,0 +1,45 @@
+"""CPU: oracle/decode_modes_oracle.py against the outputs of the UNMODIFIED reference
+keypoints_from_heatmaps committed in tests/golden/decode_modes.npz (oracle/make_golden_modes.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import decode_modes_oracle as M, vitpose_oracle as O
+
+COMBOS = [(None, False), ("default", False), ("unbiased", False), ("megvii", False), ("default", True), ("unbiased", True)]
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "decode_modes.npz"))
+    N, K, seed = (int(v) for v in g["meta"])
+    return g, O.make_decode_maps(N, K, seed)
+
+
+@pytest.mark.parametrize("pp,udp", COMBOS)
+@pytest.mark.parametrize("tag", ["f32", "i64"])
+def test_modes_match_reference(golden, pp, udp, tag):
+    g, maps = golden
+    c, s = (g["center32"], g["scale32"]) if tag == "f32" else (g["center64"], g["scale64"])
+    preds, maxvals, _ = M.keypoints_from_heatmaps(maps, c, s, post_process=pp, use_udp=udp)
+    key = f"{pp}_{'udp' if udp else 'std'}_{tag}"
+    assert np.array_equal(maxvals, g[key + "_maxvals"], equal_nan=True)
+    ref = g[key + "_preds"]
+    if pp in (None, "default", "megvii") and not udp:
+        assert np.array_equal(preds, ref, equal_nan=True)          # integer / quarter-pixel arithmetic: bit-exact
+    else:
+        assert np.array_equal(np.isnan(preds), np.isnan(ref))
+        assert np.nanmax(np.abs(preds - ref)) < 1e-3                # Taylor modes: float32 inverse
+
+
+def test_zero_padded_blur_properties():
+    taps = O.gaussian_taps(11)
+    h = np.zeros((64, 48), np.float32); h[30, 20] = 1.0
+    g = M.blur_zero_padded(h, taps)
+    assert np.array_equal(g[25:36, 15:26], np.outer(taps, taps).astype(np.float32))   # impulse response = the separable kernel
+    corner = np.zeros((64, 48), np.float32); corner[0, 0] = 1.0
+    gc = M.blur_zero_padded(corner, taps)
+    assert gc[0, 0] == np.float32(taps[5] * taps[5]) and gc[6:, :].max() == 0            # zero border: nothing reflects back
+    m = M.gaussian_modulate(h, taps)
+    assert m.max() == np.float32(1.0)                                                   # maximum preserved (:456)

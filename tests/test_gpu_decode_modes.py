@@ -1,0 +1,80 @@
+"""-m gpu: every GaussianHeatmap branch of keypoints_from_heatmaps on the GPU against the
+unmodified reference's outputs (tests/golden/decode_modes.npz) and against the oracle on more maps."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode_modes_oracle as M, vitpose_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+COMBOS = [(None, False), ("default", False), ("unbiased", False), ("megvii", False), ("default", True), ("unbiased", True)]
+
+
+def _check(preds, maxvals, ref_preds, ref_maxvals, exact):
+    assert preds.dtype == np.float32 and maxvals.dtype == np.float32 and maxvals.shape == ref_maxvals.shape
+    assert np.array_equal(maxvals, ref_maxvals, equal_nan=True)                       # scores: bit-exact in every mode
+    assert np.array_equal(np.isnan(preds), np.isnan(ref_preds))
+    if exact:
+        assert np.array_equal(preds, ref_preds, equal_nan=True)                       # argmax / quarter-pixel modes: bit-exact
+    else:
+        # Taylor modes: logf vs np.log ulps through a 2x2 solve; image pixels (scales up to ~8 px per heatmap cell)
+        assert np.nanmax(np.abs(preds - ref_preds)) < 2e-2
+
+
+@pytest.mark.parametrize("pp,udp", COMBOS)
+@pytest.mark.parametrize("tag", ["f32", "i64"])
+def test_modes_vs_reference_fixture(golden_dir, pp, udp, tag):
+    from easy_vitpose_b200 import keypoints_from_heatmaps
+    g = np.load(os.path.join(golden_dir, "decode_modes.npz"))
+    N, K, seed = (int(v) for v in g["meta"])
+    maps = O.make_decode_maps(N, K, seed)
+    c, s = (g["center32"], g["scale32"]) if tag == "f32" else (g["center64"], g["scale64"])
+    before = maps.copy()
+    preds, maxvals = keypoints_from_heatmaps(maps, c, s, post_process=pp, use_udp=udp)
+    assert np.array_equal(maps, before, equal_nan=True)                               # the caller's heatmaps are not modified
+    key = f"{pp}_{'udp' if udp else 'std'}_{tag}"
+    _check(preds, maxvals, g[key + "_preds"], g[key + "_maxvals"], exact=pp in (None, "default", "megvii") and not udp)
+
+
+@pytest.mark.parametrize("pp,udp", COMBOS)
+def test_modes_vs_oracle_on_more_maps(pp, udp):
+    from easy_vitpose_b200 import keypoints_from_heatmaps
+    N, K = 5, 25
+    maps = O.make_decode_maps(N, K, 977)
+    rs = np.random.RandomState(3)
+    c = rs.uniform(10, 800, (N, 2)).astype(np.float32); s = rs.uniform(40, 500, (N, 2)).astype(np.float32)
+    preds, maxvals, idx = keypoints_from_heatmaps(torch.from_numpy(maps).cuda(), c, s, post_process=pp, use_udp=udp, return_idx=True)
+    op, om, oi = M.keypoints_from_heatmaps(maps, c, s, post_process=pp, use_udp=udp)
+    assert np.array_equal(idx, oi)                                                    # integer argmax (megvii: of the blurred map)
+    _check(preds, maxvals, op, om, exact=pp in (None, "default", "megvii") and not udp)
+
+
+def test_config_normalisation_and_errors():
+    from easy_vitpose_b200 import decode_topdown, keypoints_from_heatmaps
+    maps = O.make_decode_maps(2, 17, 5)
+    c = np.array([[96, 128], [100, 100]], np.int64); s = np.array([[192, 256], [200, 201]], np.int64)
+    a = keypoints_from_heatmaps(maps, c, s, unbiased=True, post_process="default", use_udp=True)      # VitInference's call
+    b = keypoints_from_heatmaps(maps, c, s, post_process="unbiased", use_udp=True)
+    assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(a, b))
+    d = keypoints_from_heatmaps(maps, c, s, unbiased=True, post_process=True)                           # deprecated spellings
+    e = keypoints_from_heatmaps(maps, c, s, post_process="unbiased")
+    assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(d, e))
+    with pytest.raises(AssertionError):
+        keypoints_from_heatmaps(maps, c, s, post_process="megvii", use_udp=True)
+    with pytest.raises(NotImplementedError):
+        keypoints_from_heatmaps(maps, c, s, use_udp=True, target_type="CombinedTarget")
+    with pytest.raises(NotImplementedError):
+        keypoints_from_heatmaps(maps, c, s, post_process="unbiased", kernel=17)
+    # TopdownHeatmapBaseHead.decode with the reference's test_cfg (configs/ViTPose_common.py:123-129)
+    metas = [{"center": [96.5, 128.0], "scale": [192.0, 256.0], "image_file": "a.jpg", "bbox_score": 0.9, "bbox_id": 7},
+             {"center": [50.0, 60.0], "scale": [120.0, 160.0], "image_file": "b.jpg", "bbox_id": 8}]
+    cfg = dict(flip_test=True, post_process="default", shift_heatmap=False, target_type="GaussianHeatmap", modulate_kernel=11, use_udp=True)
+    res = decode_topdown(metas, maps, cfg)
+    c32 = np.array([[96.5, 128.0], [50.0, 60.0]], np.float32); s32 = np.array([[192.0, 256.0], [120.0, 160.0]], np.float32)
+    op, om, _ = M.keypoints_from_heatmaps(maps, c32, s32, post_process="default", use_udp=True)
+    assert np.array_equal(res["preds"][..., 2:3], om, equal_nan=True) and np.nanmax(np.abs(res["preds"][..., :2] - op)) < 2e-2
+    assert res["image_paths"] == ["a.jpg", "b.jpg"] and res["bbox_ids"] == [7, 8]
+    assert np.allclose(res["boxes"], [[96.5, 128, 192, 256, 192 * 200 * 256 * 200, 0.9], [50, 60, 120, 160, 120 * 200 * 160 * 200, 1.0]])
