@@ -736,6 +736,25 @@ extern "C" int vpb_decode(const float* d_heatmaps, int32_t n, int32_t k, const i
                           int32_t wrap_batch, void* stream) {
   return decode_launch(d_heatmaps, n, k, d_org_wh, nullptr, d_kpts, d_idx, wrap_batch, stream);
 }
+// keypoint_head(features): TopdownHeatmapSimpleHead.forward (head/topdown_heatmap_simple_head.py:188-193) on backbone features
+extern "C" int vpb_head(vpb_engine* e, const float* d_features, int32_t batch, float* d_heatmaps, void* stream) {
+  VPB_TRY(check_ready(e, batch));
+  if (!d_features || !d_heatmaps) return fail(VPB_ERR_ARG, "vpb_head: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long tot = static_cast<long long>(batch) * e->D * 192;
+  nchw_to_tokens<<<cdiv(tot, 256), 256, 0, st>>>(d_features, e->xn, batch, e->D);
+  CU_TRY(cudaGetLastError());
+  return head(e, batch, d_heatmaps, st);
+}
+extern "C" int vpb_flip_back(const float* d_in, int32_t n, int32_t k, const int32_t* d_perm, int32_t shift, float* d_out, void* stream) {
+  if (!d_in || !d_out || !d_perm || d_in == d_out) return fail(VPB_ERR_ARG, "vpb_flip_back: null or aliased pointers");
+  if (n < 0 || k < 1) return fail(VPB_ERR_ARG, "vpb_flip_back: n=%d k=%d", n, k);
+  if (n == 0) return VPB_OK;
+  const long long tot = static_cast<long long>(n) * k * 3072;
+  flip_back_heatmaps<<<cdiv(tot, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, d_out, d_perm, n, k, shift);
+  CU_TRY(cudaGetLastError());
+  return VPB_OK;
+}
 extern "C" int vpb_decode_modes(const float* d_heatmaps, int32_t n, int32_t k, int32_t mode, const float* d_cs32, const double* d_cs64,
                                 float* d_kpts, int32_t* d_idx, void* stream) {
   if (!d_heatmaps || !d_kpts || (d_cs32 == nullptr) == (d_cs64 == nullptr))

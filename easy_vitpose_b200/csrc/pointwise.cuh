@@ -170,4 +170,30 @@ __global__ void tokens_to_nchw(const __nv_bfloat16* __restrict__ tok, float* __r
   out[i] = __bfloat162float(tok[(static_cast<size_t>(b) * 192 + t) * D + d]);
 }
 
+// f32 NCHW [B, D, 16, 12] -> token-major bf16 [B*192, D]: the way back, for callers that hand backbone features to the head
+// (TopdownHeatmapSimpleHead.forward / inference_model, head/topdown_heatmap_simple_head.py:188-218).  Features produced by
+// tokens_to_nchw are bf16 values, so the round trip is exact.
+__global__ void nchw_to_tokens(const float* __restrict__ in, __nv_bfloat16* __restrict__ tok, int batch, int D) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;      // output index: coalesced bf16 writes
+  if (i >= static_cast<long long>(batch) * D * 192) return;
+  const int d = static_cast<int>(i % D);
+  const int t = static_cast<int>((i / D) % 192);
+  const int b = static_cast<int>(i / (192LL * D));
+  tok[i] = __float2bfloat16_rn(__ldg(in + (static_cast<size_t>(b) * D + d) * 192 + t));
+}
+
+// flip_back (vit_utils/post_processing/post_transforms.py:110-147, GaussianHeatmap) + the optional one-pixel shift of
+// inference_model (head/topdown_heatmap_simple_head.py:210-212):  out[n,k,y,x] = in[n, perm[k], y, W-1-x'] with x' = x, or
+// x' = max(x - 1, 0) when shift is set (numpy's overlapping `a[..., 1:] = a[..., :-1]` copies first).  perm is the
+// keypoint permutation the left/right pairs induce.  Pure data movement: bit-exact.
+__global__ void flip_back_heatmaps(const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ perm, int n, int k,
+                                   int shift) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(n) * k * 3072) return;
+  const int x = static_cast<int>(i % 48), y = static_cast<int>((i / 48) % 64);
+  const int kk = static_cast<int>((i / 3072) % k), nn = static_cast<int>(i / (3072LL * k));
+  const int xs = shift ? max(x - 1, 0) : x;
+  out[i] = __ldg(in + ((static_cast<size_t>(nn) * k + perm[kk]) * 64 + y) * 48 + (47 - xs));
+}
+
 }  // namespace vpb

@@ -46,6 +46,41 @@ def _expected_shapes(D: int, depth: int, K: int) -> "OrderedDict[str, tuple]":
     return s
 
 
+class _Backbone:
+    """`model.backbone` of the reference ViTPose (vit_models/model.py:14): callable, [B,3,256,192] -> [B,D,16,12]."""
+
+    def __init__(self, owner):
+        self._owner = owner
+        self.num_heads = owner.num_heads if hasattr(owner, "num_heads") else None
+
+    def __call__(self, x):
+        return self._owner.forward_features(x)
+
+    forward = __call__
+
+
+class _Head:
+    """`model.keypoint_head` (vit_models/model.py:15, head/topdown_heatmap_simple_head.py): forward and inference_model."""
+
+    def __init__(self, owner):
+        self._owner = owner
+        self.target_type = "GaussianHeatmap"
+        self.test_cfg = {}
+
+    def __call__(self, features):
+        return self._owner.head_forward(features)
+
+    forward = __call__
+
+    def inference_model(self, x, flip_pairs=None):
+        """head/topdown_heatmap_simple_head.py:195-218: numpy heatmaps, flipped back (and shifted by one pixel when
+        test_cfg['shift_heatmap']) if flip_pairs is given."""
+        out = self._owner.head_forward(x)
+        if flip_pairs is not None:
+            out = self._owner.flip_back(out, flip_pairs, bool(self.test_cfg.get("shift_heatmap", False)))
+        return out.cpu().numpy()
+
+
 class ViTPose:
     """Drop-in for the reference `ViTPose(cfg)` on the inference path.
 
@@ -76,6 +111,8 @@ class ViTPose:
         self._state: "OrderedDict[str, torch.Tensor] | None" = None
         self._device = None
         self._side = None
+        self.backbone = _Backbone(self)              # model.backbone(x) / model.keypoint_head(f), as on the reference module
+        self.keypoint_head = _Head(self)
         if device is not None:
             self.to(device)
 
@@ -201,6 +238,48 @@ class ViTPose:
         return out
 
     @torch.no_grad()
+    def head_forward(self, features: torch.Tensor) -> torch.Tensor:
+        """Backbone features [B,D,16,12] -> heatmaps [B,K,64,48]: TopdownHeatmapSimpleHead.forward
+        (head/topdown_heatmap_simple_head.py:188-193).  The engine's head consumes bf16 features; those returned by
+        forward_features are bf16 values already, so backbone -> head in two calls equals forward()."""
+        self._ensure()
+        if not isinstance(features, torch.Tensor) or features.dim() != 4 or tuple(features.shape[1:]) != (self.embed_dim, 16, 12):
+            raise ValueError(f"expected features [B,{self.embed_dim},16,12]")
+        if features.shape[0] < 1 or features.shape[0] > self.max_batch:
+            raise ValueError(f"batch {features.shape[0]} outside 1..max_batch={self.max_batch}")
+        f = features.to(device=torch.device("cuda", self._device), dtype=torch.float32).contiguous()
+        out = torch.empty((f.shape[0], self.num_keypoints, HM_H, HM_W), dtype=torch.float32, device=f.device)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().vpb_head(self._handle, C.c_void_p(f.data_ptr()), f.shape[0], C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    @torch.no_grad()
+    def flip_back(self, heatmaps: torch.Tensor, flip_pairs, shift_heatmap: bool = False) -> torch.Tensor:
+        """flip_back (post_processing/post_transforms.py:110-147) + the optional shift of inference_model (:210-212) on the GPU."""
+        hm = heatmaps.to(device=torch.device("cuda", self._device if self._device is not None else torch.cuda.current_device()),
+                         dtype=torch.float32).contiguous()
+        if hm.dim() != 4 or tuple(hm.shape[2:]) != (HM_H, HM_W):
+            raise ValueError(f"expected [N,K,64,48], got {tuple(hm.shape)}")
+        K = hm.shape[1]
+        perm = list(range(K))
+        for left, right in flip_pairs:                       # sequential, like the reference's loop over (left, right)
+            perm[left], perm[right] = right, left
+        pt = torch.tensor(perm, dtype=torch.int32, device=hm.device)
+        out = torch.empty_like(hm)
+        with torch.cuda.device(hm.device):
+            _lib.check(_lib.lib().vpb_flip_back(C.c_void_p(hm.data_ptr()), hm.shape[0], K, C.c_void_p(pt.data_ptr()), 1 if shift_heatmap else 0,
+                                                C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream(hm.device).cuda_stream)))
+        return out
+
+    @torch.no_grad()
+    def forward_flip_test(self, x: torch.Tensor, flip_pairs, shift_heatmap: bool = False) -> torch.Tensor:
+        """mmpose's flip test (the `flip_test=True` of the reference configs, configs/ViTPose_common.py:124): heatmaps of the
+        image and of its mirror image (flipped back, keypoint pairs swapped) averaged -- the published-AP protocol."""
+        x = self._check_input(x)
+        hm = self.forward(x)
+        hm_f = self.flip_back(self.forward(torch.flip(x, dims=[3])), flip_pairs, shift_heatmap)
+        return (hm + hm_f) * 0.5
+
     def _call_on_stream(self, tensors, call) -> None:
         """Runs `call(stream)` on the caller's current stream; on the legacy default stream (which cannot be captured into a
         CUDA graph) on a side stream ordered after / before it by two event waits, so small batches get graph replay."""
@@ -218,6 +297,7 @@ class ViTPose:
             else:
                 _lib.check(call(C.c_void_p(cur.cuda_stream)))
 
+    @torch.no_grad()
     def infer_crops(self, x: torch.Tensor, org_wh: torch.Tensor, return_heatmaps: bool = False):
         """Batched crops -> keypoints [B,K,3] (y, x, score) in crop pixels + flat argmax [B,K].
         org_wh int32 [B,2] = each crop's (width, height) before the resize to 192x256."""

@@ -68,6 +68,14 @@ int vpb_forward_features(vpb_engine* e, const float* d_crops, int32_t batch, flo
 int vpb_decode(const float* d_heatmaps, int32_t n, int32_t k, const int32_t* d_org_wh, float* d_kpts, int32_t* d_idx,
                int32_t wrap_batch, void* stream);
 
+/* Replaces TopdownHeatmapSimpleHead.forward (vit_models/head/topdown_heatmap_simple_head.py:188-193) on its own:
+ * d_features f32 [batch,D,16,12] (what vpb_forward_features returns) -> d_heatmaps f32 [batch,K,64,48]. */
+int vpb_head(vpb_engine* e, const float* d_features, int32_t batch, float* d_heatmaps, void* stream);
+/* Replaces flip_back (vit_utils/post_processing/post_transforms.py:110-147, GaussianHeatmap) plus the optional one-pixel
+ * shift of TopdownHeatmapSimpleHead.inference_model (:210-212): d_in / d_out f32 [n,k,64,48] (distinct buffers), d_perm i32 [k]
+ * = the keypoint permutation the flip pairs induce (perm[left] = right, perm[right] = left, identity elsewhere). */
+int vpb_flip_back(const float* d_in, int32_t n, int32_t k, const int32_t* d_perm, int32_t shift, float* d_out, void* stream);
+
 /* The other modes of keypoints_from_heatmaps (vit_utils/top_down_eval.py:493-641), with the
  * general transform_preds (post_processing/post_transforms.py:150-194).  mode: 0 post_process=None (:598), 1 'default' (+-0.25 px,
  * :617-631), 2 'unbiased' (Gaussian modulation + log + _taylor, :600-607), 3 'megvii' (:573-574,:629-639) -- all use_udp=False --

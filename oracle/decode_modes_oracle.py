@@ -149,3 +149,19 @@ def _dark_udp_general(heatmaps, center, scale, kernel):
         xy = np.stack([kp[n, :, 1] * np.float32(0.5), kp[n, :, 0] * np.float32(0.5)], 1).astype(np.float32)
         preds[n] = transform(xy, center[n], scale[n], W, H, True)
     return preds, kp[:, :, 2:3].copy(), idx
+
+
+COCO_FLIP_PAIRS = [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]]     # datasets/COCO.py:114
+
+
+def flip_back(heatmaps: np.ndarray, flip_pairs, shift_heatmap: bool = False) -> np.ndarray:
+    """flip_back for GaussianHeatmap (post_processing/post_transforms.py:110-147) followed by the optional one-pixel shift of
+    TopdownHeatmapSimpleHead.inference_model (head/topdown_heatmap_simple_head.py:210-212)."""
+    out = heatmaps.copy()
+    for left, right in flip_pairs:
+        out[:, left] = heatmaps[:, right]
+        out[:, right] = heatmaps[:, left]
+    out = np.ascontiguousarray(out[..., ::-1])
+    if shift_heatmap:
+        out[:, :, :, 1:] = out[:, :, :, :-1].copy()
+    return out

@@ -52,6 +52,17 @@ def main() -> None:
             ok_max = np.array_equal(omax, maxvals.astype(np.float32), equal_nan=True)
             dev = np.nanmax(np.abs(opreds - preds))
             print(key, "oracle maxvals equal:", ok_max, "preds max |diff|:", float(dev), "dtype", preds.dtype)
+    # flip_back (post_transforms.py:110-147) + inference_model's shift (:210-212): data movement, pinned by digest
+    import hashlib
+    ptr = importlib.import_module("vit_utils.post_processing.post_transforms")
+    for shift in (False, True):
+        ref = ptr.flip_back(maps.copy(), M.COCO_FLIP_PAIRS, target_type="GaussianHeatmap")
+        if shift:
+            ref[:, :, :, 1:] = ref[:, :, :, :-1]
+        mine = M.flip_back(maps, M.COCO_FLIP_PAIRS, shift)
+        assert np.array_equal(mine, ref, equal_nan=True)
+        out[f"flip_digest_shift{int(shift)}"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(ref).tobytes()).digest(), np.uint8)
+    print("flip_back (+shift): oracle equals the reference")
     np.savez_compressed(os.path.join(OUT, "decode_modes.npz"), **out)
     print("written", os.path.getsize(os.path.join(OUT, "decode_modes.npz")), "bytes")
 

@@ -43,3 +43,13 @@ def test_zero_padded_blur_properties():
     assert gc[0, 0] == np.float32(taps[5] * taps[5]) and gc[6:, :].max() == 0            # zero border: nothing reflects back
     m = M.gaussian_modulate(h, taps)
     assert m.max() == np.float32(1.0)                                                   # maximum preserved (:456)
+
+
+def test_flip_back_matches_reference_digest(golden):
+    import hashlib
+    g, maps = golden
+    for shift in (False, True):
+        mine = M.flip_back(maps, M.COCO_FLIP_PAIRS, shift)
+        assert np.array_equal(np.frombuffer(hashlib.sha256(mine.tobytes()).digest(), np.uint8), g[f"flip_digest_shift{int(shift)}"])
+    twice = M.flip_back(M.flip_back(maps, M.COCO_FLIP_PAIRS), M.COCO_FLIP_PAIRS)
+    assert np.array_equal(twice, maps, equal_nan=True)                                 # an involution

@@ -78,3 +78,29 @@ def test_config_normalisation_and_errors():
     assert np.array_equal(res["preds"][..., 2:3], om, equal_nan=True) and np.nanmax(np.abs(res["preds"][..., :2] - op)) < 2e-2
     assert res["image_paths"] == ["a.jpg", "b.jpg"] and res["bbox_ids"] == [7, 8]
     assert np.allclose(res["boxes"], [[96.5, 128, 192, 256, 192 * 200 * 256 * 200, 0.9], [50, 60, 120, 160, 120 * 200 * 160 * 200, 1.0]])
+
+
+def test_head_alone_and_flip_test(golden_dir):
+    """model.backbone / model.keypoint_head as on the reference module (vit_models/model.py:14-24), flip_back on the GPU
+    (bit-exact data movement) and the flip-test average of the reference configs (flip_test=True)."""
+    from easy_vitpose_b200 import ViTPose, model_cfg
+    g = np.load(os.path.join(golden_dir, "fwd_s_coco.npz"))
+    D, depth, heads, K, B, wseed, xseed = (int(v) for v in g["meta"])
+    m = ViTPose(model_cfg("s", K), max_batch=4)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in O.make_state_dict(D, depth, K, wseed, peaky=float(g["peaky"]), bumps=True).items()})
+    m.to("cuda:0")
+    x = torch.from_numpy(O.make_crops(3, 31)).cuda()
+    hm = m(x)
+    feats = m.backbone(x)
+    assert tuple(feats.shape) == (3, D, 16, 12)
+    assert torch.equal(m.keypoint_head(feats), hm)                                     # backbone -> head == forward, bit for bit
+    assert np.array_equal(m.keypoint_head.inference_model(feats), hm.cpu().numpy())
+    hn = hm.cpu().numpy()
+    for shift in (False, True):
+        m.keypoint_head.test_cfg = {"shift_heatmap": shift}
+        assert np.array_equal(m.keypoint_head.inference_model(feats, M.COCO_FLIP_PAIRS), M.flip_back(hn, M.COCO_FLIP_PAIRS, shift))
+    ft = m.forward_flip_test(x, M.COCO_FLIP_PAIRS)
+    hf = m(torch.flip(x, dims=[3])).cpu().numpy()
+    assert np.array_equal(ft.cpu().numpy(), (hn + M.flip_back(hf, M.COCO_FLIP_PAIRS)) * np.float32(0.5))
+    with pytest.raises(ValueError):
+        m.keypoint_head(feats[:, :-1])
