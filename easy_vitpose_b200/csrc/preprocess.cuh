@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(PP_W) crop_resize_normalise(const PreprocParam
 // The same pre-processing fused with the patch-embedding im2col (pointwise.cuh: patch_im2col): frame + boxes -> bf16 patch
 // rows [n*192, 768] directly, so the f32 crops (589 824 B each) are never written or re-read.  Values are bf16(table[v]),
 // i.e. exactly what patch_im2col produces from crop_resize_normalise's output.  One CTA = one crop x one patch row (16 image
-// rows incl. the conv's 2-pixel zero border); thread (ky, xchunk) = 8 consecutive kx for the 3 channels -> three 16 B stores.
+// rows incl. the conv's 2-pixel zero border): the 16 x 192 x 3 pixels are gathered with lanes along the image row into a
+// shared bf16 tile, which is then written out as 16-byte chunks of the im2col rows.
 // Like patch_im2col, the launch also seeds the fp32 token stream with pos_embed + conv bias (vit.py:382).
 struct FramePatchParams {
   PreprocParams pp;             // crops / status unused
@@ -135,9 +136,11 @@ struct FramePatchParams {
 };
 
 __global__ void __launch_bounds__(384) frame_to_patch_rows(const FramePatchParams q) {
+  constexpr int FP_PITCH = 208;                               // 2 + 192 + 14 bf16 per tile row: 16-byte aligned rows
   __shared__ uint16_t s_lut[3][256];
   __shared__ PpAxis s_ay[16];
   __shared__ PpAxis s_ax[PP_W];
+  __shared__ __align__(16) uint16_t s_tile[3 * 16 * FP_PITCH];
   const PreprocParams& p = q.pp;
   const int crop = blockIdx.x, py = blockIdx.y, tid = threadIdx.x;
   pdl_launch_dependents();
@@ -176,22 +179,24 @@ __global__ void __launch_bounds__(384) frame_to_patch_rows(const FramePatchParam
     if (dy >= 0) s_ay[tid - PP_W] = pp_axis(dy, pp_scale(PP_H, ch), ch, false);
   }
   __syncthreads();
-  const int ky = tid / 24, xc = tid % 24;
-  const int dy = 16 * py - 2 + ky, dx0 = xc * 8 - 2;
-  uint32_t o[3][4] = {};
-  if (dy >= 0) {
-    const PpAxis ay = s_ay[ky];
-    const int cy0 = ay.i0 - top, cy1 = ay.i1 - top;
-    const bool vy0 = cy0 >= 0 && cy0 < h, vy1 = cy1 >= 0 && cy1 < h;
-    const uint8_t* r0 = p.frame + static_cast<size_t>(vy0 ? y0 + cy0 : 0) * p.pitch;
-    const uint8_t* r1 = p.frame + static_cast<size_t>(vy1 ? y0 + cy1 : 0) * p.pitch;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int dx = dx0 + j;
-      if (dx < 0 || dx >= PP_W) continue;                    // conv zero padding: stays 0
+  // Phase 1: one (row, column) pixel per thread-iteration with consecutive lanes on consecutive output columns, so that a
+  // warp's byte gathers fall into neighbouring sectors; bf16 values go to a shared tile laid out [channel][ky][2 + dx]
+  // (column 0,1 and 194..207 = the conv's zero padding / alignment).
+  for (int i = tid; i < 3 * 16 * 8; i += 384) {              // zero the padding columns once: 16 bf16 per (c, ky) row
+    const int row = i >> 3, e = i & 7;
+    s_tile[row * FP_PITCH + (e < 2 ? e : 192 + e)] = 0;
+  }
+  for (int i = tid; i < 16 * PP_W; i += 384) {
+    const int ky = i / PP_W, dx = i % PP_W;
+    const int dy = 16 * py - 2 + ky;
+    uint16_t v3[3] = {0, 0, 0};
+    if (dy >= 0) {
+      const PpAxis ay = s_ay[ky];
       const PpAxis ax = s_ax[dx];
-      const int cx0 = ax.i0 - left, cx1 = ax.i1 - left;
-      const bool vx0 = cx0 >= 0 && cx0 < w, vx1 = cx1 >= 0 && cx1 < w;
+      const int cy0 = ay.i0 - top, cy1 = ay.i1 - top, cx0 = ax.i0 - left, cx1 = ax.i1 - left;
+      const bool vy0 = cy0 >= 0 && cy0 < h, vy1 = cy1 >= 0 && cy1 < h, vx0 = cx0 >= 0 && cx0 < w, vx1 = cx1 >= 0 && cx1 < w;
+      const uint8_t* r0 = p.frame + static_cast<size_t>(vy0 ? y0 + cy0 : 0) * p.pitch;
+      const uint8_t* r1 = p.frame + static_cast<size_t>(vy1 ? y0 + cy1 : 0) * p.pitch;
       const int f0 = (vx0 ? x0 + cx0 : 0) * 3, f1 = (vx1 ? x0 + cx1 : 0) * 3;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -199,15 +204,19 @@ __global__ void __launch_bounds__(384) frame_to_patch_rows(const FramePatchParam
         const int p10 = (vy1 && vx0) ? r1[f0 + c] : 0, p11 = (vy1 && vx1) ? r1[f1 + c] : 0;
         const int s0 = p00 * ax.a0 + p01 * ax.a1, s1 = p10 * ax.a0 + p11 * ax.a1;
         int v = (((ay.a0 * (s0 >> 4)) >> 16) + ((ay.a1 * (s1 >> 4)) >> 16) + 2) >> 2;
-        v = min(max(v, 0), 255);
-        o[c][j >> 1] |= static_cast<uint32_t>(s_lut[c][v]) << ((j & 1) * 16);
+        v3[c] = s_lut[c][min(max(v, 0), 255)];
       }
     }
-  }
-  const int px = xc >> 1, kx0 = (xc & 1) * 8;
-  __nv_bfloat16* dst = q.rows + ((static_cast<size_t>(crop) * 16 + py) * 12 + px) * 768 + ky * 16 + kx0;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) *reinterpret_cast<uint4*>(dst + c * 256) = make_uint4(o[c][0], o[c][1], o[c][2], o[c][3]);
+    for (int c = 0; c < 3; ++c) s_tile[(c * 16 + ky) * FP_PITCH + 2 + dx] = v3[c];
+  }
+  __syncthreads();
+  // Phase 2: the im2col rows of this patch row, 16 bytes (8 kx) per store: element (px, c, ky, kx) = tile[c][ky][16 px + kx]
+  for (int i = tid; i < 12 * 3 * 16 * 2; i += 384) {
+    const int hf = i & 1, ky = (i >> 1) & 15, c = (i >> 5) % 3, px = i / 96;
+    const uint4 v = *reinterpret_cast<const uint4*>(&s_tile[(c * 16 + ky) * FP_PITCH + 16 * px + 8 * hf]);
+    *reinterpret_cast<uint4*>(q.rows + ((static_cast<size_t>(crop) * 16 + py) * 12 + px) * 768 + c * 256 + ky * 16 + 8 * hf) = v;
+  }
 }
 
 }  // namespace vpb
