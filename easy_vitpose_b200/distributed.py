@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_counts", "shard_range", "gather_keypoints", "infer_sharded"]
+__all__ = ["shard_counts", "shard_range", "gather_keypoints", "infer_sharded", "infer_frame_sharded"]
 
 
 def shard_counts(n: int, world: int) -> list[int]:
@@ -65,4 +65,26 @@ def infer_sharded(model, crops: torch.Tensor, org_wh: torch.Tensor, group=None):
         dev = torch.device("cuda", torch.cuda.current_device())
         kp = torch.empty((0, model.num_keypoints, 3), dtype=torch.float32, device=dev)
         idx = torch.empty((0, model.num_keypoints), dtype=torch.int32, device=dev)
+    return gather_keypoints(kp, n, group), gather_keypoints(idx.unsqueeze(-1), n, group).squeeze(-1)
+
+
+@torch.no_grad()
+def infer_frame_sharded(model, frame: torch.Tensor, bboxes: torch.Tensor, group=None):
+    """Frame-level form (SURVEY.md section 8 rows f1/f2 + e): every rank holds the SAME uint8 frame [H,W,3] and the SAME boxes
+    [n,4]; the people of the frame are sharded by index, each rank runs its slice through `model.infer_frame` (crop
+    pre-processing, model, decode, offsets back to frame pixels on its GPU) and all ranks return the full frame-space
+    keypoints [n,K,3] and argmax [n,K] in box order.  The only exchange is the keypoint gather."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = bboxes.shape[0]
+    lo, hi = shard_range(n, rank, world)
+    outs_kp, outs_idx = [], []
+    for s in range(lo, hi, model.max_batch):
+        kp, idx = model.infer_frame(frame, bboxes[s:min(hi, s + model.max_batch)])
+        outs_kp.append(kp)
+        outs_idx.append(idx)
+    if outs_kp:
+        kp, idx = torch.cat(outs_kp, 0), torch.cat(outs_idx, 0)
+    else:   # more ranks than people
+        kp = torch.empty((0, model.num_keypoints, 3), dtype=torch.float32, device=frame.device)
+        idx = torch.empty((0, model.num_keypoints), dtype=torch.int32, device=frame.device)
     return gather_keypoints(kp, n, group), gather_keypoints(idx.unsqueeze(-1), n, group).squeeze(-1)
