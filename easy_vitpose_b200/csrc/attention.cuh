@@ -1,16 +1,18 @@
 // Fused multi-head attention for one ViTPose crop: T = 192 tokens, head_dim 32 / 64 / 80 (ViT-S / B,L / H), on chip.
 //
 // Work item = (crop b, head h); one CTA per SM walks items blockIdx.x, +gridDim.x, ...  An item is two 128-row M tiles
-// (tokens 0..127, then 128..191), i.e. two "steps"; steps run through a software pipeline with three kinds of warps:
-//   warp 12, one thread  TMA: Q,K,V [192 x hd] bf16 boxes straight out of the qkv activation [M, 3D] -> swizzled smem,
-//                        double buffered per item.  UMMA issue: S = Q K^T (M=128 x N=192, fp32 -> TMEM buffer step%2),
-//                        always one step AHEAD of the softmax; O = P V as soon as P is published.
-//   warps 0..7           softmax, TWO threads per row (96 keys each), S read from TMEM exactly ONCE into registers (TMEM
-//                        read bandwidth, ~64 B/clk/SM, is what bounds this stage): max (exchanged through smem), exp2, sum;
-//                        P is written back IN PLACE as packed bf16 (tcgen05.st, columns [0,96) of the S buffer) -- P never
-//                        touches shared memory.  These warps never wait for the tensor pipe in steady state.
-//   warps 8..11          epilogue: O (TMEM columns [96, 96+hd) of the same buffer, dead S columns) / rowsum -> bf16 ->
-//                        smem staging -> coalesced 16-byte stores to attn_out[b*192 + t, h*hd + d]; frees the buffer.
+// (tokens 0..127, then 128..191), i.e. two "steps"; steps run through a software pipeline with four kinds of warps:
+//   warp 12, one thread  TMA of Q,K [192 x hd] bf16 boxes straight out of the qkv activation [M, 3D] -> swizzled smem (double
+//                        buffered per item) and UMMA issue of S = Q K^T (M=128 x N=192, fp32 -> TMEM buffer step%2), ahead of the
+//                        softmax as far as the two S buffers allow.
+//   warp 13, one thread  TMA of V and UMMA issue of O = P V, in three 64-key slices as the softmax publishes P.  (Two issuing
+//                        threads: a tcgen05.mma costs its issuing thread ~100 cycles and a step has 16..29 of them.)
+//   warps 0..7           softmax, TWO threads per row (96 keys each), S read from TMEM exactly ONCE into registers: max (exchanged
+//                        through smem), exp2 (the MUFU, 16 ex2/clk/SM, bounds this stage), sum; P is written back IN PLACE as
+//                        packed bf16 (tcgen05.st, columns [0,96) of the S buffer) -- P never touches shared memory.
+//   warps 8..11          epilogue: O (head_dim <= 64: its own TMEM columns [384 + 64*(step&1), +hd); head_dim 80: the dead S
+//                        columns [96, 96+hd) of the same buffer) / rowsum -> bf16 -> smem staging -> coalesced 16-byte stores
+//                        to attn_out[b*192 + t, h*hd + d].
 // O = P V takes A = P from TMEM and B = V as an MN-major smem operand, i.e. exactly the [token][dim] box TMA delivered.
 // Operand tiles: head_dim 64 -> one 128-byte-swizzled box per operand; 32 -> one 64-byte-swizzled box; 80 -> a
 // 128B-swizzled box of 64 dims plus a 32B-swizzled box of the last 16 (QK^T: 4+1 K steps; PV: an N=64 and an N=16 MMA).
@@ -25,10 +27,11 @@
 namespace vpb {
 
 constexpr int ATT_T = 192;
-constexpr int ATT_THREADS = 13 * 32;                          // 8 softmax warps, 4 epilogue warps, 1 control warp
+constexpr int ATT_THREADS = 14 * 32;                          // 8 softmax warps, 4 epilogue warps, 2 issue warps (QK / PV)
 constexpr int ATT_TMEM_COLS = 512;                            // two S/P/O buffers of 192 columns
 constexpr int ATT_BUF_COLS = 192;
-constexpr int ATT_O_COL = 96;                                 // O inside the S buffer, behind P
+constexpr int ATT_O_COL = 96;                                 // head_dim 80: O inside the S buffer, behind P
+constexpr int ATT_O_SEP_COL = 384;                            // head_dim <= 64: O in its own columns [384 + 64*(step&1), +hd)
 
 template <int HD>
 struct AttCfg {
@@ -40,9 +43,14 @@ struct AttCfg {
   static constexpr int TAIL_BYTES = TAIL ? ATT_T * 32 : 0;    // 6144
   static constexpr int OPER_BYTES = MAIN_BYTES + TAIL_BYTES;  // one of Q / K / V
   static constexpr int STAGE_BYTES = 3 * OPER_BYTES;          // Q, K, V of one item
+  // The kernel is bound by a latency chain, not by a pipe: softmax(t) -> PV(t) -> O drained -> QK(t+2) ->
+  // S(t+2).  Two things shorten it: PV is issued in three 64-key slices as the softmax publishes P (p_chunk barriers), so only
+  // the last four UMMAs trail the softmax; and for head_dim <= 64 O has its own TMEM columns, so the S buffer is released by
+  // PV's commit instead of by the epilogue's drain (2*192 + 2*80 columns do not fit: head_dim 80 keeps O behind P).
+  static constexpr bool O_SEP = HD <= 64;
   static constexpr int OUT_PITCH = HD * 2 + 16;               // staging row pitch (bytes): conflict-free 16-byte accesses
   static constexpr int OUT_STAGE = 4 * 32 * OUT_PITCH;        // 4 epilogue warps x 32 rows
-  static constexpr int SMEM = 2 * STAGE_BYTES + OUT_STAGE + 4096 /*row sums, partial maxima*/ + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM = 2 * STAGE_BYTES + OUT_STAGE + 6144 /*row sums, partial maxima*/ + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct AttnParams {
@@ -79,16 +87,18 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sOut = smem + 2 * Cfg::STAGE_BYTES;               // per-warp output staging (coalesced global stores)
-  float* s_sum = reinterpret_cast<float*>(sOut + Cfg::OUT_STAGE);   // [2 buffers][2 halves][128 rows]
-  float* s_max = s_sum + 512;                                 // [2 step parities][2 halves][128 rows]
+  float* s_sum = reinterpret_cast<float*>(sOut + Cfg::OUT_STAGE);   // [4 slots = step & 3][2 halves][128 rows]: the softmax may
+                                                              // run two steps ahead of the epilogue's read
+  float* s_max = s_sum + 1024;                                // [2 step parities][2 halves][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_max + 512);
   uint64_t* qk_full = bars;          // [2] Q,K of item stage landed            (TMA -> control)
   uint64_t* v_full = bars + 2;       // [2] V landed                             (TMA -> control)
   uint64_t* s_full = bars + 4;       // [2] S complete                           (MMA commit -> softmax)
   uint64_t* p_ready = bars + 6;      // [2] P + row sums published               (128 softmax threads -> control, epilogue)
   uint64_t* o_full = bars + 8;       // [2] O complete                           (MMA commit -> epilogue, control)
-  uint64_t* s_free = bars + 10;      // [2] O drained, buffer reusable           (128 epilogue threads -> control)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* s_free = bars + 10;      // [2] O drained                            (128 epilogue threads -> control)
+  uint64_t* p_chunk = bars + 12;     // [2][3] P keys 32c..32c+31 of both halves published (256 softmax threads -> control)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,6 +117,7 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
       mbar_init(&p_ready[i], 256);
       mbar_init(&o_full[i], 1);
       mbar_init(&s_free[i], 128);
+      for (int c = 0; c < 3; ++c) mbar_init(&p_chunk[i * 3 + c], 256);
     }
     fence_mbar_init();
   }
@@ -118,28 +129,25 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
   pdl_launch_dependents();
   pdl_wait();                                               // qkv from the previous GEMM is complete
 
+  // shared by the two issuing threads
+  auto stage_ptr = [&](int q, int oper) { return smem + q * Cfg::STAGE_BYTES + oper * Cfg::OPER_BYTES; };
+  auto load_oper = [&](uint8_t* dst, uint64_t* bar, int col0, int row0) {
+    tma_load_2d(dst, &tmap_main, bar, col0, row0);
+    if constexpr (Cfg::TAIL > 0) tma_load_2d(dst + Cfg::MAIN_BYTES, &tmap_tail, bar, col0 + Cfg::MAIN, row0);
+  };
+
   if (warp == 12) {
     if (lane == 0) {
-      // ------------------------------------------------------------------ TMA + MMA issue (one thread)
-      auto stage_ptr = [&](int q, int oper) { return smem + q * Cfg::STAGE_BYTES + oper * Cfg::OPER_BYTES; };
-      auto load_oper = [&](uint8_t* dst, uint64_t* bar, int col0, int row0) {
-        tma_load_2d(dst, &tmap_main, bar, col0, row0);
-        if constexpr (Cfg::TAIL > 0) tma_load_2d(dst + Cfg::MAIN_BYTES, &tmap_tail, bar, col0 + Cfg::MAIN, row0);
-      };
+      // ------------------------------------------------------------------ issue thread 1: TMA of Q,K and S = Q K^T
+      // (tcgen05.mma issue costs the issuing thread ~100 cycles per instruction: with one thread for all 16-17 UMMAs of a step
+      // the kernel was bound by that thread; Q K^T and P V now have a thread each)
       auto load_qk = [&](int i) {
         const int item = blockIdx.x + i * gridDim.x, b = item / p.heads, h = item % p.heads, q = i & 1;
         mbar_expect_tx(&qk_full[q], 2 * Cfg::OPER_BYTES);
         load_oper(stage_ptr(q, 0), &qk_full[q], h * HD, b * ATT_T);
         load_oper(stage_ptr(q, 1), &qk_full[q], p.dim + h * HD, b * ATT_T);
       };
-      auto load_v = [&](int i) {
-        const int item = blockIdx.x + i * gridDim.x, b = item / p.heads, h = item % p.heads, q = i & 1;
-        mbar_expect_tx(&v_full[q], Cfg::OPER_BYTES);
-        load_oper(stage_ptr(q, 2), &v_full[q], 2 * p.dim + h * HD, b * ATT_T);
-      };
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, ATT_T);
-      constexpr uint32_t idesc_o_main = umma_idesc_bf16(128, Cfg::MAIN, /*b_mn_major=*/true);
-      constexpr uint32_t idesc_o_tail = umma_idesc_bf16(128, 16, /*b_mn_major=*/true);
       // S(step t) = Q K^T into buffer t&1
       auto issue_qk = [&](int t) {
         const int i = t >> 1, mt = t & 1, q = i & 1;
@@ -154,45 +162,64 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
           umma_bf16(d, umma_desc_rows<32>(sQ + Cfg::MAIN_BYTES + q_row0 * 32), umma_desc_rows<32>(sK + Cfg::MAIN_BYTES), idesc_s, true);
         umma_commit(&s_full[t & 1]);
       };
-      // O(step t) = P V: P = packed bf16 in columns [0,96) of the buffer, O -> columns [96, 96+hd)
-      auto issue_pv = [&](int t) {
+      load_qk(0);
+      if (n_my > 1) load_qk(1);
+      for (int t = 0; t < T; ++t) {                          // S runs one step ahead of the softmax
+        const int i = t >> 1, mt = t & 1;
+        // the S buffer was last used by step t-2: PV(t-2) has consumed P (O elsewhere), or the epilogue has drained O from it
+        if (i >= 1) mbar_wait(Cfg::O_SEP ? &o_full[t & 1] : &s_free[t & 1], (i - 1) & 1);
+        if (mt == 0) mbar_wait(&qk_full[i & 1], (i >> 1) & 1);
+        tc_fence_after_sync();
+        issue_qk(t);
+        if (mt == 0 && i >= 1 && i + 1 < n_my) {
+          // item i-1's last Q K^T (step t-1) was issued before this one and has retired by now or soon: its Q/K stage is free
+          mbar_wait(&s_full[(t - 1) & 1], (i - 1) & 1);
+          load_qk(i + 1);
+        }
+      }
+    }
+  } else if (warp == 13) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ issue thread 2: TMA of V and O = P V
+      auto load_v = [&](int i) {
+        const int item = blockIdx.x + i * gridDim.x, b = item / p.heads, h = item % p.heads, q = i & 1;
+        mbar_expect_tx(&v_full[q], Cfg::OPER_BYTES);
+        load_oper(stage_ptr(q, 2), &v_full[q], 2 * p.dim + h * HD, b * ATT_T);
+      };
+      constexpr uint32_t idesc_o_main = umma_idesc_bf16(128, Cfg::MAIN, /*b_mn_major=*/true);
+      constexpr uint32_t idesc_o_tail = umma_idesc_bf16(128, 16, /*b_mn_major=*/true);
+      // O(step t) = P V, slice c = keys 32c..32c+31 of each half (UMMA k-steps 2c, 2c+1, 6+2c, 7+2c): P = packed bf16 in columns
+      // [0,96) of the buffer; O -> its own columns (head_dim <= 64) or columns [96, 96+hd) of the buffer
+      auto issue_pv_slice = [&](int t, int c) {
         const int q = (t >> 1) & 1;
         const uint32_t sV = smem_u32(stage_ptr(q, 2));
         const uint32_t buf = tmem_base + (t & 1) * ATT_BUF_COLS;
+        const uint32_t od = Cfg::O_SEP ? tmem_base + ATT_O_SEP_COL + (t & 1) * 64 : buf + ATT_O_COL;
 #pragma unroll
-        for (int kk = 0; kk < ATT_T / 16; ++kk) {
+        for (int j = 0; j < 4; ++j) {
           // 16 keys = 8 packed TMEM columns of P; V (MN-major): 16 tokens = two 8-row groups of the box
-          umma_bf16_ts(buf + ATT_O_COL, buf + kk * 8, umma_desc_rows<Cfg::MAIN_ROW>(sV + kk * 16 * Cfg::MAIN_ROW), idesc_o_main, kk != 0);
+          const int kk = (j >> 1) * 6 + 2 * c + (j & 1);
+          const bool acc = !(c == 0 && j == 0);
+          umma_bf16_ts(od, buf + kk * 8, umma_desc_rows<Cfg::MAIN_ROW>(sV + kk * 16 * Cfg::MAIN_ROW), idesc_o_main, acc);
           if constexpr (Cfg::TAIL > 0)
-            umma_bf16_ts(buf + ATT_O_COL + Cfg::MAIN, buf + kk * 8, umma_desc_rows<32>(sV + Cfg::MAIN_BYTES + kk * 16 * 32), idesc_o_tail,
-                         kk != 0);
+            umma_bf16_ts(od + Cfg::MAIN, buf + kk * 8, umma_desc_rows<32>(sV + Cfg::MAIN_BYTES + kk * 16 * 32), idesc_o_tail, acc);
         }
-        umma_commit(&o_full[t & 1]);
+        if (c == 2) umma_commit(&o_full[t & 1]);
       };
-
-      load_qk(0); load_v(0);
-      if (n_my > 1) { load_qk(1); load_v(1); }
-      mbar_wait(&qk_full[0], 0);
-      tc_fence_after_sync();
-      issue_qk(0);
+      load_v(0);
+      if (n_my > 1) load_v(1);
       for (int t = 0; t < T; ++t) {
         const int i = t >> 1, mt = t & 1, bf = t & 1, q = i & 1;
-        if (t + 1 < T) {
-          // keep S one step ahead of the softmax: buffer (t+1)&1 was last used by step t-1
-          const int t1 = t + 1, i1 = t1 >> 1;
-          if (i1 >= 1) mbar_wait(&s_free[t1 & 1], (i1 - 1) & 1);
-          if ((t1 & 1) == 0) mbar_wait(&qk_full[i1 & 1], (i1 >> 1) & 1);
-          tc_fence_after_sync();
-          issue_qk(t1);
-        }
-        mbar_wait(&p_ready[bf], i & 1);                      // P(t) is in TMEM
         if (mt == 0) mbar_wait(&v_full[q], (i >> 1) & 1);
-        tc_fence_after_sync();
-        issue_pv(t);
+        if (Cfg::O_SEP && i >= 1) mbar_wait(&s_free[bf], (i - 1) & 1);      // O(t-2) has left this step parity's O columns
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+          mbar_wait(&p_chunk[bf * 3 + c], i & 1);            // this slice of P(t) is in TMEM
+          tc_fence_after_sync();
+          issue_pv_slice(t, c);
+        }
         if (mt == 1 && i + 2 < n_my) {
-          // item i's last S retired long ago (its softmax has run): Q/K stage free.  V is free once this PV retires.
-          load_qk(i + 2);
-          mbar_wait(&o_full[bf], i & 1);
+          mbar_wait(&o_full[bf], i & 1);                     // item i's last P V has retired: its V stage is free
           load_v(i + 2);
         }
       }
@@ -238,19 +265,24 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
             pk[j >> 1] = pack_bf16(e0, e1);
           }
           tmem_st16(buf + 48 * hf + (c >> 1), pk);          // P = 96 packed columns [0,96): keys 96*hf + c .. + 31
+          tmem_st_wait();
+          tc_fence_before_sync();
+          mbar_arrive(&p_chunk[bf * 3 + (c >> 5)]);         // the control thread issues this slice of P V right away
         };
         exp_chunk(r0, 0);
         exp_chunk(r1, 32);
         exp_chunk(r2, 64);
-        tmem_st_wait();
-        s_sum[(bf * 2 + hf) * 128 + tl] = sum;
+        s_sum[((t & 3) * 2 + hf) * 128 + tl] = sum;
+      } else {
+        tc_fence_before_sync();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) mbar_arrive(&p_chunk[bf * 3 + c]);
       }
-      tc_fence_before_sync();
-      mbar_arrive(&p_ready[bf]);                            // (s_max is double buffered by step parity: no second barrier)
+      mbar_arrive(&p_ready[bf]);                            // row sums published (s_max is double buffered by step parity)
       if (p.dbg) w_busy += clock64() - c0;
     }
     if (p.dbg && threadIdx.x == 0) { p.dbg[blockIdx.x * 8 + 1] = w_wait; p.dbg[blockIdx.x * 8 + 2] = w_busy; }
-  } else {
+  } else if (warp < 12) {
     // -------------------------------------------------------------------- epilogue (warps 8..11)
     const int quarter = warp - 8;
     const int tl = quarter * 32 + lane;
@@ -274,12 +306,13 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
       float sum = 1.0f;
       if (live) {
 #pragma unroll
-        for (int qq = 0; qq < OCH; ++qq) tmem_ld16(lane_base + bf * ATT_BUF_COLS + ATT_O_COL + 16 * qq, o[qq]);
+        for (int qq = 0; qq < OCH; ++qq)
+          tmem_ld16(lane_base + (Cfg::O_SEP ? ATT_O_SEP_COL + bf * 64 : bf * ATT_BUF_COLS + ATT_O_COL) + 16 * qq, o[qq]);
         tmem_ld_wait();
-        sum = s_sum[(bf * 2) * 128 + tl] + s_sum[(bf * 2 + 1) * 128 + tl];
+        sum = s_sum[((t & 3) * 2) * 128 + tl] + s_sum[((t & 3) * 2 + 1) * 128 + tl];
       }
       tc_fence_before_sync();
-      mbar_arrive(&s_free[bf]);                             // O and the row sum are in registers: the buffer may be reused
+      mbar_arrive(&s_free[bf]);                             // O and the row sum are in registers: the O columns may be reused
       if (live) {
         // O rows -> this warp's smem staging (row pitch hd*2+16 B: conflict-free), then the warp writes its 32 rows with
         // consecutive lanes on consecutive 16-byte chunks of a row
