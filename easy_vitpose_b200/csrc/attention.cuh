@@ -100,7 +100,7 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
   uint64_t* p_chunk = bars + 12;     // [2][3] P keys 32c..32c+31 of both halves published (256 softmax threads -> control)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform for the compiler (see elect_one)
   const int lane = threadIdx.x & 31;
   const int items = p.batch * p.heads;
   const int n_my = (items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -125,7 +125,7 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
   pdl_launch_dependents();
   pdl_wait();                                               // qkv from the previous GEMM is complete
 
@@ -137,15 +137,19 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
   };
 
   if (warp == 12) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ issue thread 1: TMA of Q,K and S = Q K^T
+    {
+      // ------------------------------------------------------------------ issue warp 1: TMA of Q,K and S = Q K^T
+      // (the whole warp runs the loop, one elected lane issues: see elect_one)
       // (tcgen05.mma issue costs the issuing thread ~100 cycles per instruction: with one thread for all 16-17 UMMAs of a step
       // the kernel was bound by that thread; Q K^T and P V now have a thread each)
       auto load_qk = [&](int i) {
         const int item = blockIdx.x + i * gridDim.x, b = item / p.heads, h = item % p.heads, q = i & 1;
-        mbar_expect_tx(&qk_full[q], 2 * Cfg::OPER_BYTES);
-        load_oper(stage_ptr(q, 0), &qk_full[q], h * HD, b * ATT_T);
-        load_oper(stage_ptr(q, 1), &qk_full[q], p.dim + h * HD, b * ATT_T);
+        if (elect_one()) {
+          mbar_expect_tx(&qk_full[q], 2 * Cfg::OPER_BYTES);
+          load_oper(stage_ptr(q, 0), &qk_full[q], h * HD, b * ATT_T);
+          load_oper(stage_ptr(q, 1), &qk_full[q], p.dim + h * HD, b * ATT_T);
+        }
+        __syncwarp();
       };
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, ATT_T);
       // S(step t) = Q K^T into buffer t&1
@@ -156,11 +160,14 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
         const uint32_t d = tmem_base + (t & 1) * ATT_BUF_COLS;
         const uint64_t qd = umma_desc_rows<Cfg::MAIN_ROW>(sQ + q_row0 * Cfg::MAIN_ROW);
         const uint64_t kd = umma_desc_rows<Cfg::MAIN_ROW>(sK);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < Cfg::MAIN / 16; ++k) umma_bf16(d, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
-        if constexpr (Cfg::TAIL > 0)
-          umma_bf16(d, umma_desc_rows<32>(sQ + Cfg::MAIN_BYTES + q_row0 * 32), umma_desc_rows<32>(sK + Cfg::MAIN_BYTES), idesc_s, true);
-        umma_commit(&s_full[t & 1]);
+          for (int k = 0; k < Cfg::MAIN / 16; ++k) umma_bf16(d, qd + 2 * k, kd + 2 * k, idesc_s, k != 0);
+          if constexpr (Cfg::TAIL > 0)
+            umma_bf16(d, umma_desc_rows<32>(sQ + Cfg::MAIN_BYTES + q_row0 * 32), umma_desc_rows<32>(sK + Cfg::MAIN_BYTES), idesc_s, true);
+          umma_commit(&s_full[t & 1]);
+        }
+        __syncwarp();
       };
       load_qk(0);
       if (n_my > 1) load_qk(1);
@@ -179,12 +186,15 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
       }
     }
   } else if (warp == 13) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ issue thread 2: TMA of V and O = P V
+    {
+      // ------------------------------------------------------------------ issue warp 2: TMA of V and O = P V
       auto load_v = [&](int i) {
         const int item = blockIdx.x + i * gridDim.x, b = item / p.heads, h = item % p.heads, q = i & 1;
-        mbar_expect_tx(&v_full[q], Cfg::OPER_BYTES);
-        load_oper(stage_ptr(q, 2), &v_full[q], 2 * p.dim + h * HD, b * ATT_T);
+        if (elect_one()) {
+          mbar_expect_tx(&v_full[q], Cfg::OPER_BYTES);
+          load_oper(stage_ptr(q, 2), &v_full[q], 2 * p.dim + h * HD, b * ATT_T);
+        }
+        __syncwarp();
       };
       constexpr uint32_t idesc_o_main = umma_idesc_bf16(128, Cfg::MAIN, /*b_mn_major=*/true);
       constexpr uint32_t idesc_o_tail = umma_idesc_bf16(128, 16, /*b_mn_major=*/true);
@@ -195,16 +205,19 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
         const uint32_t sV = smem_u32(stage_ptr(q, 2));
         const uint32_t buf = tmem_base + (t & 1) * ATT_BUF_COLS;
         const uint32_t od = Cfg::O_SEP ? tmem_base + ATT_O_SEP_COL + (t & 1) * 64 : buf + ATT_O_COL;
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          // 16 keys = 8 packed TMEM columns of P; V (MN-major): 16 tokens = two 8-row groups of the box
-          const int kk = (j >> 1) * 6 + 2 * c + (j & 1);
-          const bool acc = !(c == 0 && j == 0);
-          umma_bf16_ts(od, buf + kk * 8, umma_desc_rows<Cfg::MAIN_ROW>(sV + kk * 16 * Cfg::MAIN_ROW), idesc_o_main, acc);
-          if constexpr (Cfg::TAIL > 0)
-            umma_bf16_ts(od + Cfg::MAIN, buf + kk * 8, umma_desc_rows<32>(sV + Cfg::MAIN_BYTES + kk * 16 * 32), idesc_o_tail, acc);
+          for (int j = 0; j < 4; ++j) {
+            // 16 keys = 8 packed TMEM columns of P; V (MN-major): 16 tokens = two 8-row groups of the box
+            const int kk = (j >> 1) * 6 + 2 * c + (j & 1);
+            const bool acc = !(c == 0 && j == 0);
+            umma_bf16_ts(od, buf + kk * 8, umma_desc_rows<Cfg::MAIN_ROW>(sV + kk * 16 * Cfg::MAIN_ROW), idesc_o_main, acc);
+            if constexpr (Cfg::TAIL > 0)
+              umma_bf16_ts(od + Cfg::MAIN, buf + kk * 8, umma_desc_rows<32>(sV + Cfg::MAIN_BYTES + kk * 16 * 32), idesc_o_tail, acc);
+          }
+          if (c == 2) umma_commit(&o_full[t & 1]);
         }
-        if (c == 2) umma_commit(&o_full[t & 1]);
+        __syncwarp();
       };
       load_v(0);
       if (n_my > 1) load_v(1);

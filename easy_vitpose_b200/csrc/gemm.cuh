@@ -148,7 +148,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   volatile int* ln_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);   // "this CTA finishes the row block" broadcast
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);     // warp-uniform for the compiler (see elect_one in ptx.cuh)
   const int lane = threadIdx.x & 31;
   const int cta_rank = static_cast<int>(cluster_ctarank());
   const int cluster = static_cast<int>(cluster_id_x());
@@ -187,16 +187,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_before_sync();
   cluster_sync_all();                               // barriers + TMEM of BOTH CTAs are live before any remote arrive / pair MMA
   tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
   pdl_launch_dependents();                          // the next kernel may start its prologue as SMs free up
   pdl_wait();                                       // previous kernel's outputs (our A operand / residual) are complete
 
-  if (warp == 10 && lane == 0) {
-    // ------------------------------------------------------------ TMA producer
+  if (warp == 10) {
+    // ------------------------------------------------------------ TMA producer: the whole warp runs the (uniform) loop, one
+    // elected lane issues -- inside an `if (lane == 0)` branch every UTMALDG / UTCHMMA gets an ELECT + R2UR + BRA.U.ANY loop
     int stage = 0;
     uint32_t phase = 0;
     long long t_wait = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = p.dbg ? clock64() : 0;
     for (int pair = cluster; pair < num_pairs; pair += num_clusters) {
       const int mp_i = (p.dbg_flags & 4) ? pair % num_mp : pair / num_n;
       const int mt = mp_i * GEMM_CL + cta_rank;                          // this CTA's M tile
@@ -207,10 +208,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int tiles_per_img = kDeconv ? (p.up_h / p.up_tr) * tiles_x : 1;
       const int kb_per_tap = kDeconv ? p.up_c / GEMM_BK : 1;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const long long w0 = clock64();
+        const long long w0 = p.dbg ? clock64() : 0;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        t_wait += clock64() - w0;
+        if (p.dbg) t_wait += clock64() - w0;
         uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
+        if (elect_one()) {
         if constexpr (kDeconv) {
           // A tile = a up_tr x up_tw patch of the input map shifted by the tap's (dy, dx); the 4-D box is zero filled
           // outside the map (= the transposed conv's border).  With 96-position tiles rows 96..127 of the smem tile are
@@ -228,45 +230,50 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
         }
         tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_w, &full_bar[stage], kb * GEMM_BK, n0 + cta_rank * (BN / GEMM_CL));
+        }
+        __syncwarp();
         if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
     }
-    if (p.dbg) { p.dbg[blockIdx.x * 8 + 3] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 4] = t_wait; }
-  } else if (warp == 11 && lane == 0 && cta_rank == 0) {
+    if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 3] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 4] = t_wait; }
+  } else if (warp == 11 && cta_rank == 0) {
     // ------------------------------------------------------------ MMA issuer (leader CTA of the pair only)
     constexpr uint32_t idesc = umma_idesc_bf16(GEMM_CL * GEMM_BM, BN);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     long long t_wfull = 0, t_wacc = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = p.dbg ? clock64() : 0;
     for (int pair = cluster; pair < num_pairs; pair += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      long long w0 = clock64();
+      long long w0 = p.dbg ? clock64() : 0;
       mbar_wait(&acc_empty[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
-      t_wacc += clock64() - w0;
+      if (p.dbg) t_wacc += clock64() - w0;
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
       for (int kb = 0; kb < num_kb; ++kb) {
-        w0 = clock64();
+        if (p.dbg) w0 = clock64();
         mbar_wait(&full_bar[stage], phase);
-        t_wfull += clock64() - w0;
+        if (p.dbg) t_wfull += clock64() - w0;
         tc_fence_after_sync();
         const uint32_t sa = smem_u32(ring + stage * Cfg::STAGE_BYTES);
         const uint64_t adesc = umma_desc_sw128(sa, 1024);
         const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k) {
-          // +32 B per K=16 step inside the 128-byte swizzle atom (start-address field is >>4)
-          umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // +32 B per K=16 step inside the 128-byte swizzle atom (start-address field is >>4)
+            umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit_pair(&empty_bar[stage], kAllCtas);    // slot reusable in both CTAs once these MMAs retire
+          if (kb == num_kb - 1) umma_commit_pair(&acc_full[acc], kAllCtas);   // accumulators complete in both CTAs -> epilogues
         }
-        umma_commit_pair(&empty_bar[stage], kAllCtas);    // slot reusable in both CTAs once these MMAs retire
+        __syncwarp();
         if (++stage == num_stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit_pair(&acc_full[acc], kAllCtas);     // accumulators complete in both CTAs -> epilogues
     }
-    if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 1] = t_wfull; p.dbg[blockIdx.x * 8 + 2] = t_wacc; }
+    if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 8 + 0] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 1] = t_wfull; p.dbg[blockIdx.x * 8 + 2] = t_wacc; }
   } else if (warp < GEMM_EPI_WARPS) {
     // ------------------------------------------------------------ epilogue
     const int ew = warp;
@@ -300,7 +307,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         for (int c = 0; c < Cfg::HALF; c += COLS) {
           const int col = half * Cfg::HALF + c;
           const int n = n0 + col;
-          if (lane == 0) tma_store_wait_read<0>();    // previous store has finished reading the staging tile
+          if (elect_one()) tma_store_wait_read<0>();  // previous store has finished reading the staging tile (elect.sync is
+                                                      // deterministic for a full mask: the same lane commits and waits)
           __syncwarp();
 #pragma unroll
           for (int sub = 0; sub < COLS; sub += 32) {
@@ -336,7 +344,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
           fence_proxy_async_smem();                   // staging writes -> visible to the TMA engine
           __syncwarp();
-          if (lane == 0 && n < p.N) {
+          if (n < p.N && elect_one()) {
             if constexpr (EPI == EPI_F32_ADD) tma_reduce_add_2d(&tmap_out, stile, n, m0 + quarter * 32);
             else tma_store_2d(&tmap_out, stile, n, m0 + quarter * 32);   // rows past M are clipped by the tensor map
             tma_store_commit();
@@ -402,7 +410,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if constexpr (EPI == EPI_F32_ADD) {
         if (p.ln_out != nullptr && mt < num_m) {
           // ---- fused LayerNorm tail
-          if (lane == 0) tma_store_wait_all<0>();           // this warp's reduce-adds have been performed in L2
+          if (elect_one()) tma_store_wait_all<0>();         // this warp's reduce-adds have been performed in L2
           asm volatile("bar.sync 2, 256;" ::: "memory");    // all 8 epilogue warps of this CTA are done with the tile
           if (threadIdx.x == 0) {
             __threadfence();
@@ -433,7 +441,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
     if constexpr (epi_uses_tma(EPI)) {
-      if (lane == 0) tma_store_wait_read<0>();        // staging must stay alive until the TMA engine has read it; the
+      if (elect_one()) tma_store_wait_read<0>();      // staging must stay alive until the TMA engine has read it; the
                                                       // writes themselves complete before the grid does
     }
     if (p.dbg && warp == 0 && lane == 0) { p.dbg[blockIdx.x * 8 + 5] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 6] = t_wfull; }

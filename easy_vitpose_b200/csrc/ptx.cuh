@@ -301,6 +301,22 @@ __device__ __forceinline__ float gelu_tanh_fit(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
+// One lane of a fully converged warp.  Issue loops run WARP-UNIFORM (all 32 lanes execute the control flow, descriptors and
+// addresses are the same in every lane) and only the tcgen05 / TMA instruction itself is predicated on this: inside an
+// `if (lane == 0)` branch the compiler cannot prove the operands uniform and wraps every UTCHMMA / UTMALDG in an
+// ELECT + R2UR.BROADCAST + BRA.U.ANY "waterfall" loop, which costs the issuing thread ~100 cycles per instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// warp-uniform copy of a value that is the same in every lane (e.g. loaded from shared memory)
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
