@@ -277,13 +277,21 @@ def bench_frame_path(model, B: int, K: int, steps: int, dev) -> dict:
                                    "note": "frame_to_patch_rows inside vpb_infer_frame: replaces crop_resize_normalise + patch_im2col"}}
     try:
         import cv2
-        from oracle import preproc_oracle as PO              # geometry helpers only; the resize below is cv2 itself
-        MEAN, STD = np.array(PO.MEAN), np.array(PO.STD)
+        MEAN, STD = np.array([0.485, 0.456, 0.406]), np.array([0.229, 0.224, 0.225])
         n_cpu = min(B, 32)
         t0 = time.perf_counter()
         for b in boxes[:n_cpu]:
-            canvas, _ = PO.crop_canvas(fr[0], b)
-            x = cv2.resize(canvas, (192, 256), interpolation=cv2.INTER_LINEAR) / 255
+            # what VitInference.inference does per person on the CPU (easy_ViTPose/inference.py:259-265,314-318)
+            x0, x1 = np.clip([b[0] - 10, b[2] + 10], 0, FW); y0, y1 = np.clip([b[1] - 10, b[3] + 10], 0, FH)
+            crop = fr[0][y0:y1, x0:x1]
+            h, w = crop.shape[:2]
+            if w / h < 3 / 4:
+                pad = int(3 / 4 * h) - w
+                crop = np.pad(crop, ((0, 0), (pad // 2, pad - pad // 2), (0, 0)))
+            else:
+                pad = int(w / (3 / 4)) - h
+                crop = np.pad(crop, ((pad // 2, pad - pad // 2), (0, 0), (0, 0)))
+            x = cv2.resize(crop, (192, 256), interpolation=cv2.INTER_LINEAR) / 255
             x = ((x - MEAN) / STD).transpose(2, 0, 1)[None].astype(np.float32)
         cdt = time.perf_counter() - t0
         res["cpu_preprocess_reference"] = {"value": n_cpu / cdt, "unit": "crops/s", "cores": 1,
@@ -320,7 +328,7 @@ def run_gpu(args) -> None:
     import torch.distributed as dist
 
     from easy_vitpose_b200 import ViTPose, model_cfg
-    from oracle import vitpose_oracle as O      # seeded weights / crops generator only
+    from easy_vitpose_b200.synthetic import random_state_dict      # the GPU arm never touches oracle/
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -339,7 +347,7 @@ def run_gpu(args) -> None:
 
     D, depth, heads = MODELS[args.model]
     K, B = args.keypoints, args.batch
-    sd = O.make_state_dict(D, depth, K, seed=1, peaky=0.1, bumps=True)
+    sd = random_state_dict(args.model, K, seed=1, peaks=True)
     model = ViTPose(model_cfg(args.model, K), max_batch=B)
     model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}).to(dev)
     del sd

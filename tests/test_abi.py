@@ -67,3 +67,22 @@ def test_state_dict_contract_is_strict():
     m.load_state_dict({"state_dict": sd})                     # both checkpoint layouts (inference.py:162-166)
     out = m.state_dict()
     assert set(out) == set(sd) and torch.equal(out["backbone.pos_embed"], sd["backbone.pos_embed"])
+
+
+def test_synthetic_weights_follow_the_state_dict_contract():
+    """easy_vitpose_b200.synthetic (what bench.py's GPU arm loads: it must not import oracle/) produces exactly the reference's
+    state_dict keys and shapes, and a strict load accepts them without a GPU."""
+    import numpy as np
+    import torch
+
+    from easy_vitpose_b200 import ViTPose, model_cfg
+    from easy_vitpose_b200.synthetic import random_crops, random_state_dict
+    from oracle import vitpose_oracle as O
+    for size, K in (("s", 17), ("b", 25), ("h", 133)):
+        D, depth, heads = O.MODEL_DIMS[size]
+        mine = random_state_dict(size, K, seed=3)
+        ref = {k: v.shape for k, v in O.make_state_dict(D, depth, K, 3).items() if not k.endswith("num_batches_tracked")}
+        assert {k: v.shape for k, v in mine.items()} == ref
+        assert all(v.dtype == np.float32 for v in mine.values())
+        ViTPose(model_cfg(size, K)).load_state_dict({k: torch.from_numpy(v) for k, v in mine.items()})      # strict, CPU side only
+    assert random_crops(2, 1).shape == (2, 3, 256, 192) and np.array_equal(random_crops(2, 1), random_crops(2, 1))

@@ -10,11 +10,11 @@ import numpy as np
 import torch
 
 from easy_vitpose_b200 import ViTPose, model_cfg
-from oracle import vitpose_oracle as O      # seeded weights only
+from easy_vitpose_b200.synthetic import random_state_dict
 
 B, K = 64, 17
 m = ViTPose(model_cfg("b", K), max_batch=B)
-m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in O.make_state_dict(768, 12, K, 11, peaky=0.1, bumps=True).items()}).to("cuda:0")
+m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in random_state_dict("b", K, seed=11).items()}).to("cuda:0")
 m.set_option("graph", 0)
 rs = np.random.RandomState(5)
 frame = torch.from_numpy(rs.randint(0, 256, size=(1080, 1920, 3), dtype=np.uint8)).cuda()

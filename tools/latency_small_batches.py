@@ -6,9 +6,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from easy_vitpose_b200 import ViTPose, dyn_model_import
-from oracle import vitpose_oracle as O
+from easy_vitpose_b200.synthetic import random_state_dict
 m = ViTPose(dyn_model_import("ap10k", "b"), max_batch=32)
-m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in O.make_state_dict(768, 12, 17, 1, peaky=0.1, bumps=True).items()}).to("cuda:0")
+m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in random_state_dict("b", 17, seed=1).items()}).to("cuda:0")
 for graph in (0, 1):
     m.set_option("graph", graph)
     for n in (1, 2, 6, 16, 32):
