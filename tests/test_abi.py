@@ -86,3 +86,29 @@ def test_synthetic_weights_follow_the_state_dict_contract():
         assert all(v.dtype == np.float32 for v in mine.values())
         ViTPose(model_cfg(size, K)).load_state_dict({k: torch.from_numpy(v) for k, v in mine.items()})      # strict, CPU side only
     assert random_crops(2, 1).shape == (2, 3, 256, 192) and np.array_equal(random_crops(2, 1), random_crops(2, 1))
+
+
+def test_decode_api_fails_loudly_without_cuda_and_checks_its_config():
+    """No CPU fallback anywhere on the product path: decode entry points refuse CPU tensors; the reference's config conflicts
+    (vit_utils/top_down_eval.py:548-553) and the combinations that are not built raise before any device work."""
+    import numpy as np
+    import pytest
+    import torch
+
+    from easy_vitpose_b200 import decode_heatmaps, keypoints_from_heatmaps
+    hm = np.zeros((1, 17, 64, 48), np.float32)
+    c = np.array([[96, 128]]); s = np.array([[192, 256]])
+    with pytest.raises(RuntimeError):
+        decode_heatmaps(torch.zeros(1, 17, 64, 48), torch.tensor([[192, 256]]))
+    with pytest.raises(AssertionError):
+        keypoints_from_heatmaps(hm, c, s, post_process="megvii", use_udp=True)
+    with pytest.raises(AssertionError):
+        keypoints_from_heatmaps(hm, c, s, unbiased=True, post_process="megvii")
+    with pytest.raises(NotImplementedError):
+        keypoints_from_heatmaps(hm, c, s, use_udp=True, target_type="CombinedTarget")
+    with pytest.raises(ValueError):
+        keypoints_from_heatmaps(hm, c, s, use_udp=True, target_type="nonsense")
+    with pytest.raises(NotImplementedError):
+        keypoints_from_heatmaps(hm, c, s, post_process="unbiased", kernel=17)
+    with pytest.raises(ValueError):
+        keypoints_from_heatmaps(hm, c, s, post_process="fancy")
