@@ -38,6 +38,7 @@ def test_no_cpu_fallback_without_gpu():
 
 def test_configs_match_reference_shapes():
     from easy_vitpose_b200 import dyn_model_import
+    from easy_vitpose_b200.model import _expected_shapes
     from oracle import vitpose_oracle as O
     for size, ds, K in [("s", "coco", 17), ("b", "ap10k", 17), ("l", "coco_25", 25), ("h", "wholebody", 133)]:
         cfg = dyn_model_import(ds, size)
