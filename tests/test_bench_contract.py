@@ -1,0 +1,29 @@
+"""CPU: the JSON-line contract of bench.py's reference arm (the arm that runs without a GPU) and of the argument defaults."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--model", "s", "--cpu-sample", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout                       # exactly one JSON line on stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "crops/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["steps"] == 1 and d["value"] > 0 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_defaults_finish_within_minutes_by_construction():
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert 'add_argument("--gpus", type=int, default=1)' in src
+    assert 'add_argument("--warmup", type=int, default=20)' in src      # W >= 3
