@@ -301,6 +301,12 @@ def bench_frame_path(model, B: int, K: int, steps: int, dev) -> dict:
     return res
 
 
+def workload_name(model: str, K: int, B: int) -> str:
+    """config.workload, the same string in both arms."""
+    return (f"ViT-{model.upper()} K={K} bf16, batch={B} synthetic 256x192 crops per GPU"
+            + (" (BASELINE configs[1]: ViT-B COCO-17, batch 64)" if (model, K, B) == ("b", 17, 64) else ""))
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -312,8 +318,9 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ViT-{args.model.upper()} COCO-{args.keypoints}, 256x192 crops, CPU sample of {sample} crops per step",
-                   "batch_per_gpu": args.batch},
+        "config": {"workload": workload_name(args.model, args.keypoints, args.batch), "batch_per_gpu": args.batch,
+                   "global_batch": args.gpus * args.batch,
+                   "reference_sample": f"each step = {sample} crops of that workload on the host cores (bounded sample)"},
         "cpu_baseline": {"value": value, "unit": "crops/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} crops/step x {args.steps} steps, torch CPU fp32 forward + numpy decode (oracle/)"},
         "e2e": {"value": value, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -491,8 +498,7 @@ def run_gpu(args) -> None:
             "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"ViT-{args.model.upper()} K={K} bf16, batch={B} synthetic 256x192 crops per GPU"
-                                   + (" (BASELINE configs[1]: ViT-B COCO-17, batch 64)" if (args.model, K, B) == ("b", 17, 64) else ""),
+            "config": {"workload": workload_name(args.model, K, B),
                        "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"dp{world} (crops sharded, weights replicated)",
                        "l2": f"inputs rotate over {NBUF} device batches ({NBUF * B * 589824 / 1e6:.0f} MB > 126 MB L2); "
                              "weights + activations touched per step exceed L2 several times over",
