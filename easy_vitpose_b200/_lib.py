@@ -39,6 +39,7 @@ EXPORTS = {
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "vpb_decode_frame": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "vpb_infer_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vpb_frame_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "vpb_infer_frame_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vpb_submit_frame_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
     "vpb_host_alloc": (C.c_void_p, [C.c_int64]),
@@ -65,9 +66,13 @@ def lib():
             try:
                 build()                              # nvcc cross-compiles sm_100a anywhere; seconds
             except Exception as exc:
-                if not os.path.exists(LIB):
-                    raise RuntimeError(f"{LIB} is missing and could not be built ({exc}); build it with "
-                                       "`python -m easy_vitpose_b200.build`; there is no fallback implementation") from exc
+                # never load a library older than its sources: its ABI / kernels may no longer match the header and
+                # the argtypes below.  VPB_ALLOW_STALE=1 is the explicit escape hatch (e.g. a box without nvcc).
+                if not os.path.exists(LIB) or os.environ.get("VPB_ALLOW_STALE", "0") != "1":
+                    raise RuntimeError(f"{LIB} is missing or older than its sources and could not be rebuilt ({exc}); build it "
+                                       "with `python -m easy_vitpose_b200.build`; there is no fallback implementation") from exc
+                import warnings
+                warnings.warn(f"loading a STALE {LIB} (VPB_ALLOW_STALE=1): {exc}")
         handle = C.CDLL(LIB)
         for name, (res, args) in EXPORTS.items():
             fn = getattr(handle, name)          # AttributeError here = header and library disagree

@@ -114,9 +114,24 @@ static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+// ------------------------------------------------------------------------------------------------ per-device state
+// cudaFuncSetAttribute (dynamic smem above 48 KB) applies to the CURRENT device's context and the SM count sizes every
+// persistent grid, so both are tracked per device: engines on different GPUs of one process each set their own.
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+  int sms = 0;                      // 0 = not checked yet
+  bool attn_attr = false;
+  unsigned gemm_attr = 0;           // bit per gemm instantiation (see gemm_slot)
+};
+static DeviceState g_devs[kMaxDevices];
+static DeviceState* cur_dev() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return &g_devs[d];
+}
+static int num_sms() { return cur_dev()->sms; }
+
 // ------------------------------------------------------------------------------------------------ GEMM dispatch
-static int g_num_sms = 0;
-static bool g_attr_done = false;
 
 // `tout` is the output tensor map of the TMA epilogues (EPI_BF16, EPI_BF16_GELU: bf16 box 64x32; EPI_F32_ADD: f32 box
 // 32x32); direct epilogues ignore it (pass any valid map).  W maps carry boxes of BN/2 rows: each CTA of the pair
@@ -125,15 +140,17 @@ template <int BN, int EPI>
 static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tout, const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN, EPI>;
   auto kern = gemm_bf16_tcgen05<BN, EPI>;
-  static bool attr = false;
-  if (!attr) {
+  DeviceState* ds = cur_dev();
+  if (ds->sms == 0) return fail(VPB_ERR_STATE, "gemm: device not initialised (device_check)");
+  constexpr unsigned slot = 1u << (EPI * 4 + (BN == 256 ? 0 : BN == 128 ? 1 : BN == 144 ? 2 : 3));
+  if (!(ds->gemm_attr & slot)) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr = true;
+    ds->gemm_attr |= slot;
   }
   const bool deconv = (EPI == EPI_BF16_RELU_UP);
   const int num_m = deconv ? p.M / (p.up_tr * p.up_tw) : (p.M + GEMM_BM - 1) / GEMM_BM;
   const int pairs = ((num_m + GEMM_CL - 1) / GEMM_CL) * (deconv ? 4 : (p.N + BN - 1) / BN);
-  const int max_clusters = g_num_sms / GEMM_CL;
+  const int max_clusters = ds->sms / GEMM_CL;
   const int grid = GEMM_CL * (pairs < max_clusters ? pairs : max_clusters);
   CU_TRY(launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, ta, tw, tout, p));
   return VPB_OK;
@@ -154,21 +171,20 @@ static int gemm_launch(int bn, int epi, const CUtensorMap& ta, const CUtensorMap
 }
 static int bn_for(int n) { return (n % 256 == 0 && !(g_dbg_flags & 8)) ? 256 : 128; }   // debug flag 8: force 128-wide tiles
 
+// `device` must be the current device (callers cudaSetDevice / cudaGetDevice first)
 static int device_check(int device) {
-  static int checked_device = -1;
-  if (checked_device == device && g_num_sms > 0) return VPB_OK;
+  if (device < 0 || device >= kMaxDevices) return fail(VPB_ERR_ARG, "device %d out of range", device);
+  DeviceState* ds = &g_devs[device];
+  if (ds->sms > 0 && ds->attn_attr) return VPB_OK;
   cudaDeviceProp prop;
   CU_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(VPB_ERR_ARG, "device %d is sm_%d%d; this library only runs on sm_100 (B200), no fallback", device,
                                     prop.major, prop.minor);
-  g_num_sms = prop.multiProcessorCount;
-  if (!g_attr_done) {
-    CU_TRY(cudaFuncSetAttribute(attention_tcgen05<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<32>::SMEM));
-    CU_TRY(cudaFuncSetAttribute(attention_tcgen05<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<64>::SMEM));
-    CU_TRY(cudaFuncSetAttribute(attention_tcgen05<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<80>::SMEM));
-    g_attr_done = true;
-  }
-  checked_device = device;
+  CU_TRY(cudaFuncSetAttribute(attention_tcgen05<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<32>::SMEM));
+  CU_TRY(cudaFuncSetAttribute(attention_tcgen05<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<64>::SMEM));
+  CU_TRY(cudaFuncSetAttribute(attention_tcgen05<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<80>::SMEM));
+  ds->attn_attr = true;
+  ds->sms = prop.multiProcessorCount;
   return VPB_OK;
 }
 
@@ -183,7 +199,8 @@ static int make_attn_maps(CUtensorMap* main, CUtensorMap* tail, const void* qkv,
 }
 static int attention_launch(int hd, const CUtensorMap& main, const CUtensorMap& tail, const AttnParams& ap, cudaStream_t st) {
   const int items = ap.batch * ap.heads;
-  const dim3 grid(items < g_num_sms ? items : g_num_sms);      // one CTA per SM (512 TMEM columns each)
+  const int sms = num_sms();
+  const dim3 grid(items < sms ? items : sms);      // one CTA per SM (512 TMEM columns each)
   cudaError_t err;
   switch (hd) {
     case 32: err = launch_k(attention_tcgen05<32>, grid, dim3(ATT_THREADS), AttCfg<32>::SMEM, st, main, tail, ap); break;
@@ -280,6 +297,11 @@ struct vpb_engine {
   int32_t *idx[2], *org_wh[2];
   cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  // One activation workspace per engine: calls on DIFFERENT streams are ordered against each other by an event recorded
+  // after every enqueue (ws_release) and waited on when the stream changes (ws_acquire); calls on one stream order themselves.
+  cudaEvent_t ev_ws = nullptr;
+  cudaStream_t ws_last = nullptr;
+  bool ws_used = false;
   CUtensorMap m_patch_rows, m_xn, m_attn, m_hid, m_d2, m_qkv_att, m_qkv_att_tail;   // A operands / attention boxes
   CUtensorMap m_feat_nhwc, m_d1_nhwc;                                 // implicit-GEMM deconv inputs (4-D)
   CUtensorMap o_qkv, o_hid, o_x;                                                             // TMA-epilogue outputs
@@ -354,6 +376,7 @@ extern "C" void vpb_destroy(vpb_engine* e) {
     if (e->ev_h2d[s]) cudaEventDestroy(e->ev_h2d[s]);
     if (e->ev_done[s]) cudaEventDestroy(e->ev_done[s]);
   }
+  if (e->ev_ws) cudaEventDestroy(e->ev_ws);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->compute_stream) cudaStreamDestroy(e->compute_stream);
   for (int s = 0; s < 2; ++s) if (e->frame_stage[s]) cudaFree(e->frame_stage[s]);
@@ -472,6 +495,7 @@ extern "C" int vpb_finalize(vpb_engine* e) {
     CU_TRY(cudaEventCreateWithFlags(&e->ev_h2d[s], cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&e->ev_done[s], cudaEventDisableTiming));
   }
+  CU_TRY(cudaEventCreateWithFlags(&e->ev_ws, cudaEventDisableTiming));
   VPB_TRY(dev_alloc(e, &e->ln_counters, (M + 127) / 128 + 1));
   CU_TRY(cudaMemset(e->ln_counters, 0, ((M + 127) / 128 + 1) * sizeof(int)));
   VPB_TRY(dev_alloc(e, &e->g_kpts, B * e->K * 3));
@@ -519,7 +543,7 @@ extern "C" int vpb_finalize(vpb_engine* e) {
 // ------------------------------------------------------------------------------------------------ forward
 template <int D>
 static void ln_launch(const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, float eps, cudaStream_t st) {
-  const int want = cdiv(rows, 4), cap = g_num_sms * 4;     // 4 warps per CTA, at most 4 CTAs per SM (persistent, row stride)
+  const int want = cdiv(rows, 4), cap = num_sms() * 4;     // 4 warps per CTA, at most 4 CTAs per SM (persistent, row stride)
   launch_k(layernorm_f32_to_bf16<D>, dim3(want < cap ? want : cap), dim3(128), 0, st, x, g, b, y, rows, eps);
 }
 static int layernorm(const float* x, const float* g, const float* b, __nv_bfloat16* y, int rows, int D, float eps, cudaStream_t st) {
@@ -690,6 +714,37 @@ static int apply_l2_policy(vpb_engine* e, cudaStream_t st) {
   return VPB_OK;
 }
 
+static bool stream_is_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (st == nullptr) return false;                              // the legacy default stream cannot be captured
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs != cudaStreamCaptureStatusNone;
+}
+// Workspace hand-over between streams (see vpb_engine::ev_ws).  Inside a caller-side stream capture the events are left
+// alone (a wait on an event recorded outside the capture would be a cross-capture dependency): the caller then owns the
+// ordering of that graph against the engine's other users.
+static int ws_acquire(vpb_engine* e, cudaStream_t st) {
+  if (e->ws_used && e->ws_last != st && !stream_is_capturing(st)) CU_TRY(cudaStreamWaitEvent(st, e->ev_ws, 0));
+  return VPB_OK;
+}
+static int ws_release(vpb_engine* e, cudaStream_t st) {
+  if (stream_is_capturing(st)) return VPB_OK;
+  CU_TRY(cudaEventRecord(e->ev_ws, st));
+  e->ws_last = st; e->ws_used = true;
+  return VPB_OK;
+}
+
+// Makes the engine's device current for the scope of an entry point and restores the caller's afterwards, so engines on
+// different GPUs can be driven from one thread (the stream argument must belong to the engine's device).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(const vpb_engine* e) {
+    int cur = -1;
+    if (e && cudaGetDevice(&cur) == cudaSuccess && cur != e->cfg.device && cudaSetDevice(e->cfg.device) == cudaSuccess) prev = cur;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 static int check_ready(vpb_engine* e, int batch) {
   if (!e) return fail(VPB_ERR_ARG, "null engine");
   if (!e->finalized) return fail(VPB_ERR_STATE, "weights not finalized: call vpb_finalize first");
@@ -699,25 +754,29 @@ static int check_ready(vpb_engine* e, int batch) {
 
 extern "C" int vpb_forward(vpb_engine* e, const float* d_crops, int32_t batch, float* d_heatmaps, void* stream) {
   VPB_TRY(check_ready(e, batch));
+  DeviceGuard dev_guard(e);
   if (!d_crops || !d_heatmaps) return fail(VPB_ERR_ARG, "vpb_forward: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VPB_TRY(apply_l2_policy(e, st));
+  VPB_TRY(ws_acquire(e, st));
   VPB_TRY(patch_gather(e, d_crops, batch, st));
   VPB_TRY(backbone(e, batch, st));
-  if (e->stop_after && e->stop_after <= 10) return VPB_OK;
-  return head(e, batch, d_heatmaps, st);
+  if (!(e->stop_after && e->stop_after <= 10)) VPB_TRY(head(e, batch, d_heatmaps, st));
+  return ws_release(e, st);
 }
 
 extern "C" int vpb_forward_features(vpb_engine* e, const float* d_crops, int32_t batch, float* d_features, void* stream) {
   VPB_TRY(check_ready(e, batch));
+  DeviceGuard dev_guard(e);
   if (!d_crops || !d_features) return fail(VPB_ERR_ARG, "vpb_forward_features: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VPB_TRY(ws_acquire(e, st));
   VPB_TRY(patch_gather(e, d_crops, batch, st));
   VPB_TRY(backbone(e, batch, st));
   const long long tot = static_cast<long long>(batch) * e->D * 192;
   tokens_to_nchw<<<cdiv(tot, 256), 256, 0, st>>>(e->xn, d_features, batch, e->D);
   CU_TRY(cudaGetLastError());
-  return VPB_OK;
+  return ws_release(e, st);
 }
 
 static int decode_launch(const float* d_heatmaps, int32_t n, int32_t k, const int32_t* d_org_wh, const int32_t* d_offs_yx, float* d_kpts,
@@ -739,12 +798,15 @@ extern "C" int vpb_decode(const float* d_heatmaps, int32_t n, int32_t k, const i
 // keypoint_head(features): TopdownHeatmapSimpleHead.forward (head/topdown_heatmap_simple_head.py:188-193) on backbone features
 extern "C" int vpb_head(vpb_engine* e, const float* d_features, int32_t batch, float* d_heatmaps, void* stream) {
   VPB_TRY(check_ready(e, batch));
+  DeviceGuard dev_guard(e);
   if (!d_features || !d_heatmaps) return fail(VPB_ERR_ARG, "vpb_head: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long tot = static_cast<long long>(batch) * e->D * 192;
+  VPB_TRY(ws_acquire(e, st));
   nchw_to_tokens<<<cdiv(tot, 256), 256, 0, st>>>(d_features, e->xn, batch, e->D);
   CU_TRY(cudaGetLastError());
-  return head(e, batch, d_heatmaps, st);
+  VPB_TRY(head(e, batch, d_heatmaps, st));
+  return ws_release(e, st);
 }
 extern "C" int vpb_flip_back(const float* d_in, int32_t n, int32_t k, const int32_t* d_perm, int32_t shift, float* d_out, void* stream) {
   if (!d_in || !d_out || !d_perm || d_in == d_out) return fail(VPB_ERR_ARG, "vpb_flip_back: null or aliased pointers");
@@ -795,12 +857,23 @@ static int infer_enqueue(vpb_engine* e, const Source& src, const int32_t* d_org_
 }
 
 // crops -> keypoints; d_offs_yx (nullable) moves the keypoints from crop to frame coordinates inside the decode kernel
+static int infer_core_locked(vpb_engine* e, const Source& src, const int32_t* d_org_wh, const int32_t* d_offs_yx, int32_t batch,
+                             float* d_kpts, int32_t* d_idx, float* d_heatmaps, void* stream);
 static int infer_core(vpb_engine* e, const Source& src, const int32_t* d_org_wh, const int32_t* d_offs_yx, int32_t batch,
                       float* d_kpts, int32_t* d_idx, float* d_heatmaps, void* stream) {
-  float* heat = d_heatmaps ? d_heatmaps : e->heat;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VPB_TRY(apply_l2_policy(e, st));
-  if (!e->use_graph || e->prof.on || e->stop_after || st == nullptr)      // the legacy default stream cannot be captured
+  VPB_TRY(ws_acquire(e, st));
+  VPB_TRY(infer_core_locked(e, src, d_org_wh, d_offs_yx, batch, d_kpts, d_idx, d_heatmaps, stream));
+  return ws_release(e, st);
+}
+static int infer_core_locked(vpb_engine* e, const Source& src, const int32_t* d_org_wh, const int32_t* d_offs_yx, int32_t batch,
+                             float* d_kpts, int32_t* d_idx, float* d_heatmaps, void* stream) {
+  float* heat = d_heatmaps ? d_heatmaps : e->heat;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // eager launches on the legacy default stream (cannot be captured) and when the CALLER is already capturing `st`
+  // (a nested cudaStreamBeginCapture would fail): the engine's kernels then simply become nodes of the caller's graph
+  if (!e->use_graph || e->prof.on || e->stop_after || st == nullptr || stream_is_capturing(st))
     return infer_enqueue(e, src, d_org_wh, d_offs_yx, batch, d_kpts, d_idx, heat, stream);
   vpb_engine::GraphEntry* g = nullptr;
   for (auto& c : e->graphs)
@@ -837,6 +910,7 @@ static int infer_core(vpb_engine* e, const Source& src, const int32_t* d_org_wh,
 extern "C" int vpb_infer(vpb_engine* e, const float* d_crops, const int32_t* d_org_wh, int32_t batch, float* d_kpts, int32_t* d_idx,
                          float* d_heatmaps, void* stream) {
   VPB_TRY(check_ready(e, batch));
+  DeviceGuard dev_guard(e);
   if (!d_crops || !d_org_wh || !d_kpts) return fail(VPB_ERR_ARG, "vpb_infer: null pointer");
   Source src;
   src.crops = d_crops;
@@ -871,8 +945,21 @@ static int infer_frame_enqueue(vpb_engine* e, const uint8_t* d_frame, int32_t fr
 extern "C" int vpb_infer_frame(vpb_engine* e, const uint8_t* d_frame, int32_t frame_h, int32_t frame_w, const int32_t* d_bboxes,
                                int32_t n, float* d_kpts, int32_t* d_idx, void* stream) {
   VPB_TRY(check_ready(e, n));
+  DeviceGuard dev_guard(e);
   if (!d_frame || !d_bboxes || !d_kpts || frame_h < 1 || frame_w < 1) return fail(VPB_ERR_ARG, "vpb_infer_frame: bad argument");
   return infer_frame_enqueue(e, d_frame, frame_h, frame_w, d_bboxes, n, d_kpts, d_idx, static_cast<cudaStream_t>(stream));
+}
+
+// Status word of the device-side frame path (bit 0: a box was empty after padding + clipping; such a box is decoded from
+// a black crop with scale 0 where the reference raises).  Synchronous: waits for the device, copies the word, clears it.
+extern "C" int vpb_frame_status(vpb_engine* e, int32_t* h_status) {
+  if (!e || !h_status) return fail(VPB_ERR_ARG, "vpb_frame_status: null argument");
+  if (!e->finalized) return fail(VPB_ERR_STATE, "not finalized");
+  DeviceGuard dev_guard(e);
+  CU_TRY(cudaDeviceSynchronize());
+  CU_TRY(cudaMemcpy(h_status, e->pp_status, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  CU_TRY(cudaMemset(e->pp_status, 0, sizeof(int32_t)));
+  return VPB_OK;
 }
 
 // host boxes are checked here, where the reference raises (ZeroDivisionError in pad_image / cv2.resize on an empty crop)
@@ -899,16 +986,19 @@ static int frame_stage_reserve(vpb_engine* e, int slot, size_t bytes) {
 extern "C" int vpb_infer_frame_host(vpb_engine* e, const uint8_t* h_frame, int32_t frame_h, int32_t frame_w, const int32_t* h_bboxes,
                                     int32_t n, float* h_kpts, int32_t* h_idx, void* stream) {
   VPB_TRY(check_ready(e, n));
+  DeviceGuard dev_guard(e);
   if (!h_frame || !h_bboxes || !h_kpts || frame_h < 1 || frame_w < 1) return fail(VPB_ERR_ARG, "vpb_infer_frame_host: bad argument");
   VPB_TRY(check_boxes_host(h_bboxes, n, frame_h, frame_w));
   const size_t fbytes = static_cast<size_t>(frame_h) * frame_w * 3;
   VPB_TRY(frame_stage_reserve(e, 0, fbytes));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU_TRY(cudaStreamWaitEvent(st, e->ev_done[0], 0));      // slot 0 is shared with the pipelined path: its last user is done
   CU_TRY(cudaMemcpyAsync(e->frame_stage[0], h_frame, fbytes, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(e->bbox_stage[0], h_bboxes, static_cast<size_t>(n) * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   VPB_TRY(infer_frame_enqueue(e, e->frame_stage[0], frame_h, frame_w, e->bbox_stage[0], n, e->kpts[0], e->idx[0], st));
   CU_TRY(cudaMemcpyAsync(h_kpts, e->kpts[0], static_cast<size_t>(n) * e->K * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (h_idx) CU_TRY(cudaMemcpyAsync(h_idx, e->idx[0], static_cast<size_t>(n) * e->K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaEventRecord(e->ev_done[0], st));
   CU_TRY(cudaStreamSynchronize(st));
   return VPB_OK;
 }
@@ -918,10 +1008,10 @@ extern "C" int vpb_infer_frame_host(vpb_engine* e, const uint8_t* h_frame, int32
 extern "C" int vpb_submit_frame_host(vpb_engine* e, const uint8_t* h_frame, int32_t frame_h, int32_t frame_w, const int32_t* h_bboxes,
                                      int32_t n, float* h_kpts, int32_t* h_idx, int32_t slot) {
   VPB_TRY(check_ready(e, n));
+  DeviceGuard dev_guard(e);
   if (!h_frame || !h_bboxes || !h_kpts || frame_h < 1 || frame_w < 1 || slot < 0 || slot > 1)
     return fail(VPB_ERR_ARG, "vpb_submit_frame_host: bad argument");
   VPB_TRY(check_boxes_host(h_bboxes, n, frame_h, frame_w));
-  CU_TRY(cudaSetDevice(e->cfg.device));
   const size_t fbytes = static_cast<size_t>(frame_h) * frame_w * 3;
   VPB_TRY(frame_stage_reserve(e, slot, fbytes));
   CU_TRY(cudaStreamWaitEvent(e->copy_stream, e->ev_done[slot], 0));
@@ -939,13 +1029,16 @@ extern "C" int vpb_submit_frame_host(vpb_engine* e, const uint8_t* h_frame, int3
 extern "C" int vpb_infer_host(vpb_engine* e, const float* h_crops, const int32_t* h_org_wh, int32_t batch, float* h_kpts,
                               int32_t* h_idx, void* stream) {
   VPB_TRY(check_ready(e, batch));
+  DeviceGuard dev_guard(e);
   if (!h_crops || !h_org_wh || !h_kpts) return fail(VPB_ERR_ARG, "vpb_infer_host: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU_TRY(cudaStreamWaitEvent(st, e->ev_done[0], 0));      // slot 0 is shared with the pipelined path: its last user is done
   CU_TRY(cudaMemcpyAsync(e->crops_stage[0], h_crops, static_cast<size_t>(batch) * 3 * 256 * 192 * sizeof(float), cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(e->org_wh[0], h_org_wh, static_cast<size_t>(batch) * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   VPB_TRY(vpb_infer(e, e->crops_stage[0], e->org_wh[0], batch, e->kpts[0], e->idx[0], nullptr, st));
   CU_TRY(cudaMemcpyAsync(h_kpts, e->kpts[0], static_cast<size_t>(batch) * e->K * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (h_idx) CU_TRY(cudaMemcpyAsync(h_idx, e->idx[0], static_cast<size_t>(batch) * e->K * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaEventRecord(e->ev_done[0], st));
   CU_TRY(cudaStreamSynchronize(st));
   return VPB_OK;
 }
@@ -956,8 +1049,8 @@ extern "C" int vpb_infer_host(vpb_engine* e, const float* h_crops, const int32_t
 extern "C" int vpb_submit_host(vpb_engine* e, const float* h_crops, const int32_t* h_org_wh, int32_t batch, float* h_kpts,
                                int32_t* h_idx, int32_t slot) {
   VPB_TRY(check_ready(e, batch));
+  DeviceGuard dev_guard(e);
   if (!h_crops || !h_org_wh || !h_kpts || slot < 0 || slot > 1) return fail(VPB_ERR_ARG, "vpb_submit_host: bad argument");
-  CU_TRY(cudaSetDevice(e->cfg.device));
   // the slot's previous use must have finished with its staging buffers before they are overwritten
   CU_TRY(cudaStreamWaitEvent(e->copy_stream, e->ev_done[slot], 0));
   CU_TRY(cudaMemcpyAsync(e->crops_stage[slot], h_crops, static_cast<size_t>(batch) * 3 * 256 * 192 * sizeof(float), cudaMemcpyHostToDevice,

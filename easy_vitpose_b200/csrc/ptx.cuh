@@ -289,11 +289,14 @@ __device__ __forceinline__ float erf_as(float x) {
   return copysignf(fmaf(-p * t, e, 1.0f), x);
 }
 // GELU(x) = x * Phi(x) with erf(z) evaluated as tanh(P(z)): 0.5 x (1 + tanh(x (c0 + c1 x^2 + c2 x^4))), coefficients
-// fitted to the exact erf form (max |error| 2.5e-5 over all x with an exact tanh; tools/fit_gelu.py) -- NOT the
-// 0.044715 "tanh GELU".  tanh.approx.f32 adds <= 2^-11 relative error.  7 instructions instead of ~18, one MUFU.
+// fitted to the exact erf form on [-8, 8] (max |error| 2.5e-5 with an exact tanh; tools/fit_gelu.py) -- NOT the
+// 0.044715 "tanh GELU".  c2 < 0, so the polynomial would change sign near |x| = 11.1 and flip the tanh: x^2 is clamped
+// to 64, beyond which P(x^2) = P(64) = 1.726 > 0 and tanh(1.726 x) is +-1 to fp32 precision, i.e. GELU(x) = x or 0 exactly
+// as the erf form gives there (tests/test_gelu_fit.py bounds the formula against erf over +-40).
+// tanh.approx.f32 adds <= 2^-11 relative error.  8 instructions instead of ~18, one MUFU.
 // The result is rounded to bf16 (relative step 2^-8) right after, which dominates both error terms.
 __device__ __forceinline__ float gelu_tanh_fit(float x) {
-  const float x2 = x * x;
+  const float x2 = fminf(x * x, 64.0f);
   float p = fmaf(-3.51516782e-4f, x2, 3.70056460e-2f);
   p = fmaf(p, x2, 7.97507884e-1f);
   float t;

@@ -383,11 +383,19 @@ class ViTPose:
                 raise ValueError("a box is empty after padding and clipping to the frame")
         return crops, org, offs
 
-    def infer_frame(self, frame: torch.Tensor, bboxes):
+    def frame_status(self) -> int:
+        """Status word of the device-side frame calls since the last query (bit 0: a box was empty after padding and
+        clipping).  Synchronises the device and clears the word (vpb_frame_status)."""
+        self._ensure()
+        st = C.c_int32(0)
+        _lib.check(_lib.lib().vpb_frame_status(self._handle, C.byref(st)))
+        return int(st.value)
+
+    def infer_frame(self, frame: torch.Tensor, bboxes, check: bool = False):
         """uint8 RGB frame [H,W,3] (CUDA) + boxes [n,4] -> (kpts f32 [n,K,3] (y, x, score) in FRAME pixels, idx i32 [n,K]):
         the whole per-person loop of VitInference.inference (easy_ViTPose/inference.py:258-272) as one enqueue, no host sync.
-        Boxes that are empty after clipping are not detected here (that would need a sync); use infer_frame_host or
-        preprocess() when the boxes are untrusted."""
+        A box that is empty after clipping only sets the engine's status word (frame_status()); `check=True` synchronises
+        and raises ValueError like the reference does (pad_image / cv2.resize on an empty crop)."""
         frame, bb = self._check_frame(frame, bboxes)
         n = bb.shape[0]
         kp = torch.empty((n, self.num_keypoints, 3), dtype=torch.float32, device=frame.device)
@@ -396,6 +404,8 @@ class ViTPose:
             self._call_on_stream((frame, bb, kp, idx), lambda st: _lib.lib().vpb_infer_frame(
                 self._handle, C.c_void_p(frame.data_ptr()), frame.shape[0], frame.shape[1], C.c_void_p(bb.data_ptr()), n,
                 C.c_void_p(kp.data_ptr()), C.c_void_p(idx.data_ptr()), st))
+            if check and self.frame_status() & 1:
+                raise ValueError("a box is empty after padding and clipping to the frame")
         return kp, idx
 
     @staticmethod
@@ -459,7 +469,7 @@ class ViTPose:
         _lib.check(L.vpb_profile_collect(self._handle, ms, cnt))
         return {L.vpb_profile_class_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
 
-    def read_buffer(self, name: str, shape, dtype) -> np.ndarray:
+    def read_buffer(self, name: str, shape, dtype) -> torch.Tensor:
         """Debug: synchronous copy of an internal activation buffer (see vpb_read_buffer)."""
         self._ensure()
         tdtype = torch.bfloat16 if dtype == "bf16" else torch.float32

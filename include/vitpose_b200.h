@@ -8,6 +8,19 @@
  * asynchronous on `stream` unless stated; none of them frees or keeps caller memory.
  * There is no CPU fallback: every entry point fails (non-zero + vpb_last_error()) without an sm_100 GPU.
  *
+ * Concurrency contract.  An engine owns ONE activation workspace, two host-staging slots and its CUDA graphs:
+ *   - calls on one engine must come from one host thread at a time (the handle holds no lock);
+ *   - calls on the same engine from DIFFERENT streams are safe and are executed one after the other: every entry point
+ *     waits (on the device, cudaStreamWaitEvent) for the engine's previous enqueue when the stream changes -- there is no
+ *     overlap between two calls of one engine; use one engine per stream (or per GPU) for concurrency;
+ *   - the synchronous host calls (vpb_infer_host, vpb_infer_frame_host) use staging slot 0, the same buffers as
+ *     vpb_submit_host / vpb_submit_frame_host with slot 0; they are ordered after that slot's last submit and the next
+ *     submit(0) is ordered after them;
+ *   - if `stream` is being captured by the caller, the engine launches its kernels eagerly into that capture (no nested
+ *     graph) and leaves its cross-stream ordering to the caller;
+ *   - engines on different devices may live in one process: each entry point makes its engine's device current for the
+ *     duration of the call and restores the caller's; `stream` must belong to the engine's device.
+ *
  * Each entry point names the reference interface it replaces (paths relative to the reference repo).
  */
 #ifndef VITPOSE_B200_H
@@ -130,6 +143,11 @@ int vpb_decode_frame(const float* d_heatmaps, int32_t n, int32_t k, const int32_
  * pad_bbox is the reference's 10. */
 int vpb_infer_frame(vpb_engine* e, const uint8_t* d_frame, int32_t frame_h, int32_t frame_w, const int32_t* d_bboxes,
                     int32_t n, float* d_kpts, int32_t* d_idx, void* stream);
+/* Status of the device-side frame calls since the last query: bit 0 = some box was empty after padding and clipping
+ * (the reference raises there: ZeroDivisionError in pad_image / cv2.resize, easy_ViTPose/inference.py:259-265; the
+ * device path cannot raise without a sync and decodes such a box from a black crop).  Synchronises the device, clears
+ * the word. */
+int vpb_frame_status(vpb_engine* e, int32_t* h_status);
 /* Same with HOST buffers (H2D of the packed uint8 frame + 16 B per box, D2H of the keypoints, stream sync); empty boxes
  * return VPB_ERR_ARG where the reference raises.  The pipelined form shares its slots and vpb_wait_host with vpb_submit_host. */
 int vpb_infer_frame_host(vpb_engine* e, const uint8_t* h_frame, int32_t frame_h, int32_t frame_w, const int32_t* h_bboxes,
