@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_counts", "shard_range", "gather_keypoints", "infer_sharded", "infer_frame_sharded"]
+__all__ = ["shard_counts", "shard_range", "gather_keypoints", "infer_sharded", "infer_frame_sharded", "ShardPipeline"]
 
 
 def shard_counts(n: int, world: int) -> list[int]:
@@ -88,3 +88,62 @@ def infer_frame_sharded(model, frame: torch.Tensor, bboxes: torch.Tensor, group=
         kp = torch.empty((0, model.num_keypoints, 3), dtype=torch.float32, device=frame.device)
         idx = torch.empty((0, model.num_keypoints), dtype=torch.int32, device=frame.device)
     return gather_keypoints(kp, n, group), gather_keypoints(idx.unsqueeze(-1), n, group).squeeze(-1)
+
+
+class ShardPipeline:
+    """Host crops in -> gathered host keypoints out, `depth` batches in flight per rank (one process per GPU).
+
+    Per submit(): H2D of this rank's pinned crops on a copy stream, the engine on a compute stream, the only exchange of the
+    path -- an all_gather of the [B,K,3] keypoints -- on a third stream, then the D2H of the gathered tensor into pinned
+    memory.  Nothing blocks the host until wait(); the gather and the copies of batch i run under the compute of batch i+1.
+    With world size 1 (or torch.distributed not initialised) the gather is skipped.  Every rank must call submit()/wait()
+    the same number of times with the same batch size (the collective is symmetric)."""
+
+    def __init__(self, model, batch: int, depth: int = 2, group=None):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.model, self.batch, self.depth, self.group = model, batch, depth, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        K = model.num_keypoints
+        self.s_copy, self.s_comp, self.s_comm = (torch.cuda.Stream(dev) for _ in range(3))
+        self.x = [torch.empty((batch, 3, 256, 192), dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.org = [torch.empty((batch, 2), dtype=torch.int32, device=dev) for _ in range(depth)]
+        self.kp = [torch.empty((batch, K, 3), dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.full = [torch.empty((self.world * batch, K, 3), dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.host = [torch.empty((self.world * batch, K, 3), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.ev_h2d = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_comp = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_done = [torch.cuda.Event() for _ in range(depth)]
+        self.used = [False] * depth
+
+    @torch.no_grad()
+    def submit(self, slot: int, h_crops: torch.Tensor, h_org_wh: torch.Tensor) -> None:
+        """h_crops float32 [B,3,256,192] and h_org_wh int32 [B,2] on the host (pinned for real overlap); they must stay
+        unmodified until wait(slot)."""
+        if self.used[slot]:
+            self.s_copy.wait_event(self.ev_comp[slot])       # the slot's device inputs are free once its compute is done
+        with torch.cuda.stream(self.s_copy):
+            self.x[slot].copy_(h_crops, non_blocking=True)
+            self.org[slot].copy_(h_org_wh, non_blocking=True)
+            self.ev_h2d[slot].record(self.s_copy)
+        with torch.cuda.stream(self.s_comp):
+            self.s_comp.wait_event(self.ev_h2d[slot])
+            if self.used[slot]:
+                self.s_comp.wait_event(self.ev_done[slot])   # kp[slot] was read by the previous gather
+            kp, _ = self.model.infer_crops(self.x[slot], self.org[slot])
+            self.kp[slot].copy_(kp)
+            self.ev_comp[slot].record(self.s_comp)
+        with torch.cuda.stream(self.s_comm):
+            self.s_comm.wait_event(self.ev_comp[slot])
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.full[slot], self.kp[slot], group=self.group)
+                self.host[slot].copy_(self.full[slot], non_blocking=True)
+            else:
+                self.host[slot].copy_(self.kp[slot], non_blocking=True)
+            self.ev_done[slot].record(self.s_comm)
+        self.used[slot] = True
+
+    def wait(self, slot: int) -> torch.Tensor:
+        """Blocks until slot's gathered keypoints [world*B,K,3] are in pinned host memory; the tensor is reused by the
+        slot's next submit()."""
+        self.ev_done[slot].synchronize()
+        return self.host[slot]

@@ -1,4 +1,4 @@
-"""Import the UNMODIFIED reference modules from /root/reference  --  TEST INFRASTRUCTURE ONLY.
+"""Import the UNMODIFIED reference modules from /root/reference (or baseline/_ref)  --  TEST INFRASTRUCTURE ONLY.
 
 Used by oracle/make_golden.py (and by tests that are skipped when the reference tree is
 absent, i.e. on the GPU box) to pin oracle/vitpose_oracle.py against the reference's own
@@ -15,7 +15,21 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("EASY_VITPOSE_REF", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    """Where the UNMODIFIED reference package lives: $EASY_VITPOSE_REF, the read-only mount of the build container, or the
+    copy `pip install --target baseline/_ref /root/reference` leaves in the repo (git-ignored; it travels to the GPU box,
+    which has no /root/reference)."""
+    cands = [os.environ.get("EASY_VITPOSE_REF"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "easy_ViTPose", "vit_models")):
+            return c
+    return cands[1]
+
+
+REF_ROOT = _find_root()
 REF_PKG = os.path.join(REF_ROOT, "easy_ViTPose")
 
 

@@ -125,6 +125,31 @@ def _add_bump_pathway(sd: dict, rs, D: int, F: int, K: int) -> None:
         sd["keypoint_head.final_layer.weight"][k, c, 0, 0] += np.float32(0.03)
 
 
+def add_outliers(sd: dict, seed: int, stream_channels: int = 4, stream_value: float = 100.0, gelu_value: float = 13.0) -> dict:
+    """Real-ViT-like outliers on top of make_state_dict (in place, returns sd):
+      * `stream_channels` residual-stream channels sit at about +-`stream_value` on EVERY token (pos_embed), the "massive
+        activation" channels of trained ViTs: LayerNorm statistics are then dominated by a handful of channels and the bf16
+        operand of the qkv / fc1 GEMMs carries values two orders of magnitude apart;
+      * eight fc1 biases per block at +-`gelu_value` and +-2*`gelu_value`: pre-GELU activations beyond the range the
+        engine's tanh-form GELU was fitted on (the round-1 advisor finding: the unclamped fit flipped sign at |x| ~ 11).
+    Seeded separately from the weights so that fixtures made before this existed do not change."""
+    rs = np.random.RandomState(seed)
+    D = sd["backbone.pos_embed"].shape[-1]
+    depth = sum(1 for k in sd if k.endswith(".norm1.weight"))
+    ch = rs.choice(np.arange(300, D), size=stream_channels, replace=False)      # away from the bump pathway's channels (< 256)
+    # the outliers raise every row's standard deviation from ~1 to ~stream_value * sqrt(channels / D): lift the bump
+    # pathway's pos_embed entries (the only ones above 5) by the same factor so the heatmaps keep one clear peak per keypoint
+    pe = sd["backbone.pos_embed"]
+    pe[np.abs(pe) > 5.0] *= np.float32(max(1.0, stream_value * math.sqrt(stream_channels / D)))
+    signs = np.where(np.arange(stream_channels) % 2 == 0, 1.0, -1.0) * rs.uniform(0.8, 1.2, size=stream_channels)
+    sd["backbone.pos_embed"][0, 1:, ch] += (signs * stream_value).astype(np.float32)[:, None]
+    for i in range(depth):
+        b = sd[f"backbone.blocks.{i}.mlp.fc1.bias"]
+        idx = rs.choice(b.shape[0], size=8, replace=False)
+        b[idx] = np.array([1, -1, 2, -2, 1, -1, 2, -2], np.float32) * np.float32(gelu_value)
+    return sd
+
+
 def make_crops(batch: int, seed: int) -> np.ndarray:
     """Synthetic normalised crops ~N(0,1), the distribution of (img/255-MEAN)/STD
     (easy_ViTPose/inference.py:314-318)."""

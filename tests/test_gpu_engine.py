@@ -11,8 +11,9 @@ from oracle import vitpose_oracle as O
 pytestmark = pytest.mark.gpu
 
 # heatmap L_inf tolerance as a fraction of the reference heatmap range (bf16 operands, fp32 accumulate,
-# fp32 residual stream / LayerNorm / softmax): SURVEY.md 9.6 measured torch-bf16 vs fp32 at 0.5 % of range.
-HEATMAP_TOL = 0.02
+# fp32 residual stream / LayerNorm / softmax): SURVEY.md 9.6 measured torch-bf16 vs fp32 at 0.5 % of range; the engine
+# measured 0.37-0.61 % in round 1, so 1 % leaves a x1.6-2.7 margin (printed per case) and a 2x regression fails.
+HEATMAP_TOL = 0.01
 KPT_MEAN_PX_TOL = 0.5          # north_star: <= 0.5 px mean keypoint deviation
 
 
@@ -34,7 +35,7 @@ def test_forward_heatmaps_vs_reference(golden_dir, name):
     ref = g["heatmaps"]
     rng = float(ref.max() - ref.min())
     linf = float(np.abs(hm - ref).max())
-    print(name, "heatmap Linf", linf, "range", rng, "rel", linf / rng)
+    print(name, f"heatmap Linf {linf:.5f} = {linf / rng:.3%} of range {rng:.4f} (tol {HEATMAP_TOL:.0%}, margin x{HEATMAP_TOL * rng / linf:.2f})")
     assert linf < HEATMAP_TOL * rng
     # integer argmax of the engine's OWN heatmaps must equal np.argmax of them, bit for bit
     kp, idx, hm2 = m.infer_crops(torch.from_numpy(x).cuda(), torch.from_numpy(g["org_wh"]), return_heatmaps=True)

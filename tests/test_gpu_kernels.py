@@ -108,6 +108,30 @@ def test_gemm_gelu():
     assert _rel(out.float(), ref) < 1e-2
 
 
+def test_gemm_gelu_wide_range():
+    """Pre-activations from -40 to +40 (bias sweep; the product term is small): the fc1 epilogue's GELU must follow the
+    exact erf form everywhere, in particular beyond |x| ~ 11 where the unclamped fit flipped sign."""
+    from gpu_util import EPI_BF16_GELU, gemm
+    torch.manual_seed(5)
+    M, N, K = 256, 1024, 64
+    a = (torch.randn(M, K, device=_dev()) * 0.1).bfloat16()
+    w = (torch.randn(N, K, device=_dev()) * 0.05).bfloat16()
+    bias = torch.linspace(-40.0, 40.0, N, device=_dev())
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device=_dev())
+    gemm(a, w, bias, out, EPI_BF16_GELU)
+    pre = a.float() @ w.float().T + bias
+    ref = torch.nn.functional.gelu(pre)                       # exact erf GELU (vit.py:127,132)
+    err = (out.float() - ref).abs()
+    tol = 2.0 ** -8 * ref.abs() + 4e-5                        # bf16 output rounding + the fit's 2.6e-5 + tanh.approx
+    worst = float((err / tol).max())
+    print("gelu wide range: max err / tol", worst, "| max abs err", float(err.max()), "at pre =", float(pre.flatten()[err.argmax()]))
+    assert worst < 1.0
+    big = pre.abs() > 11
+    pos, neg = big & (pre > 0), big & (pre < 0)
+    assert float(((out.float() - pre).abs() / pre.abs())[pos].max()) <= 2.0 ** -8                 # GELU(x) = x there (bf16 step)
+    assert float(out[neg].float().abs().max()) < 1e-5                                             # and 0 on the other side
+
+
 def test_gemm_reduce_add_into_fp32_stream():
     from gpu_util import EPI_F32_ADD, gemm
     torch.manual_seed(2)

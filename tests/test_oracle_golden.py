@@ -77,3 +77,35 @@ def test_torch_restatement_matches_reference(golden_dir, name):
     with torch.no_grad():
         hm = T.forward(torch.from_numpy(O.make_crops(B, xseed)), sd, depth, heads).numpy()
     assert np.abs(hm - g["heatmaps"]).max() < 1e-5 * np.abs(g["heatmaps"]).max()
+
+
+def test_outlier_fixture_pins_the_oracle_too(golden_dir):
+    """Real-ViT-like outliers (residual channels at +-100, pre-GELU +-13 / +-26; oracle.add_outliers): the oracle follows the
+    reference there as well, and the fixture really contains what it claims."""
+    g = _load(golden_dir, "outlier_b_coco")
+    D, depth, heads, K, B, wseed, xseed, oseed = (int(v) for v in g["meta"])
+    sd = O.add_outliers(O.make_state_dict(D, depth, K, wseed, peaky=0.1, bumps=True), oseed)
+    tok_outliers = np.abs(sd["backbone.pos_embed"][0, 1:]).max(0)
+    assert int((tok_outliers > 70).sum()) >= 4                    # four stream channels beyond +-70 on every token
+    assert float(np.abs(sd["backbone.blocks.3.mlp.fc1.bias"]).max()) >= 25.0
+    hm = O.forward_heatmaps(O.make_crops(B, xseed), sd, depth, heads)
+    ref = g["heatmaps"]
+    assert np.abs(hm - ref).max() < 5e-4 * (ref.max() - ref.min())
+    assert np.array_equal(hm.reshape(B, K, -1).argmax(-1), g["idx"])
+
+
+@pytest.mark.parametrize("name", ["batch_b_coco_64", "batch_h_wholebody_32", "batch_l_coco_25_64"])
+def test_batch_fixtures_are_self_consistent(golden_dir, name):
+    """The batch-size fixtures store reference keypoints for every crop but heatmaps only for a sample: the oracle's decode of
+    the sampled reference maps must reproduce the stored keypoints of those crops / keypoints (scores exactly)."""
+    g = _load(golden_dir, name)
+    hm = g["sample_hm"]                                              # [4 crops, 8 keypoints, 64, 48]
+    org = g["org_wh"][g["crop_ids"]]
+    kp, idx = O.decode_maps(hm, org, wrap="crop")
+    ref = g["kpts"][g["crop_ids"]][:, g["kp_ids"]]
+    assert np.array_equal(idx, g["idx"][g["crop_ids"]][:, g["kp_ids"]])
+    assert np.array_equal(kp[..., 2], ref[..., 2])
+    # the reference decodes a crop's K maps in one call; a sentinel map (max <= 0) reads its neighbour map there, so compare
+    # coordinates only where the map has a real peak
+    ok = ref[..., 2] > 0.05
+    assert np.abs(kp[..., :2] - ref[..., :2])[ok].max() < 2e-3 * max(1.0, float(org.max()) / 48.0)
