@@ -38,7 +38,18 @@ def _check_keypoints(name, g, kp, idx, hm_engine):
           f"(tol mean {KPT_MEAN_PX_TOL}); argmax identical to the fp32 reference on {float((idx == g['idx'])[vis].mean()):.4f} of visible")
     assert vis.sum() >= 0.7 * vis.size
     assert dev[vis].mean() < KPT_MEAN_PX_TOL
-    assert cell[vis].max() <= 1                                      # a peak between two cells may flip to its neighbour
+    # a peak lying between two cells may flip to its neighbour; a flip to a FAR cell is only legitimate for a map with two
+    # near-equal maxima (the fp32 reference picks one, bf16 rounding the other): the engine's own value at the reference's
+    # arg-max must then be within twice the heatmap tolerance of the engine's maximum
+    far = vis & (cell > 1)
+    rng = float(g["range"][1] - g["range"][0])
+    flat = hm_engine.reshape(B, K, -1)
+    at_ref = np.take_along_axis(flat, g["idx"][..., None].astype(np.int64), -1)[..., 0]
+    gap = flat.max(-1) - at_ref
+    print(name, f"far arg-max flips: {int(far.sum())} of {int(vis.sum())} visible maps; largest gap between the engine's maximum and its value "
+          f"at the reference arg-max {float(gap[far].max()) / rng if far.any() else 0.0:.3%} of range")
+    assert far.sum() <= 0.002 * vis.sum() + 1
+    assert np.all(gap[far] <= 2 * HEATMAP_TOL * rng)
     # bit-exact integer work: the engine's argmax is np.argmax of the engine's own heatmaps
     assert np.array_equal(idx, hm_engine.reshape(B, K, -1).argmax(-1).astype(np.int32))
 

@@ -27,7 +27,11 @@ for heads, hd, B in ((12, 64, 64), (16, 80, 32), (12, 32, 64)):
     L.vpb_debug_gemm(0, C.c_void_p(dbg.data_ptr()))
     attention(qkv, B, heads, hd)
     L.vpb_debug_gemm(0, None)
-    m = dbg.cpu().reshape(n, 8).double().mean(0)
-    steps = 2 * B * heads / n
-    print(f"hd={hd} B={B} heads={heads}: {us:.1f} us/launch; per CTA: lifetime {m[0]:.0f} cyc, {steps:.1f} tile steps -> {m[0]/steps:.0f} cyc/step")
-    print(f"   softmax warp 0: wait S {m[1]/steps:.0f}  busy {m[2]/steps:.0f}   | epilogue warp 4: wait {m[3]/steps:.0f}  busy {m[4]/steps:.0f}  (cycles per tile step)")
+    d = dbg.cpu().reshape(n, 8).double()
+    m = d.mean(0)
+    steps = m[7]
+    flops = 4 * B * heads * 192 * 192 * hd
+    print(f"hd={hd} B={B} heads={heads}: {us:.1f} us/launch = {flops / us / 1e6:.0f} TFLOP/s; per CTA: lifetime {m[0]:.0f} cyc (max {d[:,0].max():.0f}), "
+          f"{steps:.2f} tile steps (max {d[:,7].max():.0f}) -> {m[0]/steps:.0f} cyc/step")
+    print(f"   softmax group A warp 0 (per step of the CTA): wait S {m[1]/steps:.0f} busy {m[2]/steps:.0f} | group B warp 4: wait S {m[5]/steps:.0f} busy {m[6]/steps:.0f} "
+          f"| epilogue warp 8: wait {m[3]/steps:.0f} busy {m[4]/steps:.0f}")
