@@ -48,6 +48,8 @@ def flops_per_crop(D: int, depth: int, heads: int, K: int) -> dict:
         "gemm_final_conv": 2 * 3072 * 256 * K,
     }
     f["total"] = sum(f.values())
+    # the chained launches (chain.cuh) carry the patch-embed, qkv, proj, fc1 and fc2 GEMMs of the step
+    f["gemm_chain"] = f["gemm_patch_embed"] + f["gemm_qkv"] + f["gemm_proj"] + f["gemm_fc1_gelu"] + f["gemm_fc2"]
     return f
 
 
@@ -531,6 +533,20 @@ def run_gpu(args) -> None:
     ms_prof_total = pv0.elapsed_time(pv1)
     clocks = sampler.stop() if rank == 0 else None
     prof = model.profile_collect()
+    prof_unchained = None
+    if prof.get("gemm_chain", (0.0, 0))[1] > 0:
+        # the chained launches hide the per-GEMM split: one more profiled pass with one kernel per GEMM / LayerNorm
+        # (set_option("chain", 0)) for the per-class table and the attention-GEMM figure the north star asks for
+        model.set_option("chain", 0)
+        for i in range(3):
+            step(i)
+        barrier()
+        model.profile_collect()
+        for i in range(args.steps):
+            step(i)
+        barrier()
+        prof_unchained = model.profile_collect()
+        model.set_option("chain", 1)
     model.set_option("profile", 0)
 
     # ---- end to end with pinned HOST buffers, host->device and device->host copies inside the timed region.
@@ -637,7 +653,13 @@ def run_gpu(args) -> None:
         except Exception:
             traffic = None
         whole = fl["total"] * job_crops_per_step / world * args.steps / (ms_total / 1e3) / 1e12
-        att_ms = prof["gemm_qkv"][0] + prof["attention"][0] + prof["gemm_proj"][0]
+        pu = prof_unchained or prof
+        att_ms = pu["gemm_qkv"][0] + pu["attention"][0] + pu["gemm_proj"][0]
+        kernels_unchained = None
+        if prof_unchained is not None:
+            kernels_unchained = {name: {"ms_per_step": ms / args.steps, "launches_per_step": n / args.steps,
+                                        **({"tflops": fl[name] * crops_per_step * args.steps / (ms / 1e3) / 1e12} if name in fl and ms > 0 else {})}
+                                 for name, (ms, n) in prof_unchained.items() if n}
         roofline = {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": kernels[dom]["tflops"] / peak_tf,
                     "peak_source": f"{peak_src} " + ("bf16_tflops_sustained (sw_power_cap active in the timed region)" if peak_tf == peak_sust and capped
@@ -670,6 +692,7 @@ def run_gpu(args) -> None:
             "parity_check": parity,
             "profiled_pass_ms_per_step": ms_prof_total / args.steps,
             "kernels": kernels,
+            "kernels_unchained": kernels_unchained,
             "cpu_baseline": None if cpu_val is None else {
                 "value": cpu_val, "unit": "crops/s", "cores": cores, "kind": cpu_kind,
                 "sample": f"{args.cpu_sample} crops x 3 steps, " + ("UNMODIFIED reference ViTPose(cfg).forward fp32 + keypoints_from_heatmaps per crop"

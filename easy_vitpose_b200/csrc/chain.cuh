@@ -1,0 +1,419 @@
+// One persistent launch for a CHAIN of dependent GEMMs of a transformer block, with the LayerNorms between them:
+//
+//     [proj (+= x)] -> LN -> [fc1 + GELU] -> [fc2 (+= x)] -> LN -> [qkv of the next block]        (backbone/vit.py:202-205,164-180)
+//
+// Round 1 ran these as 4 GEMM launches + 2 LayerNorm launches.  Each tensor-core launch paid ~2 us of head (barrier init,
+// TMEM alloc, first TMA round trip) and ~3 us of tail (last tile's epilogue, idle SMs in the last wave) that programmatic
+// dependent launch cannot hide (a 227 KB CTA leaves no room for the next grid), and every LayerNorm was a separate pass of
+// the fp32 stream through all SMs with nothing else running.  Here the tiles of all phases form ONE list, handed out
+// statically (tile g -> cluster g mod #clusters, phase-major, n fastest), and what used to be a kernel boundary is a counter:
+//
+//   * every 128-row block `mt` of an activation has a counter that the producing epilogue warps bump once their TMA stores /
+//     reduce-adds of a tile have COMPLETED (cp.async.bulk.wait_group 0, cross-proxy fence, release);
+//   * the TMA-producer warp of a consuming tile spins (acquire) on the counter of its A rows before its first load;
+//   * LayerNorm runs on four dedicated warps of every CTA, concurrently with that CTA's tensor-core tiles: 16-row jobs handed
+//     out statically (job j -> CTA j mod grid), each waiting for its row block's residual adds to complete; they read the fp32
+//     stream out of L2 (ld.global.cg) and write the bf16 operand rows, then bump the "normalised rows ready" counter.
+//
+// Dependencies only point to tiles that come earlier in the list (and LN jobs only to tiles), all CTAs are resident (one per
+// SM, grid <= #SMs), every role walks its own list in order: the smallest unfinished tile can always run, so the waits cannot
+// deadlock; a counter that never arrives traps (VPB_HANG_TRAP_SPINS) instead of hanging the GPU.
+// The arithmetic of every phase is that of gemm.cuh's kernels and of layernorm_f32_to_bf16, in the same order: results are
+// bit-identical to the unchained path (tests/test_gpu_engine.py::test_chain_is_bit_identical).
+//
+//   warps 0..7   epilogue (tcgen05.ld -> bias / GELU -> swizzled smem staging -> TMA store or TMA reduce-add)
+//   warp  8      TMEM allocator            warp 10  TMA producer (+ dependency waits)      warp 11  tcgen05.mma issuer (leader CTA)
+//   warps 12..15 LayerNorm jobs
+#pragma once
+#include "gemm.cuh"
+
+namespace vpb {
+
+constexpr int CHAIN_MAX_PHASES = 4;
+constexpr int CHAIN_MAX_LN = 2;
+constexpr int CHAIN_THREADS = 512;
+constexpr int CHAIN_LN_WARPS = 4;
+constexpr int CHAIN_LN_JOB_ROWS = 16;      // rows per LayerNorm job: 4 per warp
+
+struct ChainPhase {
+  int N, K;                 // W is [N,K]; N % BN == 0, K % 64 == 0
+  int epi;                  // EPI_BF16 | EPI_BF16_GELU | EPI_F32_ADD
+  const float* bias;        // [N]
+  const int* a_ready;       // per 128-row block: A rows are complete once a_ready[mt] >= target (nullptr: produced by an earlier launch)
+  int a_target;             // > 0: that many arrivals (GEMM-produced A: column tiles * 8 epilogue warps);
+                            // 0: LayerNorm-produced A: CHAIN_LN_WARPS arrivals per 16-row job of the block
+  int* out_done;            // per 128-row block, += 1 per epilogue warp per tile once its stores have completed (nullptr: nobody waits)
+};
+struct ChainLn {
+  const int* src_done;      // out_done of the residual phase that completes the fp32 rows
+  int src_target;           // column tiles of that phase * 8
+  const float* gamma;       // [D]
+  const float* beta;        // [D]
+  int* ready;               // per 128-row block, += 1 per warp per finished job
+};
+struct ChainParams {
+  int M;                    // rows (tokens) of every phase
+  int D;                    // LayerNorm width = row pitch of x / xn
+  int num_phases, num_ln;
+  const float* x;           // fp32 stream [M, D]
+  __nv_bfloat16* xn;        // LayerNorm output [M, D]
+  float eps;
+  ChainPhase ph[CHAIN_MAX_PHASES];
+  ChainLn ln[CHAIN_MAX_LN];
+};
+struct alignas(64) ChainMaps {
+  CUtensorMap a[CHAIN_MAX_PHASES], w[CHAIN_MAX_PHASES], out[CHAIN_MAX_PHASES];
+};
+
+template <int BN>
+struct ChainCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_SLICE = BN * GEMM_BK * 2 / GEMM_CL;
+  static constexpr int STAGE_BYTES = A_BYTES + B_SLICE;
+  static constexpr int STAGING = GEMM_EPI_WARPS * GEMM_STAGE_TILE;
+  static constexpr int STAGES_RAW = (227 * 1024 - 2048 - STAGING) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int HALF = BN / 2;
+  static_assert(BN == 256 || BN == 128, "chain tiles");
+};
+
+// ---------------------------------------------------------------- counters in global memory
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// generic proxy <-> async proxy (TMA) ordering for global memory
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Whole warp spins (one coalesced load per probe) until *p >= target.
+__device__ __forceinline__ void wait_counter(const int* p, int target) {
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(p) < target) {
+    __nanosleep(40);
+    if (++spins > (VPB_HANG_TRAP_SPINS >> 3)) __trap();
+  }
+}
+__host__ __device__ __forceinline__ int chain_ln_jobs_in_block(int M, int mt) {
+  const int rows = M - mt * GEMM_BM < GEMM_BM ? M - mt * GEMM_BM : GEMM_BM;
+  return (rows + CHAIN_LN_JOB_ROWS - 1) / CHAIN_LN_JOB_ROWS;
+}
+
+// ---------------------------------------------------------------- LayerNorm rows (same arithmetic, same order as
+// layernorm_f32_to_bf16 in pointwise.cuh: fp32 mean, centred biased variance, rsqrtf; backbone/vit.py:190,198,304)
+template <int V>
+struct LnRow {
+  float4 v[V];
+  float rstd;
+  __device__ __forceinline__ void load(const float* __restrict__ xrow, int lane) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = __ldcg(reinterpret_cast<const float4*>(xrow) + i * 32 + lane);    // L2: written by other SMs
+  }
+  // centres v in place and leaves 1/sqrt(var + eps) in rstd
+  __device__ __forceinline__ void stats(float eps) {
+    constexpr int D = 128 * V;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    rstd = rsqrtf(q * (1.0f / D) + eps);
+  }
+  __device__ __forceinline__ uint2 out(int i, const float4& g, const float4& b) const {
+    uint2 o;
+    o.x = pack_bf16(v[i].x * rstd * g.x + b.x, v[i].y * rstd * g.y + b.y);
+    o.y = pack_bf16(v[i].z * rstd * g.z + b.z, v[i].w * rstd * g.w + b.w);
+    return o;
+  }
+};
+// rows [r0, r1) of one warp's share of a job; two rows in flight while they fit in registers (D <= 768), else one.
+// gamma / beta are fetched once per 128-column slice and shared by the rows in flight.
+template <int V>
+__device__ __forceinline__ void chain_ln_rows(const ChainParams& p, const ChainLn& ln, int r0, int r1, int lane) {
+  constexpr int D = 128 * V;
+  constexpr int R = V <= 6 ? 2 : 1;
+  for (int r = r0; r < r1; r += R) {
+    LnRow<V> row[R];
+    const bool two = R == 2 && r + 1 < r1;
+    row[0].load(p.x + static_cast<size_t>(r) * D, lane);
+    if constexpr (R == 2) { if (two) row[1].load(p.x + static_cast<size_t>(r + 1) * D, lane); }
+    row[0].stats(p.eps);
+    if constexpr (R == 2) { if (two) row[1].stats(p.eps); }
+    uint2* y0 = reinterpret_cast<uint2*>(p.xn + static_cast<size_t>(r) * D);
+    uint2* y1 = reinterpret_cast<uint2*>(p.xn + static_cast<size_t>(r + 1) * D);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(ln.gamma) + i * 32 + lane);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ln.beta) + i * 32 + lane);
+      y0[i * 32 + lane] = row[0].out(i, g, b);
+      if constexpr (R == 2) { if (two) y1[i * 32 + lane] = row[1].out(i, g, b); }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- one tile's epilogue (the TMA epilogues of gemm.cuh)
+template <int BN, int EPI>
+__device__ __forceinline__ void chain_epilogue_tile(uint32_t t_row, int half, int n0, int row0, const float* __restrict__ bias,
+                                                    uint8_t* stile, int lane, const CUtensorMap* tmap_out) {
+  constexpr int HALF = BN / 2;
+  constexpr int COLS = (EPI == EPI_F32_ADD) ? 32 : 64;       // one 128-byte staging row per round
+  const int sw = lane & 7;
+#pragma unroll 1
+  for (int c = 0; c < HALF; c += COLS) {
+    const int col = half * HALF + c;
+    const int n = n0 + col;
+    if (elect_one()) tma_store_wait_read<0>();                // previous store has finished reading the staging tile
+    __syncwarp();
+#pragma unroll
+    for (int sub = 0; sub < COLS; sub += 32) {
+      uint32_t r[32];
+      tmem_ld32(t_row + col + sub, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + sub + j));
+        v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+        v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+      }
+      if constexpr (EPI == EPI_BF16_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+      }
+      uint8_t* srow = stile + lane * 128;                     // staging row = lane, 16-byte chunk index XOR (lane % 8): SWIZZLE_128B
+      if constexpr (EPI == EPI_F32_ADD) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(srow + ((q ^ sw) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 w;
+          w.x = pack_bf16(v[8 * q], v[8 * q + 1]); w.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+          w.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); w.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+          *reinterpret_cast<uint4*>(srow + ((((sub >> 3) + q) ^ sw) << 4)) = w;
+        }
+      }
+    }
+    fence_proxy_async_smem();                                 // staging writes -> visible to the TMA engine
+    __syncwarp();
+    if (elect_one()) {
+      if constexpr (EPI == EPI_F32_ADD) tma_reduce_add_2d(tmap_out, stile, n, row0);
+      else tma_store_2d(tmap_out, stile, n, row0);            // rows past M are clipped by the tensor map
+      tma_store_commit();
+    }
+  }
+}
+
+template <int BN>
+__global__ void __cluster_dims__(GEMM_CL, 1, 1) __launch_bounds__(CHAIN_THREADS, 1)
+gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
+  using Cfg = ChainCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* acc_full = empty_bar + Cfg::STAGES;     // [2]
+  uint64_t* acc_empty = acc_full + 2;               // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int cta_rank = static_cast<int>(cluster_ctarank());
+  const int cluster = static_cast<int>(cluster_id_x());
+  const int num_clusters = static_cast<int>(cluster_count_x());
+  const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int num_mp = (num_m + GEMM_CL - 1) / GEMM_CL;
+  // tile list: phase-major, inside a phase tile = mp * num_n + nb (n fastest)
+  int tile_end[CHAIN_MAX_PHASES];
+  {
+    int acc = 0;
+#pragma unroll
+    for (int i = 0; i < CHAIN_MAX_PHASES; ++i) {
+      if (i < p.num_phases) acc += num_mp * (p.ph[i].N / BN);
+      tile_end[i] = acc;
+    }
+  }
+  const int total_tiles = tile_end[CHAIN_MAX_PHASES - 1];
+  auto locate = [&](int g, int& ph, int& mp, int& nb) {
+    ph = 0;
+    int base = 0;
+#pragma unroll
+    for (int i = 0; i < CHAIN_MAX_PHASES - 1; ++i)
+      if (g >= tile_end[i]) { ph = i + 1; base = tile_end[i]; }   // static indices only: tile_end stays in registers
+    const int local = g - base;
+    const int nn = p.ph[ph].N / BN;
+    mp = local / nn;
+    nb = local % nn;
+  };
+  constexpr uint16_t kAllCtas = (1u << GEMM_CL) - 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.num_phases; ++i) {
+      tma_prefetch_desc(&maps.a[i]);
+      tma_prefetch_desc(&maps.w[i]);
+      tma_prefetch_desc(&maps.out[i]);
+    }
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], GEMM_CL * GEMM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before_sync();
+  cluster_sync_all();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  pdl_launch_dependents();
+  pdl_wait();                                       // the previous kernel's outputs (first phase's A operand, x) are complete
+
+  if (warp == 10) {
+    // ------------------------------------------------------------ TMA producer (+ the waits that replace kernel boundaries)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int g = cluster; g < total_tiles; g += num_clusters) {
+      int ph, mp, nb;
+      locate(g, ph, mp, nb);
+      const ChainPhase& P = p.ph[ph];
+      const int mt = mp * GEMM_CL + cta_rank;
+      const int m0 = mt * GEMM_BM, n0 = nb * BN;
+      const int num_kb = P.K / GEMM_BK;
+      if (P.a_ready != nullptr && mt < num_m) {
+        wait_counter(P.a_ready + mt, P.a_target > 0 ? P.a_target : CHAIN_LN_WARPS * chain_ln_jobs_in_block(p.M, mt));
+        fence_proxy_async_all();                    // the rows were written through the generic / async proxy of other SMs
+      }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
+        if (elect_one()) {
+          if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], GEMM_CL * Cfg::STAGE_BYTES);
+          tma_load_2d_pair(sa, &maps.a[ph], &full_bar[stage], kb * GEMM_BK, m0);
+          tma_load_2d_pair(sa + Cfg::A_BYTES, &maps.w[ph], &full_bar[stage], kb * GEMM_BK, n0 + cta_rank * (BN / GEMM_CL));
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 11 && cta_rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA of the pair only)
+    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_CL * GEMM_BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int g = cluster; g < total_tiles; g += num_clusters, ++it) {
+      int ph, mp, nb;
+      locate(g, ph, mp, nb);
+      const int num_kb = p.ph[ph].K / GEMM_BK;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(ring + stage * Cfg::STAGE_BYTES);
+        const uint64_t adesc = umma_desc_sw128(sa, 1024);
+        const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES, 1024);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_pair(&empty_bar[stage], kAllCtas);
+          if (kb == num_kb - 1) umma_commit_pair(&acc_full[acc], kAllCtas);
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp < GEMM_EPI_WARPS) {
+    // ------------------------------------------------------------ epilogue
+    const int quarter = warp & 3;
+    const int half = warp >> 2;
+    uint8_t* stile = staging + warp * GEMM_STAGE_TILE;
+    int it = 0;
+    for (int g = cluster; g < total_tiles; g += num_clusters, ++it) {
+      int ph, mp, nb;
+      locate(g, ph, mp, nb);
+      const ChainPhase& P = p.ph[ph];
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int mt = mp * GEMM_CL + cta_rank;
+      const int row0 = mt * GEMM_BM + quarter * 32;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE;
+      if (P.epi == EPI_F32_ADD) chain_epilogue_tile<BN, EPI_F32_ADD>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
+      else if (P.epi == EPI_BF16_GELU) chain_epilogue_tile<BN, EPI_BF16_GELU>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
+      else chain_epilogue_tile<BN, EPI_BF16>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);   // TMEM is free for the MMA thread; the stores may still be in flight
+      if (P.out_done != nullptr && mt < num_m) {
+        // publish the tile: this warp's stores / reduce-adds have been PERFORMED (not just read out of smem), then a
+        // cross-proxy fence and a gpu-scope release on the row block's counter
+        if (elect_one()) {
+          tma_store_wait_all<0>();
+          fence_proxy_async_all();
+          __threadfence();
+          red_release_gpu_add(P.out_done + mt, 1);
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) tma_store_wait_all<0>();
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------ LayerNorm jobs
+    const int lw = warp - 12;
+    const int jobs = (p.M + CHAIN_LN_JOB_ROWS - 1) / CHAIN_LN_JOB_ROWS;
+    constexpr int ROWS_PER_WARP = CHAIN_LN_JOB_ROWS / CHAIN_LN_WARPS;
+    for (int s = 0; s < p.num_ln; ++s) {
+      const ChainLn& L = p.ln[s];
+      for (int job = blockIdx.x; job < jobs; job += gridDim.x) {
+        const int mt = (job * CHAIN_LN_JOB_ROWS) / GEMM_BM;
+        wait_counter(L.src_done + mt, L.src_target);
+        const int r0 = job * CHAIN_LN_JOB_ROWS + lw * ROWS_PER_WARP;
+        const int r1 = min(r0 + ROWS_PER_WARP, p.M);
+        switch (p.D) {
+          case 384: chain_ln_rows<3>(p, L, r0, r1, lane); break;
+          case 768: chain_ln_rows<6>(p, L, r0, r1, lane); break;
+          case 1024: chain_ln_rows<8>(p, L, r0, r1, lane); break;
+          default: chain_ln_rows<10>(p, L, r0, r1, lane); break;     // 1280
+        }
+        __syncwarp();                                                  // every lane's stores precede lane 0's release
+        if (lane == 0) {
+          fence_proxy_async_all();                                     // consumed by TMA loads (async proxy) of other SMs
+          __threadfence();
+          red_release_gpu_add(L.ready + mt, 1);
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  cluster_sync_all();
+  if (warp == 8) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+}
+
+}  // namespace vpb

@@ -17,6 +17,7 @@
 
 #include "../../include/vitpose_b200.h"
 #include "attention.cuh"
+#include "chain.cuh"
 #include "decode.cuh"
 #include "gemm.cuh"
 #include "pointwise.cuh"
@@ -188,6 +189,49 @@ static int device_check(int device) {
   return VPB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ chained GEMM launch
+template <int BN>
+static int chain_launch_t(const ChainMaps& maps, const ChainParams& p, cudaStream_t st) {
+  using Cfg = ChainCfg<BN>;
+  auto kern = gemm_chain_tcgen05<BN>;
+  DeviceState* ds = cur_dev();
+  if (ds->sms == 0) return fail(VPB_ERR_STATE, "chain: device not initialised (device_check)");
+  constexpr unsigned slot = BN == 256 ? (1u << 30) : (1u << 31);
+  if (!(ds->gemm_attr & slot)) {
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    ds->gemm_attr |= slot;
+  }
+  const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM, num_mp = (num_m + GEMM_CL - 1) / GEMM_CL;
+  int tiles = 0;
+  for (int i = 0; i < p.num_phases; ++i) {
+    if (p.ph[i].N % BN != 0 || p.ph[i].K % GEMM_BK != 0 || p.ph[i].bias == nullptr)
+      return fail(VPB_ERR_ARG, "chain: phase %d N=%d K=%d does not tile by %d x 64", i, p.ph[i].N, p.ph[i].K, BN);
+    tiles += num_mp * (p.ph[i].N / BN);
+  }
+  // every cluster of the grid must be resident at once: the in-kernel waits rely on it.  Ask the runtime how many 2-CTA
+  // clusters of this kernel the device can hold (74 on a whole B200) instead of assuming #SMs / 2.
+  static int max_active[kMaxDevices] = {0};
+  int dev_id = 0;
+  CU_TRY(cudaGetDevice(&dev_id));
+  if (max_active[dev_id] == 0) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(ds->sms); cfg.blockDim = dim3(CHAIN_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = ds->sms / GEMM_CL; }
+    max_active[dev_id] = n < ds->sms / GEMM_CL ? n : ds->sms / GEMM_CL;
+  }
+  const int max_clusters = max_active[dev_id];
+  const int grid = GEMM_CL * (tiles < max_clusters ? tiles : max_clusters);
+  CU_TRY(launch_k(kern, dim3(grid), dim3(CHAIN_THREADS), Cfg::SMEM_BYTES, st, maps, p));
+  return VPB_OK;
+}
+static int chain_launch(int bn, const ChainMaps& maps, const ChainParams& p, cudaStream_t st) {
+  if (p.num_phases < 1 || p.num_phases > CHAIN_MAX_PHASES || p.num_ln < 0 || p.num_ln > CHAIN_MAX_LN) return fail(VPB_ERR_ARG, "chain: bad phase count");
+  if (p.D != 384 && p.D != 768 && p.D != 1024 && p.D != 1280) return fail(VPB_ERR_ARG, "chain: LayerNorm width %d not instantiated", p.D);
+  return bn == 256 ? chain_launch_t<256>(maps, p, st) : chain_launch_t<128>(maps, p, st);
+}
+
 // ------------------------------------------------------------------------------------------------ attention dispatch
 // qkv bf16 [rows, 3*D]: main operand boxes [192 x 64] (128B swizzle) or [192 x 32] (64B swizzle, head_dim 32), plus a
 // [192 x 16] 32B-swizzled box for the last 16 dims of head_dim 80.
@@ -216,9 +260,9 @@ static int attention_launch(int hd, const CUtensorMap& main, const CUtensorMap& 
 // Optional ("profile" option): a CUDA-event pair around every launch, on the launch stream, summed per kernel
 // class by vpb_profile_collect.  bench.py uses it to report the dominant kernel's achieved FLOP/s live.
 enum KClass : int { KC_PATCH_IM2COL, KC_GEMM_PATCH, KC_LN, KC_GEMM_QKV, KC_ATTN, KC_GEMM_PROJ, KC_GEMM_FC1, KC_GEMM_FC2,
-                    KC_GEMM_DECONV, KC_GEMM_FINAL, KC_DECODE, KC_PREPROCESS, KC_COUNT };
+                    KC_GEMM_DECONV, KC_GEMM_FINAL, KC_DECODE, KC_PREPROCESS, KC_CHAIN, KC_COUNT };
 static const char* kclass_names[KC_COUNT] = {"patch_im2col", "gemm_patch_embed", "layernorm", "gemm_qkv", "attention", "gemm_proj",
-                                             "gemm_fc1_gelu", "gemm_fc2", "gemm_deconv", "gemm_final_conv", "decode", "crop_preprocess"};
+                                             "gemm_fc1_gelu", "gemm_fc2", "gemm_deconv", "gemm_final_conv", "decode", "crop_preprocess", "gemm_chain"};
 struct ProfRec { int cls; cudaEvent_t a, b; };
 struct Profiler {
   bool on = false;
@@ -243,7 +287,8 @@ struct LinearW {
   __nv_bfloat16* w = nullptr;   // [N,K] bf16
   float* b = nullptr;           // [N padded]
   int n = 0, k = 0, bn = 0;
-  CUtensorMap map;
+  CUtensorMap map;              // W boxes of bn / 2 rows (the standalone GEMM's tile width for this N)
+  CUtensorMap map_c;            // W boxes of chain_bn / 2 rows (every phase of a chained launch uses one tile width)
 };
 struct BlockW {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
@@ -292,6 +337,13 @@ struct vpb_engine {
   // that finishes a row block normalises its 128 rows alone, latency-bound, and the last blocks' LayerNorm sits on the
   // kernel's critical path; a standalone LayerNorm launch spreads the same rows over all SMs.
   bool ln_fused = false;
+  // Chained launches (chain.cuh): patch -> LN -> qkv0, then per block proj -> LN -> fc1 -> fc2 -> LN -> qkv(next) as ONE persistent
+  // kernel each; the counters that replace the kernel boundaries live in chain_counters (5 arrays of one int per 128-row
+  // block per chained launch), zeroed by one memset at the start of every forward.
+  bool use_chain = true;
+  int chain_bn = 256;
+  int* chain_counters = nullptr;
+  size_t chain_blocks = 0;         // 128-row blocks at max_batch
   // host-facing path: two staging slots (crops, org_wh in; kpts, idx out) so that slot i+1's H2D overlaps slot i's compute
   float *crops_stage[2], *kpts[2];
   int32_t *idx[2], *org_wh[2];
@@ -363,6 +415,11 @@ extern "C" int vpb_create(const vpb_config* cfg, vpb_engine** out) {
   e->cfg = *cfg;
   e->D = cfg->embed_dim; e->depth = cfg->depth; e->heads = cfg->num_heads; e->K = cfg->num_keypoints; e->maxB = cfg->max_batch;
   e->n_final = e->K <= 32 ? 32 : 144;
+  e->chain_bn = (e->D % 256 == 0) ? 256 : 128;               // D, 3D and 4D are then all multiples of the chain's tile width
+  {
+    const char* env = getenv("VPB_CHAIN");
+    if (env && env[0] == '0') e->use_chain = false;
+  }
   *out = e;
   return VPB_OK;
 }
@@ -418,7 +475,10 @@ static int pack_linear(vpb_engine* e, LinearW& L, const std::string& wkey, const
   if (!bkey.empty()) pack_bias<<<cdiv(n_pad, 256), 256>>>(e->staged[bkey].first, L.b, n, n_pad, scaled_rows, scale);
   else CU_TRY(cudaMemset(L.b, 0, n_pad * sizeof(float)));
   CU_TRY(cudaGetLastError());
-  return make_map(&L.map, L.w, n_pad, k, k, bn / GEMM_CL);
+  VPB_TRY(make_map(&L.map, L.w, n_pad, k, k, bn / GEMM_CL));
+  if (n_pad % e->chain_bn == 0) VPB_TRY(make_map(&L.map_c, L.w, n_pad, k, k, e->chain_bn / GEMM_CL));
+  else L.map_c = L.map;                                        // never chained (final 1x1 conv)
+  return VPB_OK;
 }
 
 static int copy_vec(vpb_engine* e, float** dst, const std::string& key) {
@@ -496,6 +556,9 @@ extern "C" int vpb_finalize(vpb_engine* e) {
     CU_TRY(cudaEventCreateWithFlags(&e->ev_done[s], cudaEventDisableTiming));
   }
   CU_TRY(cudaEventCreateWithFlags(&e->ev_ws, cudaEventDisableTiming));
+  e->chain_blocks = (M + GEMM_BM - 1) / GEMM_BM;
+  VPB_TRY(dev_alloc(e, &e->chain_counters, static_cast<size_t>(e->depth + 1) * 5 * e->chain_blocks));
+  CU_TRY(cudaMemset(e->chain_counters, 0, static_cast<size_t>(e->depth + 1) * 5 * e->chain_blocks * sizeof(int)));
   VPB_TRY(dev_alloc(e, &e->ln_counters, (M + 127) / 128 + 1));
   CU_TRY(cudaMemset(e->ln_counters, 0, ((M + 127) / 128 + 1) * sizeof(int)));
   VPB_TRY(dev_alloc(e, &e->g_kpts, B * e->K * 3));
@@ -602,11 +665,77 @@ static int frame_gather(vpb_engine* e, const Source& src, int B, cudaStream_t st
 static int gather(vpb_engine* e, const Source& src, int B, cudaStream_t st) {
   return src.crops ? patch_gather(e, src.crops, B, st) : frame_gather(e, src, B, st);
 }
+// Chained form of the backbone (chain.cuh): 1 + depth persistent GEMM launches + depth attention launches.
+//   launch 0:        patch embed (+= x) -> LN(norm1 of block 0) -> qkv of block 0
+//   launch i+1:      proj_i (+= x) -> LN(norm2_i) -> fc1_i + GELU -> fc2_i (+= x) -> LN(norm1_{i+1} | last_norm) [-> qkv_{i+1}]
+static int backbone_chained(vpb_engine* e, int B, cudaStream_t st) {
+  const int D = e->D, M = B * 192, bn = e->chain_bn;
+  const size_t nb = e->chain_blocks;
+  CU_TRY(cudaMemsetAsync(e->chain_counters, 0, static_cast<size_t>(e->depth + 1) * 5 * nb * sizeof(int), st));
+  auto counters = [&](int launch, int which) { return e->chain_counters + (static_cast<size_t>(launch) * 5 + which) * nb; };
+  auto phase = [&](ChainParams& p, ChainMaps& m, int i, const CUtensorMap& a, const LinearW& L, const CUtensorMap& out, int epi, const int* a_ready,
+                   int a_target, int* out_done) {
+    m.a[i] = a; m.w[i] = L.map_c; m.out[i] = out;
+    p.ph[i].N = L.n; p.ph[i].K = L.k; p.ph[i].epi = epi; p.ph[i].bias = L.b; p.ph[i].a_ready = a_ready; p.ph[i].a_target = a_target;
+    p.ph[i].out_done = out_done;
+  };
+  auto base = [&](ChainParams& p) {
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.D = D; p.x = e->x; p.xn = e->xn; p.eps = 1e-6f;
+  };
+  const int nD = D / bn, n4D = 4 * D / bn;                    // column tiles of the D-wide and 4D-wide phases
+  {
+    ChainParams p; ChainMaps m;
+    base(p);
+    // patch.b is a zero vector: the conv bias and pos_embed were folded into the stream seed by the gather
+    phase(p, m, 0, e->m_patch_rows, e->patch, e->o_x, EPI_F32_ADD, nullptr, 0, counters(0, 0));
+    p.ln[0] = {counters(0, 0), nD * GEMM_EPI_WARPS, e->blocks[0].ln1_g, e->blocks[0].ln1_b, counters(0, 1)};
+    phase(p, m, 1, e->m_xn, e->blocks[0].qkv, e->o_qkv, EPI_BF16, counters(0, 1), 0, nullptr);
+    p.num_phases = 2; p.num_ln = 1;
+    for (int i = 2; i < CHAIN_MAX_PHASES; ++i) { m.a[i] = m.a[0]; m.w[i] = m.w[0]; m.out[i] = m.out[0]; }
+    e->prof.begin(KC_CHAIN, st);
+    VPB_TRY(chain_launch(bn, m, p, st));
+    e->prof.end(st);
+  }
+  for (int i = 0; i < e->depth; ++i) {
+    BlockW& b = e->blocks[i];
+    {
+      AttnParams ap;
+      ap.batch = B; ap.heads = e->heads; ap.dim = D; ap.out = e->attn; ap.dbg = nullptr;
+      e->prof.begin(KC_ATTN, st);
+      VPB_TRY(attention_launch(D / e->heads, e->m_qkv_att, e->m_qkv_att_tail, ap, st));
+      e->prof.end(st);
+    }
+    const bool last = (i + 1 == e->depth);
+    const int L = i + 1;
+    ChainParams p; ChainMaps m;
+    base(p);
+    phase(p, m, 0, e->m_attn, b.proj, e->o_x, EPI_F32_ADD, nullptr, 0, counters(L, 0));
+    p.ln[0] = {counters(L, 0), nD * GEMM_EPI_WARPS, b.ln2_g, b.ln2_b, counters(L, 1)};
+    phase(p, m, 1, e->m_xn, b.fc1, e->o_hid, EPI_BF16_GELU, counters(L, 1), 0, counters(L, 2));
+    phase(p, m, 2, e->m_hid, b.fc2, e->o_x, EPI_F32_ADD, counters(L, 2), n4D * GEMM_EPI_WARPS, counters(L, 3));
+    p.ln[1] = {counters(L, 3), nD * GEMM_EPI_WARPS, last ? e->lnf_g : e->blocks[i + 1].ln1_g, last ? e->lnf_b : e->blocks[i + 1].ln1_b, counters(L, 4)};
+    p.num_ln = 2;
+    if (!last) {
+      phase(p, m, 3, e->m_xn, e->blocks[i + 1].qkv, e->o_qkv, EPI_BF16, counters(L, 4), 0, nullptr);
+      p.num_phases = 4;
+    } else {
+      m.a[3] = m.a[0]; m.w[3] = m.w[0]; m.out[3] = m.out[0];
+      p.num_phases = 3;
+    }
+    e->prof.begin(KC_CHAIN, st);
+    VPB_TRY(chain_launch(bn, m, p, st));
+    e->prof.end(st);
+  }
+  return VPB_OK;
+}
+
 // everything after the patch gather, up to last_norm
 static int backbone(vpb_engine* e, int B, cudaStream_t st) {
   const int D = e->D, M = B * 192;
   const int stop = e->stop_after;
   if (stop == 1) return VPB_OK;
+  if (e->use_chain && !stop && !e->ln_fused) return backbone_chained(e, B, st);
   // LayerNorm i is produced either by its own kernel or (ln_fused) by the tail of the GEMM that completes x
   auto fuse_ln = [&](GemmParams& p, const float* g, const float* b) {
     if (!e->ln_fused) return;
@@ -1083,6 +1212,7 @@ extern "C" int vpb_kernel_launches(const vpb_engine* e, int32_t) {
   if (!e) return -1;
   // patch im2col + patch GEMM + depth*(qkv, attention, proj, fc1, fc2) + 2 deconv GEMMs + 1x1 GEMM + decode; the 2*depth+1
   // LayerNorms ride in the tails of the patch / proj / fc2 GEMMs unless ln_fused is switched off
+  if (e->use_chain && !e->ln_fused) return 1 + (1 + e->depth) + e->depth + 2 + 1 + 1;   // gather, chains, attention, deconvs, 1x1, decode
   return 2 + e->depth * 5 + 2 + 1 + 1 + (e->ln_fused ? 0 : 2 * e->depth + 1);
 }
 
@@ -1092,6 +1222,11 @@ extern "C" int vpb_set_option(vpb_engine* e, const char* name, int32_t value) {
   else if (!strcmp(name, "profile")) e->prof.on = value != 0;
   else if (!strcmp(name, "pdl")) g_pdl = value != 0;
   else if (!strcmp(name, "graph")) e->use_graph = value != 0;
+  else if (!strcmp(name, "chain")) {
+    e->use_chain = value != 0;
+    for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);      // captured chains embed the choice
+    e->graphs.clear();
+  }
   else if (!strcmp(name, "ln_fused")) {
     e->ln_fused = value != 0;
     for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);      // captured chains embed the choice

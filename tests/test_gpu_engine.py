@@ -159,6 +159,26 @@ def test_fused_layernorm_tail_is_bit_identical(golden_dir):
         assert np.array_equal(a, b)                                  # counters were reset: a second fused run repeats exactly
 
 
+@pytest.mark.parametrize("name,batches", [("b_coco", (5, 3, 1)), ("s_coco", (4, 1)), ("h_wholebody", (3,)), ("l_coco_25", (2,))])
+def test_chain_is_bit_identical(golden_dir, name, batches):
+    """The chained launches (chain.cuh: patch -> LN -> qkv and proj -> LN -> fc1 -> fc2 -> LN -> qkv as one persistent kernel
+    each, LayerNorm on dedicated warps, counters instead of kernel boundaries) against the one-kernel-per-GEMM path: same
+    arithmetic in the same order -> identical heatmaps, for full, ragged and single-crop batches, and again on a second run
+    (the counters are re-zeroed per forward).  ViT-S exercises the 128-wide chain tiles, ViT-H / L the one-row LayerNorm."""
+    g = np.load(os.path.join(golden_dir, f"fwd_{name}.npz"))
+    m, _ = _engine(g, max_batch=max(batches))
+    x = torch.from_numpy(O.make_crops(max(batches), 654)).cuda()
+    outs = {0: [], 1: []}
+    for chain in (1, 0, 1):
+        m.set_option("chain", chain)
+        outs[chain].append([m(x[:n]).cpu().numpy() for n in batches])
+    for a, b in zip(outs[1][0], outs[0][0]):
+        assert np.array_equal(a, b)
+    for a, b in zip(outs[1][0], outs[1][1]):
+        assert np.array_equal(a, b)
+    assert m.kernel_launches(1) < 45
+
+
 def test_install_rebinds_a_vitinference_like_object():
     """easy_vitpose_b200.install() performs the two assignments VitInference.__init__ makes (inference.py:156,172) on an
     object that looks like a constructed VitInference; `_inference(img)` must then honour the reference contract:
