@@ -89,7 +89,8 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // tmap_main: box [192 rows x MAIN cols] (swizzle = MAIN*2 bytes); tmap_tail: box [192 x 16] (32B swizzle), hd 80 only.
-template <int HD>
+// NPOLY of every 32 exponentials go through ex2_poly (FMA pipe) instead of the MUFU: 0 (all MUFU) or 8 (every 4th)
+template <int HD, int NPOLY = 0>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_constant__ CUtensorMap tmap_tail, const AttnParams p) {
   using Cfg = AttCfg<HD>;
@@ -283,8 +284,9 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), kLog2e, -mscaled));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), kLog2e, -mscaled));
+            const float a0 = fmaf(__uint_as_float(r[j]), kLog2e, -mscaled), a1 = fmaf(__uint_as_float(r[j + 1]), kLog2e, -mscaled);
+            const float e0 = ex2_approx(a0);
+            const float e1 = (NPOLY > 0 && ((j >> 1) % (16 / (NPOLY > 0 ? NPOLY : 1)) == 0)) ? ex2_poly(a1) : ex2_approx(a1);
             sum += e0 + e1;
             pk[j >> 1] = pack_bf16(e0, e1);
           }
@@ -312,6 +314,11 @@ attention_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const __grid_co
 #pragma unroll
         for (int c = 0; c < 3; ++c) mbar_arrive(&p_chunk[grp * 3 + c]);
       }
+      // The epilogue waits on p_ready[grp] by phase parity, and nothing else keeps this group from finishing step t while the
+      // epilogue has not yet looked at step t-2 of the same buffer (S(t) only needs P V(t-2) to have retired): completing
+      // two phases ahead of a waiter would leave it waiting on the wrong phase forever.  s_free[grp] of step t-2 is arrived
+      // by the epilogue after it passed that wait -- almost always long before this point.
+      if (t >= 2) mbar_wait(&s_free[grp], (n - 1) & 1);
       mbar_arrive(&p_ready[grp]);                           // row sum published (release: visible to the epilogue's acquire)
       if (p.dbg) w_busy += clock64() - c0;
     }

@@ -184,6 +184,9 @@ static int device_check(int device) {
   CU_TRY(cudaFuncSetAttribute(attention_tcgen05<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<32>::SMEM));
   CU_TRY(cudaFuncSetAttribute(attention_tcgen05<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<64>::SMEM));
   CU_TRY(cudaFuncSetAttribute(attention_tcgen05<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<80>::SMEM));
+  CU_TRY(cudaFuncSetAttribute(attention_tcgen05<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<32>::SMEM));
+  CU_TRY(cudaFuncSetAttribute(attention_tcgen05<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<64>::SMEM));
+  CU_TRY(cudaFuncSetAttribute(attention_tcgen05<80, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<80>::SMEM));
   ds->attn_attr = true;
   ds->sms = prop.multiProcessorCount;
   return VPB_OK;
@@ -233,6 +236,11 @@ static int chain_launch(int bn, const ChainMaps& maps, const ChainParams& p, cud
 }
 
 // ------------------------------------------------------------------------------------------------ attention dispatch
+// Every 4th softmax exponential on the FMA pipe (ex2_poly) instead of the MUFU.  Process-wide switch: VPB_ATT_POLY=0/1 in the
+// environment at load time, or vpb_debug_attention() (A/B measurements in one process).
+static int g_att_poly = [] { const char* e = getenv("VPB_ATT_POLY"); return (e && e[0] == '1') ? 1 : 0; }();
+extern "C" int vpb_debug_attention(int32_t poly) { g_att_poly = poly ? 1 : 0; return VPB_OK; }
+
 // qkv bf16 [rows, 3*D]: main operand boxes [192 x 64] (128B swizzle) or [192 x 32] (64B swizzle, head_dim 32), plus a
 // [192 x 16] 32B-swizzled box for the last 16 dims of head_dim 80.
 static int make_attn_maps(CUtensorMap* main, CUtensorMap* tail, const void* qkv, uint64_t rows, int D, int hd) {
@@ -246,11 +254,20 @@ static int attention_launch(int hd, const CUtensorMap& main, const CUtensorMap& 
   const int sms = num_sms();
   const dim3 grid(items < sms ? items : sms);      // one CTA per SM (512 TMEM columns each)
   cudaError_t err;
-  switch (hd) {
-    case 32: err = launch_k(attention_tcgen05<32>, grid, dim3(ATT_THREADS), AttCfg<32>::SMEM, st, main, tail, ap); break;
-    case 64: err = launch_k(attention_tcgen05<64>, grid, dim3(ATT_THREADS), AttCfg<64>::SMEM, st, main, tail, ap); break;
-    case 80: err = launch_k(attention_tcgen05<80>, grid, dim3(ATT_THREADS), AttCfg<80>::SMEM, st, main, tail, ap); break;
-    default: return fail(VPB_ERR_ARG, "attention: head_dim %d not built (32, 64, 80)", hd);
+  if (g_att_poly) {
+    switch (hd) {
+      case 32: err = launch_k(attention_tcgen05<32, 8>, grid, dim3(ATT_THREADS), AttCfg<32>::SMEM, st, main, tail, ap); break;
+      case 64: err = launch_k(attention_tcgen05<64, 8>, grid, dim3(ATT_THREADS), AttCfg<64>::SMEM, st, main, tail, ap); break;
+      case 80: err = launch_k(attention_tcgen05<80, 8>, grid, dim3(ATT_THREADS), AttCfg<80>::SMEM, st, main, tail, ap); break;
+      default: return fail(VPB_ERR_ARG, "attention: head_dim %d not built (32, 64, 80)", hd);
+    }
+  } else {
+    switch (hd) {
+      case 32: err = launch_k(attention_tcgen05<32>, grid, dim3(ATT_THREADS), AttCfg<32>::SMEM, st, main, tail, ap); break;
+      case 64: err = launch_k(attention_tcgen05<64>, grid, dim3(ATT_THREADS), AttCfg<64>::SMEM, st, main, tail, ap); break;
+      case 80: err = launch_k(attention_tcgen05<80>, grid, dim3(ATT_THREADS), AttCfg<80>::SMEM, st, main, tail, ap); break;
+      default: return fail(VPB_ERR_ARG, "attention: head_dim %d not built (32, 64, 80)", hd);
+    }
   }
   if (err != cudaSuccess) return fail(VPB_ERR_CUDA, "attention launch: %s", cudaGetErrorString(err));
   return VPB_OK;

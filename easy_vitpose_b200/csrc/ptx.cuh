@@ -326,4 +326,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = i + f with the 1.5 * 2^23 magic constant, degree-3
+// minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, tools-free fit by weighted least squares; bf16 keeps
+// 2^-9 = 2e-3), exponent added into the float's bits.  ~10 instructions; used for a fraction of the softmax exponentials so
+// that the MUFU (16 ex2 / clk / SM) is not the only pipe working.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float xi = t - 12582912.0f;
+  const float f = x - xi;
+  float p = fmaf(0.0551716499f, f, 0.242611125f);
+  p = fmaf(p, f, 0.693260968f);
+  p = fmaf(p, f, 0.999928057f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 }  // namespace vpb

@@ -26,7 +26,7 @@ from oracle import coco_oks_eval as E, preproc_oracle as P, ref_import, vitpose_
 from oracle.make_golden_frames import stub_detector  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
-N_IMAGES, FH, FW, FSEED, SIZE, K, WSEED, GSEED = 10, 384, 512, 500, "b", 17, 121, 77
+N_IMAGES, FH, FW, FSEED, SIZE, K, WSEED, GSEED = 24, 384, 512, 500, "b", 17, 121, 77
 
 
 def detector_rows(rs) -> np.ndarray:

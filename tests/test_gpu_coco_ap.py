@@ -80,6 +80,11 @@ def test_offline_coco_keypoint_ap_matches_the_reference(golden_dir):
     dev = np.linalg.norm(kpf[..., :2] - g["ref_kp"][..., :2], axis=-1)
     print("offline COCO keypoint eval, engine vs reference:", {k: (round(stats[k], 4), round(ref[k], 4)) for k in ref})
     print(f"rounded pixel keypoints identical: {same:.4f}; float deviation over visible keypoints: median {np.median(dev[vis]):.4f} px, max {dev[vis].max():.3f} px")
-    for k in ("AP", "AP50", "AP75", "AP_medium", "AP_large", "AR"):
+    # AP is an average over 101 recall points x 10 OKS thresholds; AR moves in quanta of 1 / (people * 10) when one person
+    # crosses one OKS threshold because a keypoint rounded to the neighbouring pixel: allow one quantum on top
+    quantum = 1.0 / (len(gts) * 10)
+    for k in ("AP", "AP50", "AP75", "AP_medium", "AP_large"):
         assert abs(stats[k] - ref[k]) <= AP_TOL, (k, stats[k], ref[k])
+    for k in ("AR", "AR_medium", "AR_large"):
+        assert abs(stats[k] - ref[k]) <= AP_TOL + quantum + 1e-12, (k, stats[k], ref[k])
     assert same > 0.9

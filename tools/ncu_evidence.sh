@@ -1,0 +1,27 @@
+#!/bin/bash
+# Run under gpurun (ONE GPU): `ncu --set full` of one launch of every kernel class of the current build, each taken from a
+# warm step of the real path (bench.py, ViT-B K=17 batch 64), plus the launch list of one warm step.
+# Outputs gpurun_out/r2_ncu/<name>.ncu-rep and launches.csv; tools/ncu_summarize.py turns them into profiles/ here.
+set -u
+out=gpurun_out/r2_ncu; mkdir -p $out
+BENCH="python bench.py --config b17x64 --steps 2 --warmup 3 --no-cpu-baseline --no-frame-path"
+cap() {   # name, kernel regex, launches to skip, extra env
+  name=$1; pat=$2; skip=$3; shift 3
+  env "$@" timeout 900 ncu --set full --clock-control none --import-source on -k regex:$pat -s $skip -c 1 -f -o $out/$name $BENCH > $out/$name.log 2>&1
+  echo "$name rc=$? $(ls -la $out/$name.ncu-rep 2>/dev/null | awk '{print $5}') bytes"
+}
+# chained build: one warm forward = 1 gather + 13 chains + 12 attention + 2 deconv + 1 final + 1 decode
+cap chain_block   'gemm_chain_tcgen05'          20 VPB_CHAIN=1     # a full block chain: proj -> LN -> fc1 -> fc2 -> LN -> qkv
+cap attention     'attention_tcgen05'           20 VPB_CHAIN=1
+cap deconv        'gemm_bf16_tcgen05<256, 2>'   4  VPB_CHAIN=1
+cap final_conv    'gemm_bf16_tcgen05<32, 4>'    2  VPB_CHAIN=1
+cap decode        'decode_heatmaps'             2  VPB_CHAIN=1
+cap patch_im2col  'patch_im2col'                2  VPB_CHAIN=1
+# one kernel per GEMM / LayerNorm (the path the per-class roofline numbers come from)
+cap gemm_qkv      'gemm_bf16_tcgen05<256, 0>'   14 VPB_CHAIN=0
+cap gemm_fc1      'gemm_bf16_tcgen05<256, 1>'   14 VPB_CHAIN=0
+cap gemm_fc2_proj 'gemm_bf16_tcgen05<256, 5>'   29 VPB_CHAIN=0     # skip 29 -> an fc2 launch (patch, then proj/fc2 alternate)
+cap layernorm     'layernorm_f32_to_bf16'       30 VPB_CHAIN=0
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv $BENCH > $out/launches.log 2>&1
+echo "launch list rc=$?"
+ls -la $out
