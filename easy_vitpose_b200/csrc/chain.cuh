@@ -37,7 +37,7 @@ constexpr int CHAIN_LN_JOB_ROWS = 16;      // rows per LayerNorm job: 4 per warp
 
 struct ChainPhase {
   int N, K;                 // W is [N,K]; N % BN == 0, K % 64 == 0
-  int epi;                  // EPI_BF16 | EPI_BF16_GELU | EPI_F32_ADD
+  int epi;                  // EPI_BF16 | EPI_BF16_GELU | EPI_BF16_GELU_ERF | EPI_F32_ADD
   const float* bias;        // [N]
   const int* a_ready;       // per 128-row block: A rows are complete once a_ready[mt] >= target (nullptr: produced by an earlier launch)
   int a_target;             // > 0: that many arrivals (GEMM-produced A: column tiles * 8 epilogue warps);
@@ -58,6 +58,7 @@ struct ChainParams {
   const float* x;           // fp32 stream [M, D]
   __nv_bfloat16* xn;        // LayerNorm output [M, D]
   float eps;
+  int dbg_nowait;           // measurement only (results may be wrong): publish tiles without waiting for their stores to complete
   ChainPhase ph[CHAIN_MAX_PHASES];
   ChainLn ln[CHAIN_MAX_LN];
 };
@@ -193,6 +194,10 @@ __device__ __forceinline__ void chain_epilogue_tile(uint32_t t_row, int half, in
       if constexpr (EPI == EPI_BF16_GELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+      }
+      if constexpr (EPI == EPI_BF16_GELU_ERF) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_as(v[j]);
       }
       uint8_t* srow = stile + lane * 128;                     // staging row = lane, 16-byte chunk index XOR (lane % 8): SWIZZLE_128B
       if constexpr (EPI == EPI_F32_ADD) {
@@ -365,6 +370,7 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE;
       if (P.epi == EPI_F32_ADD) chain_epilogue_tile<BN, EPI_F32_ADD>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
       else if (P.epi == EPI_BF16_GELU) chain_epilogue_tile<BN, EPI_BF16_GELU>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
+      else if (P.epi == EPI_BF16_GELU_ERF) chain_epilogue_tile<BN, EPI_BF16_GELU_ERF>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
       else chain_epilogue_tile<BN, EPI_BF16>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
       tc_fence_before_sync();
       __syncwarp();
@@ -373,7 +379,7 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
         // publish the tile: this warp's stores / reduce-adds have been PERFORMED (not just read out of smem), then a
         // cross-proxy fence and a gpu-scope release on the row block's counter
         if (elect_one()) {
-          tma_store_wait_all<0>();
+          if (!p.dbg_nowait) tma_store_wait_all<0>();
           fence_proxy_async_all();
           __threadfence();
           red_release_gpu_add(P.out_done + mt, 1);

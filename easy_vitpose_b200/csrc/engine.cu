@@ -143,7 +143,7 @@ static int gemm_launch_t(const CUtensorMap& ta, const CUtensorMap& tw, const CUt
   auto kern = gemm_bf16_tcgen05<BN, EPI>;
   DeviceState* ds = cur_dev();
   if (ds->sms == 0) return fail(VPB_ERR_STATE, "gemm: device not initialised (device_check)");
-  constexpr unsigned slot = 1u << (EPI * 4 + (BN == 256 ? 0 : BN == 128 ? 1 : BN == 144 ? 2 : 3));
+  constexpr unsigned slot = 1u << ((EPI == EPI_BF16_GELU_ERF ? 3 : EPI) * 4 + (BN == 256 ? 0 : BN == 128 ? 1 : BN == 144 ? 2 : 3));
   if (!(ds->gemm_attr & slot)) {
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     ds->gemm_attr |= slot;
@@ -164,6 +164,7 @@ static int gemm_launch(int bn, int epi, const CUtensorMap& ta, const CUtensorMap
   if (bn == BN_ && epi == EPI_) return gemm_launch_t<BN_, EPI_>(ta, tw, tout, p, st);
   VPB_CASE(256, EPI_BF16) VPB_CASE(128, EPI_BF16)
   VPB_CASE(256, EPI_BF16_GELU) VPB_CASE(128, EPI_BF16_GELU)
+  VPB_CASE(256, EPI_BF16_GELU_ERF) VPB_CASE(128, EPI_BF16_GELU_ERF)
   VPB_CASE(256, EPI_F32_ADD) VPB_CASE(128, EPI_F32_ADD)
   VPB_CASE(256, EPI_BF16_RELU_UP)
   VPB_CASE(32, EPI_F32_NCHW) VPB_CASE(144, EPI_F32_NCHW)
@@ -357,7 +358,9 @@ struct vpb_engine {
   // Chained launches (chain.cuh): patch -> LN -> qkv0, then per block proj -> LN -> fc1 -> fc2 -> LN -> qkv(next) as ONE persistent
   // kernel each; the counters that replace the kernel boundaries live in chain_counters (5 arrays of one int per 128-row
   // block per chained launch), zeroed by one memset at the start of every forward.
+  bool gelu_erf = false;           // option "gelu_erf": fc1 epilogue with the A&S-7.1.26 erf instead of the fitted tanh form (A/B)
   bool use_chain = true;
+  int chain_min_batch = 1;         // batches below this take the one-kernel-per-GEMM path (option "chain_min_batch")
   int chain_bn = 256;
   int* chain_counters = nullptr;
   size_t chain_blocks = 0;         // 128-row blocks at max_batch
@@ -699,6 +702,8 @@ static int backbone_chained(vpb_engine* e, int B, cudaStream_t st) {
   auto base = [&](ChainParams& p) {
     memset(&p, 0, sizeof(p));
     p.M = M; p.D = D; p.x = e->x; p.xn = e->xn; p.eps = 1e-6f;
+    static const int nowait = [] { const char* v = getenv("VPB_CHAIN_NOWAIT"); return (v && v[0] == '1') ? 1 : 0; }();
+    p.dbg_nowait = nowait;
   };
   const int nD = D / bn, n4D = 4 * D / bn;                    // column tiles of the D-wide and 4D-wide phases
   {
@@ -729,7 +734,7 @@ static int backbone_chained(vpb_engine* e, int B, cudaStream_t st) {
     base(p);
     phase(p, m, 0, e->m_attn, b.proj, e->o_x, EPI_F32_ADD, nullptr, 0, counters(L, 0));
     p.ln[0] = {counters(L, 0), nD * GEMM_EPI_WARPS, b.ln2_g, b.ln2_b, counters(L, 1)};
-    phase(p, m, 1, e->m_xn, b.fc1, e->o_hid, EPI_BF16_GELU, counters(L, 1), 0, counters(L, 2));
+    phase(p, m, 1, e->m_xn, b.fc1, e->o_hid, e->gelu_erf ? EPI_BF16_GELU_ERF : EPI_BF16_GELU, counters(L, 1), 0, counters(L, 2));
     phase(p, m, 2, e->m_hid, b.fc2, e->o_x, EPI_F32_ADD, counters(L, 2), n4D * GEMM_EPI_WARPS, counters(L, 3));
     p.ln[1] = {counters(L, 3), nD * GEMM_EPI_WARPS, last ? e->lnf_g : e->blocks[i + 1].ln1_g, last ? e->lnf_b : e->blocks[i + 1].ln1_b, counters(L, 4)};
     p.num_ln = 2;
@@ -752,7 +757,7 @@ static int backbone(vpb_engine* e, int B, cudaStream_t st) {
   const int D = e->D, M = B * 192;
   const int stop = e->stop_after;
   if (stop == 1) return VPB_OK;
-  if (e->use_chain && !stop && !e->ln_fused) return backbone_chained(e, B, st);
+  if (e->use_chain && B >= e->chain_min_batch && !stop && !e->ln_fused) return backbone_chained(e, B, st);
   // LayerNorm i is produced either by its own kernel or (ln_fused) by the tail of the GEMM that completes x
   auto fuse_ln = [&](GemmParams& p, const float* g, const float* b) {
     if (!e->ln_fused) return;
@@ -799,7 +804,7 @@ static int backbone(vpb_engine* e, int B, cudaStream_t st) {
     if (stop == 6) return VPB_OK;
     VPB_TRY(standalone_ln(b.ln2_g, b.ln2_b));
     e->prof.begin(KC_GEMM_FC1, st);
-    VPB_TRY(gemm_launch(b.fc1.bn, EPI_BF16_GELU, e->m_xn, b.fc1.map, e->o_hid, gp(M, 4 * D, D, b.fc1.b, e->hid, 4 * D), st));
+    VPB_TRY(gemm_launch(b.fc1.bn, e->gelu_erf ? EPI_BF16_GELU_ERF : EPI_BF16_GELU, e->m_xn, b.fc1.map, e->o_hid, gp(M, 4 * D, D, b.fc1.b, e->hid, 4 * D), st));
     e->prof.end(st);
     if (stop == 7) return VPB_OK;
     {
@@ -1225,11 +1230,11 @@ extern "C" void vpb_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
-extern "C" int vpb_kernel_launches(const vpb_engine* e, int32_t) {
+extern "C" int vpb_kernel_launches(const vpb_engine* e, int32_t batch) {
   if (!e) return -1;
   // patch im2col + patch GEMM + depth*(qkv, attention, proj, fc1, fc2) + 2 deconv GEMMs + 1x1 GEMM + decode; the 2*depth+1
   // LayerNorms ride in the tails of the patch / proj / fc2 GEMMs unless ln_fused is switched off
-  if (e->use_chain && !e->ln_fused) return 1 + (1 + e->depth) + e->depth + 2 + 1 + 1;   // gather, chains, attention, deconvs, 1x1, decode
+  if (e->use_chain && batch >= e->chain_min_batch && !e->ln_fused) return 1 + (1 + e->depth) + e->depth + 2 + 1 + 1;   // gather, chains, attention, deconvs, 1x1, decode
   return 2 + e->depth * 5 + 2 + 1 + 1 + (e->ln_fused ? 0 : 2 * e->depth + 1);
 }
 
@@ -1239,8 +1244,10 @@ extern "C" int vpb_set_option(vpb_engine* e, const char* name, int32_t value) {
   else if (!strcmp(name, "profile")) e->prof.on = value != 0;
   else if (!strcmp(name, "pdl")) g_pdl = value != 0;
   else if (!strcmp(name, "graph")) e->use_graph = value != 0;
-  else if (!strcmp(name, "chain")) {
-    e->use_chain = value != 0;
+  else if (!strcmp(name, "chain") || !strcmp(name, "chain_min_batch") || !strcmp(name, "gelu_erf")) {
+    if (!strcmp(name, "gelu_erf")) e->gelu_erf = value != 0;
+    else if (!strcmp(name, "chain")) e->use_chain = value != 0;
+    else e->chain_min_batch = value;
     for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);      // captured chains embed the choice
     e->graphs.clear();
   }
@@ -1318,7 +1325,7 @@ extern "C" int vpb_gemm(const void* d_a, const void* d_w, const float* d_bias, v
     VPB_TRY(make_map(&tw, d_w, n, k, k, bn / GEMM_CL));
   }
   VPB_TRY(make_map(&tout, d_w, n, k, k, bn / GEMM_CL));   // placeholder for direct epilogues
-  if (epilogue == EPI_BF16 || epilogue == EPI_BF16_GELU) VPB_TRY(make_map(&tout, d_out, m, n, n, 32));
+  if (epilogue == EPI_BF16 || epilogue == EPI_BF16_GELU || epilogue == EPI_BF16_GELU_ERF) VPB_TRY(make_map(&tout, d_out, m, n, n, 32));
   if (epilogue == EPI_F32_ADD) VPB_TRY(make_map(&tout, d_out, m, n, n, 32, /*f32=*/true));
   GemmParams p = gp(m, n, k, d_bias, d_out, n);
   (void)d_resid; (void)resid_mod;

@@ -32,6 +32,8 @@ enum Epilogue : int {
                         // out bf16 NHWC (b,2y+py,2x+px) = relu(acc + bias)                                direct
   EPI_F32_NCHW = 4,     // out f32 [b,n,pix]  = acc + bias for n < n_valid              (1x1 conv)       direct
   EPI_F32_ADD = 5,      // out f32 [M,ldc]   += acc + bias                 (patch embed, proj, fc2)      TMA reduce-add
+  EPI_BF16_GELU_ERF = 6,// like EPI_BF16_GELU with erf evaluated by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7) instead of the fitted
+                        // tanh form: the A/B switch for the GELU approximation (engine option "gelu_erf")
 };
 
 struct GemmParams {
@@ -66,7 +68,7 @@ constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_CL = 2;                 // CTAs per cluster (along M)
 constexpr int GEMM_STAGE_TILE = 4096;      // one epilogue warp's staging tile: 32 rows x 128 B
 
-__host__ __device__ constexpr bool epi_uses_tma(int epi) { return epi == EPI_BF16 || epi == EPI_BF16_GELU || epi == EPI_F32_ADD; }
+__host__ __device__ constexpr bool epi_uses_tma(int epi) { return epi == EPI_BF16 || epi == EPI_BF16_GELU || epi == EPI_F32_ADD || epi == EPI_BF16_GELU_ERF; }
 
 template <int BN, int EPI>
 struct GemmCfg {
@@ -89,8 +91,9 @@ struct GemmCfg {
   static_assert(STAGES >= 3, "ring too shallow");
 };
 
+__device__ __forceinline__ float gelu_erf_as(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
 #ifdef VPB_GELU_ERF
-__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_fast(float x) { return gelu_erf_as(x); }
 #else
 __device__ __forceinline__ float gelu_fast(float x) { return gelu_tanh_fit(x); }
 #endif
@@ -325,6 +328,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if constexpr (EPI == EPI_BF16_GELU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            }
+            if constexpr (EPI == EPI_BF16_GELU_ERF) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf_as(v[j]);
             }
             // staging row = lane, 16-byte chunk index XOR (lane % 8): what a SWIZZLE_128B tensor map expects
             uint8_t* srow = stile + lane * 128;

@@ -5,7 +5,7 @@ import torch
 
 from easy_vitpose_b200 import _lib
 
-EPI_BF16, EPI_BF16_GELU, EPI_BF16_RELU_UP, EPI_F32_NCHW, EPI_F32_ADD = 0, 1, 2, 4, 5
+EPI_BF16, EPI_BF16_GELU, EPI_BF16_RELU_UP, EPI_F32_NCHW, EPI_F32_ADD, EPI_BF16_GELU_ERF = 0, 1, 2, 4, 5, 6
 
 
 def ptr(t):

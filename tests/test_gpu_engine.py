@@ -180,6 +180,27 @@ def test_chain_is_bit_identical(golden_dir, name, batches):
     assert m.kernel_launches(1) == 1 + (1 + depth) + depth + 4      # gather, chains, attention, 2 deconv + 1x1 + decode (ViT-B: 30)
 
 
+def test_gelu_erf_option_changes_nothing_visible(golden_dir):
+    """Option "gelu_erf": fc1 epilogue with an erf accurate to 1.5e-7 instead of the fitted tanh form (max error 2.6e-5 before
+    the bf16 rounding).  Both must sit at the same distance from the fp32 reference; the heatmaps may differ by rounding noise."""
+    g = np.load(os.path.join(golden_dir, "fwd_b_coco.npz"))
+    m, x = _engine(g)
+    ref = g["heatmaps"]
+    rng = float(ref.max() - ref.min())
+    out = {}
+    for chain in (1, 0):
+        m.set_option("chain", chain)
+        for erf in (0, 1):
+            m.set_option("gelu_erf", erf)
+            out[(chain, erf)] = m(torch.from_numpy(x).cuda()).cpu().numpy()
+    m.set_option("gelu_erf", 0)
+    assert np.array_equal(out[(1, 1)], out[(0, 1)])                      # chained and unchained agree under either GELU
+    e_fit, e_erf = float(np.abs(out[(1, 0)] - ref).max()) / rng, float(np.abs(out[(1, 1)] - ref).max()) / rng
+    between = float(np.abs(out[(1, 0)] - out[(1, 1)]).max()) / rng
+    print(f"heatmap Linf vs fp32 reference: fitted GELU {e_fit:.3%}, erf GELU {e_erf:.3%} of range; fitted vs erf {between:.3%}")
+    assert e_fit < HEATMAP_TOL and e_erf < HEATMAP_TOL and between < 0.5 * HEATMAP_TOL
+
+
 def test_install_rebinds_a_vitinference_like_object():
     """easy_vitpose_b200.install() performs the two assignments VitInference.__init__ makes (inference.py:156,172) on an
     object that looks like a constructed VitInference; `_inference(img)` must then honour the reference contract:
