@@ -40,16 +40,16 @@ struct ChainPhase {
   int epi;                  // EPI_BF16 | EPI_BF16_GELU | EPI_BF16_GELU_ERF | EPI_F32_ADD
   const float* bias;        // [N]
   const int* a_ready;       // per 128-row block: A rows are complete once a_ready[mt] >= target (nullptr: produced by an earlier launch)
-  int a_target;             // > 0: that many arrivals (GEMM-produced A: column tiles * 8 epilogue warps);
-                            // 0: LayerNorm-produced A: CHAIN_LN_WARPS arrivals per 16-row job of the block
-  int* out_done;            // per 128-row block, += 1 per epilogue warp per tile once its stores have completed (nullptr: nobody waits)
+  int a_target;             // > 0: that many arrivals (GEMM-produced A: one per column tile of the producing phase);
+                            // 0: LayerNorm-produced A: one arrival per 16-row job of the block
+  int* out_done;            // per 128-row block, += 1 per tile once the CTA's stores of it have completed (nullptr: nobody waits)
 };
 struct ChainLn {
   const int* src_done;      // out_done of the residual phase that completes the fp32 rows
-  int src_target;           // column tiles of that phase * 8
+  int src_target;           // column tiles of that phase
   const float* gamma;       // [D]
   const float* beta;        // [D]
-  int* ready;               // per 128-row block, += 1 per warp per finished job
+  int* ready;               // per 128-row block, += 1 per finished job
 };
 struct ChainParams {
   int M;                    // rows (tokens) of every phase
@@ -59,6 +59,10 @@ struct ChainParams {
   __nv_bfloat16* xn;        // LayerNorm output [M, D]
   float eps;
   int dbg_nowait;           // measurement only (results may be wrong): publish tiles without waiting for their stores to complete
+  long long* dbg;           // measurement: per cluster [CHAIN_MAX_PHASES][12] cycle counters (leader CTA) or nullptr (8..10: LayerNorm
+                            //   stage s under phase 2s, warp 12: wait for the residual rows, busy, jobs):
+                            //   0 mma busy+wait total, 1 mma wait full (operands), 2 mma wait acc_empty (epilogue), 3 producer dependency wait,
+                            //   4 producer wait empty (ring), 5 epilogue(warp 0) busy, 6 epilogue wait acc_full, 7 tiles
   ChainPhase ph[CHAIN_MAX_PHASES];
   ChainLn ln[CHAIN_MAX_LN];
 };
@@ -92,13 +96,22 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
 }
 // generic proxy <-> async proxy (TMA) ordering for global memory
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// Whole warp spins (one coalesced load per probe) until *p >= target.
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Whole warp spins (one coalesced load per probe) until *p >= target.  The probes are RELAXED loads and one acquire fence
+// follows the successful one: an acquire load at gpu scope is compiled to LDG + CCTL.IVALL, i.e. every probe of every waiting
+// warp invalidated the SM's L1 under the epilogue warps' bias loads (ncu source view of the first version: 8 % of all
+// stall samples on that CCTL, and the GELU epilogue three times over its pipe-bound time).
 __device__ __forceinline__ void wait_counter(const int* p, int target) {
   uint32_t spins = 0;
-  while (ld_acquire_gpu(p) < target) {
-    __nanosleep(40);
+  while (ld_relaxed_gpu(p) < target) {
+    __nanosleep(64);
     if (++spins > (VPB_HANG_TRAP_SPINS >> 3)) __trap();
   }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __host__ __device__ __forceinline__ int chain_ln_jobs_in_block(int M, int mt) {
   const int rows = M - mt * GEMM_BM < GEMM_BM ? M - mt * GEMM_BM : GEMM_BM;
@@ -304,12 +317,16 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       const int mt = mp * GEMM_CL + cta_rank;
       const int m0 = mt * GEMM_BM, n0 = nb * BN;
       const int num_kb = P.K / GEMM_BK;
+      long long c0 = p.dbg ? clock64() : 0, w_dep = 0, w_ring = 0;
       if (P.a_ready != nullptr && mt < num_m) {
-        wait_counter(P.a_ready + mt, P.a_target > 0 ? P.a_target : CHAIN_LN_WARPS * chain_ln_jobs_in_block(p.M, mt));
+        wait_counter(P.a_ready + mt, P.a_target > 0 ? P.a_target : chain_ln_jobs_in_block(p.M, mt));
         fence_proxy_async_all();                    // the rows were written through the generic / async proxy of other SMs
       }
+      if (p.dbg) w_dep = clock64() - c0;
       for (int kb = 0; kb < num_kb; ++kb) {
+        if (p.dbg) c0 = clock64();
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (p.dbg) w_ring += clock64() - c0;
         uint8_t* sa = ring + stage * Cfg::STAGE_BYTES;
         if (elect_one()) {
           if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], GEMM_CL * Cfg::STAGE_BYTES);
@@ -318,6 +335,10 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (p.dbg && cta_rank == 0 && lane == 0) {
+        p.dbg[(cluster * CHAIN_MAX_PHASES + ph) * 12 + 3] += w_dep;
+        p.dbg[(cluster * CHAIN_MAX_PHASES + ph) * 12 + 4] += w_ring;
       }
     }
   } else if (warp == 11 && cta_rank == 0) {
@@ -332,11 +353,16 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       const int num_kb = p.ph[ph].K / GEMM_BK;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const long long t0 = p.dbg ? clock64() : 0;
+      long long w_full = 0, c0 = 0;
       mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      const long long w_acc = p.dbg ? clock64() - t0 : 0;
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
       for (int kb = 0; kb < num_kb; ++kb) {
+        if (p.dbg) c0 = clock64();
         mbar_wait(&full_bar[stage], phase);
+        if (p.dbg) w_full += clock64() - c0;
         tc_fence_after_sync();
         const uint32_t sa = smem_u32(ring + stage * Cfg::STAGE_BYTES);
         const uint64_t adesc = umma_desc_sw128(sa, 1024);
@@ -349,6 +375,10 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (p.dbg && lane == 0) {
+        long long* d = p.dbg + (cluster * CHAIN_MAX_PHASES + ph) * 12;
+        d[0] += clock64() - t0; d[1] += w_full; d[2] += w_acc; d[7] += 1;
       }
     }
   } else if (warp < GEMM_EPI_WARPS) {
@@ -365,7 +395,9 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       const uint32_t acc_phase = (it >> 1) & 1;
       const int mt = mp * GEMM_CL + cta_rank;
       const int row0 = mt * GEMM_BM + quarter * 32;
+      const long long e0 = p.dbg ? clock64() : 0;
       mbar_wait(&acc_full[acc], acc_phase);
+      const long long e1 = p.dbg ? clock64() : 0;
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE;
       if (P.epi == EPI_F32_ADD) chain_epilogue_tile<BN, EPI_F32_ADD>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
@@ -375,16 +407,22 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);   // TMEM is free for the MMA thread; the stores may still be in flight
-      if (P.out_done != nullptr && mt < num_m) {
-        // publish the tile: this warp's stores / reduce-adds have been PERFORMED (not just read out of smem), then a
-        // cross-proxy fence and a gpu-scope release on the row block's counter
+      if (P.out_done != nullptr) {
+        // publish the tile ONCE per CTA: every epilogue warp waits until its own stores / reduce-adds have been PERFORMED (not
+        // just read out of smem) and fences them across the proxies; the eight warps meet on a named barrier; one thread
+        // does the gpu-scope release on the row block's counter.  (First version: fence + release per warp = eight
+        // MEMBAR.GPU / ERRBAR / CCTL.IVALL sequences per tile -- 15 % of the kernel's stall samples.)
         if (elect_one()) {
           if (!p.dbg_nowait) tma_store_wait_all<0>();
           fence_proxy_async_all();
-          __threadfence();
-          red_release_gpu_add(P.out_done + mt, 1);
         }
         __syncwarp();
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (warp == 0 && mt < num_m && elect_one()) red_release_gpu_add(P.out_done + mt, 1);
+      }
+      if (p.dbg && warp == 0 && lane == 0 && cta_rank == 0) {
+        long long* d = p.dbg + (cluster * CHAIN_MAX_PHASES + ph) * 12;
+        d[5] += clock64() - e1; d[6] += e1 - e0;
       }
     }
     if (elect_one()) tma_store_wait_all<0>();
@@ -397,7 +435,11 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       const ChainLn& L = p.ln[s];
       for (int job = blockIdx.x; job < jobs; job += gridDim.x) {
         const int mt = (job * CHAIN_LN_JOB_ROWS) / GEMM_BM;
-        wait_counter(L.src_done + mt, L.src_target);
+        const long long l0 = p.dbg ? clock64() : 0;
+        // one warp polls the counter, the other three sleep on a named barrier (bar.sync carries the acquired state over)
+        if (lw == 0) wait_counter(L.src_done + mt, L.src_target);
+        asm volatile("bar.sync 4, 128;" ::: "memory");
+        const long long l1 = p.dbg ? clock64() : 0;
         const int r0 = job * CHAIN_LN_JOB_ROWS + lw * ROWS_PER_WARP;
         const int r1 = min(r0 + ROWS_PER_WARP, p.M);
         switch (p.D) {
@@ -406,13 +448,17 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
           case 1024: chain_ln_rows<8>(p, L, r0, r1, lane); break;
           default: chain_ln_rows<10>(p, L, r0, r1, lane); break;     // 1280
         }
-        __syncwarp();                                                  // every lane's stores precede lane 0's release
-        if (lane == 0) {
+        // one gpu-scope release per job and CTA (a MEMBAR.GPU on an SM with TMA traffic in flight costs thousands of cycles):
+        // the four warps meet on a named barrier (orders their row stores before the releasing thread), warp 12 publishes
+        asm volatile("bar.sync 5, 128;" ::: "memory");
+        if (lw == 0 && lane == 0) {
           fence_proxy_async_all();                                     // consumed by TMA loads (async proxy) of other SMs
-          __threadfence();
           red_release_gpu_add(L.ready + mt, 1);
         }
-        __syncwarp();
+        if (p.dbg && lw == 0 && lane == 0 && cta_rank == 0) {
+          long long* d = p.dbg + (cluster * CHAIN_MAX_PHASES + 2 * s) * 12;
+          d[8] += l1 - l0; d[9] += clock64() - l1; d[10] += 1;
+        }
       }
     }
   }

@@ -360,7 +360,10 @@ struct vpb_engine {
   // block per chained launch), zeroed by one memset at the start of every forward.
   bool gelu_erf = false;           // option "gelu_erf": fc1 epilogue with the A&S-7.1.26 erf instead of the fitted tanh form (A/B)
   bool use_chain = true;
-  int chain_min_batch = 1;         // batches below this take the one-kernel-per-GEMM path (option "chain_min_batch")
+  // Batches below this take the one-kernel-per-GEMM path (option "chain_min_batch" / VPB_CHAIN_MIN_BATCH): measured on B200
+  // (tools/latency_small_batches.py, ViT-B) the chained launches lose 3-8 % up to 32 crops per call (few row blocks: the
+  // dependent phases cannot overlap and every CTA spins) and win from 48 crops on.
+  int chain_min_batch = 48;
   int chain_bn = 256;
   int* chain_counters = nullptr;
   size_t chain_blocks = 0;         // 128-row blocks at max_batch
@@ -439,6 +442,8 @@ extern "C" int vpb_create(const vpb_config* cfg, vpb_engine** out) {
   {
     const char* env = getenv("VPB_CHAIN");
     if (env && env[0] == '0') e->use_chain = false;
+    const char* mb = getenv("VPB_CHAIN_MIN_BATCH");
+    if (mb && atoi(mb) > 0) e->chain_min_batch = atoi(mb);
   }
   *out = e;
   return VPB_OK;
@@ -704,6 +709,7 @@ static int backbone_chained(vpb_engine* e, int B, cudaStream_t st) {
     p.M = M; p.D = D; p.x = e->x; p.xn = e->xn; p.eps = 1e-6f;
     static const int nowait = [] { const char* v = getenv("VPB_CHAIN_NOWAIT"); return (v && v[0] == '1') ? 1 : 0; }();
     p.dbg_nowait = nowait;
+    p.dbg = g_dbg_buf;                      // vpb_debug_gemm(0, counters): [74 clusters][4 phases][8] int64, accumulated over launches
   };
   const int nD = D / bn, n4D = 4 * D / bn;                    // column tiles of the D-wide and 4D-wide phases
   {
@@ -711,7 +717,7 @@ static int backbone_chained(vpb_engine* e, int B, cudaStream_t st) {
     base(p);
     // patch.b is a zero vector: the conv bias and pos_embed were folded into the stream seed by the gather
     phase(p, m, 0, e->m_patch_rows, e->patch, e->o_x, EPI_F32_ADD, nullptr, 0, counters(0, 0));
-    p.ln[0] = {counters(0, 0), nD * GEMM_EPI_WARPS, e->blocks[0].ln1_g, e->blocks[0].ln1_b, counters(0, 1)};
+    p.ln[0] = {counters(0, 0), nD, e->blocks[0].ln1_g, e->blocks[0].ln1_b, counters(0, 1)};
     phase(p, m, 1, e->m_xn, e->blocks[0].qkv, e->o_qkv, EPI_BF16, counters(0, 1), 0, nullptr);
     p.num_phases = 2; p.num_ln = 1;
     for (int i = 2; i < CHAIN_MAX_PHASES; ++i) { m.a[i] = m.a[0]; m.w[i] = m.w[0]; m.out[i] = m.out[0]; }
@@ -733,10 +739,10 @@ static int backbone_chained(vpb_engine* e, int B, cudaStream_t st) {
     ChainParams p; ChainMaps m;
     base(p);
     phase(p, m, 0, e->m_attn, b.proj, e->o_x, EPI_F32_ADD, nullptr, 0, counters(L, 0));
-    p.ln[0] = {counters(L, 0), nD * GEMM_EPI_WARPS, b.ln2_g, b.ln2_b, counters(L, 1)};
+    p.ln[0] = {counters(L, 0), nD, b.ln2_g, b.ln2_b, counters(L, 1)};
     phase(p, m, 1, e->m_xn, b.fc1, e->o_hid, e->gelu_erf ? EPI_BF16_GELU_ERF : EPI_BF16_GELU, counters(L, 1), 0, counters(L, 2));
-    phase(p, m, 2, e->m_hid, b.fc2, e->o_x, EPI_F32_ADD, counters(L, 2), n4D * GEMM_EPI_WARPS, counters(L, 3));
-    p.ln[1] = {counters(L, 3), nD * GEMM_EPI_WARPS, last ? e->lnf_g : e->blocks[i + 1].ln1_g, last ? e->lnf_b : e->blocks[i + 1].ln1_b, counters(L, 4)};
+    phase(p, m, 2, e->m_hid, b.fc2, e->o_x, EPI_F32_ADD, counters(L, 2), n4D, counters(L, 3));
+    p.ln[1] = {counters(L, 3), nD, last ? e->lnf_g : e->blocks[i + 1].ln1_g, last ? e->lnf_b : e->blocks[i + 1].ln1_b, counters(L, 4)};
     p.num_ln = 2;
     if (!last) {
       phase(p, m, 3, e->m_xn, e->blocks[i + 1].qkv, e->o_qkv, EPI_BF16, counters(L, 4), 0, nullptr);

@@ -123,7 +123,7 @@ def test_gemm_gelu_fit_against_the_erf_epilogue():
     gemm(a, w, bias, o_erf, EPI_BF16_GELU_ERF)
     ref = torch.nn.functional.gelu(a.float() @ w.float().T + bias)
     d = (o_fit.float() - o_erf.float()).abs()
-    step = 2.0 ** -8 * o_erf.float().abs() + 2.6e-5 * 2
+    step = 2.0 ** -7 * o_erf.float().abs() + 6e-5                 # one bf16 step of the result (8-bit significand) + the fit's own 2.6e-5
     differ = float((d > 0).float().mean())
     print("fit vs erf epilogue: elements that differ", differ, "| max |fit - erf|", float(d.max()), "| erf epilogue vs exact gelu rel", _rel(o_erf.float(), ref))
     assert bool((d <= step).all())
