@@ -68,10 +68,13 @@ __device__ __forceinline__ void transform_cs(float xr, float yr, int n_i, const 
   }
 }
 
-__global__ void __launch_bounds__(256) decode_heatmaps(const DecodeParams p) {
-  __shared__ float s_rowpass[8][7][11];
+// warps (= maps) per CTA: 4 gives 272 CTAs for 64 x 17 maps (two per SM, 8 warps with 24 16-byte loads each in flight) where 8
+// left 12 of the 148 SMs idle and one CTA per SM
+constexpr int DECODE_WARPS = 4;
+__global__ void __launch_bounds__(DECODE_WARPS * 32) decode_heatmaps(const DecodeParams p) {
+  __shared__ float s_rowpass[DECODE_WARPS][7][11];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x * 8 + wib;                       // map index n*K + k
+  const int g = blockIdx.x * DECODE_WARPS + wib;            // map index n*K + k
   const int total = p.n * p.k;
   pdl_launch_dependents();
   pdl_wait();
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(256) decode_heatmaps(const DecodeParams p) {
   int bi = 0x7fffffff;
   {
     const float4* h4 = reinterpret_cast<const float4*>(hm);
-#pragma unroll 6
+#pragma unroll 12
     for (int j = 0; j < HM_PIX / 128; ++j) {
       const float4 v = __ldg(h4 + j * 32 + lane);
       const int base = (j * 32 + lane) * 4;

@@ -944,7 +944,7 @@ static int decode_launch(const float* d_heatmaps, int32_t n, int32_t k, const in
   DecodeParams p;
   p.heatmaps = d_heatmaps; p.org_wh = d_org_wh; p.kpts = d_kpts; p.idx = d_idx; p.n = n; p.k = k; p.wrap_batch = wrap_batch;
   p.offs_yx = d_offs_yx;
-  launch_k(decode_heatmaps, dim3(cdiv(static_cast<long long>(n) * k, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
+  launch_k(decode_heatmaps, dim3(cdiv(static_cast<long long>(n) * k, DECODE_WARPS)), dim3(DECODE_WARPS * 32), 0, static_cast<cudaStream_t>(stream), p);
   CU_TRY(cudaGetLastError());
   return VPB_OK;
 }
@@ -985,7 +985,7 @@ extern "C" int vpb_decode_modes(const float* d_heatmaps, int32_t n, int32_t k, i
     DecodeParams p;
     p.heatmaps = d_heatmaps; p.org_wh = nullptr; p.kpts = d_kpts; p.idx = d_idx; p.n = n; p.k = k; p.wrap_batch = 1; p.offs_yx = nullptr;
     p.cs32 = d_cs32; p.cs64 = d_cs64;
-    CU_TRY(launch_k(decode_heatmaps, dim3(cdiv(static_cast<long long>(n) * k, 8)), dim3(256), 0, st, p));
+    CU_TRY(launch_k(decode_heatmaps, dim3(cdiv(static_cast<long long>(n) * k, DECODE_WARPS)), dim3(DECODE_WARPS * 32), 0, st, p));
   } else {
     DecodeModesParams p;
     p.heatmaps = d_heatmaps; p.cs32 = d_cs32; p.cs64 = d_cs64; p.kpts = d_kpts; p.idx = d_idx; p.n = n; p.k = k; p.mode = mode;
