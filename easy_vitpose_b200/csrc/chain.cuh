@@ -16,7 +16,7 @@
 //     stream out of L2 (ld.global.cg) and write the bf16 operand rows, then bump the "normalised rows ready" counter.
 //
 // Dependencies only point to tiles that come earlier in the list (and LN jobs only to tiles), all CTAs are resident (one per
-// SM, grid <= #SMs), every role walks its own list in order: the smallest unfinished tile can always run, so the waits cannot
+// SM, grid <= #SMs), every role walks its own list in order (see "Tile list" in the kernel for the order): the smallest unfinished tile can always run, so the waits cannot
 // deadlock; a counter that never arrives traps (VPB_HANG_TRAP_SPINS) instead of hanging the GPU.
 // The arithmetic of every phase is that of gemm.cuh's kernels and of layernorm_f32_to_bf16, in the same order: results are
 // bit-identical to the unchained path (tests/test_gpu_engine.py::test_chain_is_bit_identical).
@@ -58,6 +58,7 @@ struct ChainParams {
   const float* x;           // fp32 stream [M, D]
   __nv_bfloat16* xn;        // LayerNorm output [M, D]
   float eps;
+  int wave_lag[2];          // tile order: lag (in 256-row pairs) of the second phase behind the first inside wavefronts {0,1} and {2,3}
   int dbg_nowait;           // measurement only (results may be wrong): publish tiles without waiting for their stores to complete
   long long* dbg;           // measurement: per cluster [CHAIN_MAX_PHASES][12] cycle counters (leader CTA) or nullptr (8..10: LayerNorm
                             //   stage s under phase 2s, warp 12: wait for the residual rows, busy, jobs):
@@ -258,27 +259,34 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
   const int num_clusters = static_cast<int>(cluster_count_x());
   const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int num_mp = (num_m + GEMM_CL - 1) / GEMM_CL;
-  // tile list: phase-major, inside a phase tile = mp * num_n + nb (n fastest)
-  int tile_end[CHAIN_MAX_PHASES];
-  {
-    int acc = 0;
+  // Tile list.  Default (lag >= #pairs): PHASE-MAJOR, inside a phase tile = mp * num_n + nb (n fastest).  The general form pairs the
+  // phases into two wavefronts, {0, 1} then {2, 3}: slot s holds the tiles of the first phase for row-block pair s and those of the
+  // second phase for pair s - lag, so that a cluster alternates between a reduce-add phase (proj, fc2: epilogues bound by the
+  // L2's fp32 adds) and its consumer.  Dependencies only point backwards for any lag (tests/test_chain_order.py), but every lag
+  // tried was SLOWER than phase-major (engine.cu: VPB_CHAIN_LAG0/1), so this is kept as a measured experiment only.
+  int n_of[CHAIN_MAX_PHASES];
 #pragma unroll
-    for (int i = 0; i < CHAIN_MAX_PHASES; ++i) {
-      if (i < p.num_phases) acc += num_mp * (p.ph[i].N / BN);
-      tile_end[i] = acc;
-    }
-  }
-  const int total_tiles = tile_end[CHAIN_MAX_PHASES - 1];
+  for (int i = 0; i < CHAIN_MAX_PHASES; ++i) n_of[i] = i < p.num_phases ? p.ph[i].N / BN : 0;
+  const int lag0 = p.wave_lag[0] < num_mp ? p.wave_lag[0] : num_mp, lag1 = p.wave_lag[1] < num_mp ? p.wave_lag[1] : num_mp;
+  const int wave0_tiles = num_mp * (n_of[0] + n_of[1]);
+  const int total_tiles = wave0_tiles + num_mp * (n_of[2] + n_of[3]);
   auto locate = [&](int g, int& ph, int& mp, int& nb) {
-    ph = 0;
-    int base = 0;
-#pragma unroll
-    for (int i = 0; i < CHAIN_MAX_PHASES - 1; ++i)
-      if (g >= tile_end[i]) { ph = i + 1; base = tile_end[i]; }   // static indices only: tile_end stays in registers
-    const int local = g - base;
-    const int nn = p.ph[ph].N / BN;
-    mp = local / nn;
-    nb = local % nn;
+    const bool w1 = g >= wave0_tiles;
+    const int gg = w1 ? g - wave0_tiles : g;
+    const int na = w1 ? n_of[2] : n_of[0], nbb = w1 ? n_of[3] : n_of[1];
+    const int lag = nbb == 0 ? num_mp : (w1 ? lag1 : lag0);
+    const int pa = w1 ? 2 : 0;
+    const int head = na * lag;                               // slots [0, lag): first phase only
+    const int mid = (num_mp - lag) * (na + nbb);             // slots [lag, num_mp): both
+    if (gg < head) { ph = pa; mp = gg / na; nb = gg % na; }
+    else if (gg < head + mid) {
+      const int q = gg - head, s = lag + q / (na + nbb), r = q % (na + nbb);
+      if (r < na) { ph = pa; mp = s; nb = r; }
+      else { ph = pa + 1; mp = s - lag; nb = r - na; }
+    } else {
+      const int q = gg - head - mid;                         // slots [num_mp, num_mp + lag): second phase only
+      ph = pa + 1; mp = num_mp - lag + q / nbb; nb = q % nbb;
+    }
   };
   constexpr uint16_t kAllCtas = (1u << GEMM_CL) - 1;
 

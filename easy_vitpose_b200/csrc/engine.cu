@@ -709,6 +709,14 @@ static int backbone_chained(vpb_engine* e, int B, cudaStream_t st) {
     p.M = M; p.D = D; p.x = e->x; p.xn = e->xn; p.eps = 1e-6f;
     static const int nowait = [] { const char* v = getenv("VPB_CHAIN_NOWAIT"); return (v && v[0] == '1') ? 1 : 0; }();
     p.dbg_nowait = nowait;
+    // tile order inside a chained launch: phase-major by default (lag >= number of row-block pairs).  Interleaving the
+    // reduce-add phases with their consumers (VPB_CHAIN_LAG0/1 = lag in 256-row pairs) was measured slower at every lag tried
+    // (B = 64: 27.4 k crops/s phase-major, 25.2 k at 24/32, 23.4 k at 16/22, 20.1 k at 8/12): a consumer tile needs the
+    // producer's tile + epilogue + LayerNorm job (~30 k cycles) behind it, and clusters stalled on that delay the very
+    // producer tiles the next consumers wait for.
+    static const int lag0 = [] { const char* v = getenv("VPB_CHAIN_LAG0"); return v ? atoi(v) : (1 << 20); }();
+    static const int lag1 = [] { const char* v = getenv("VPB_CHAIN_LAG1"); return v ? atoi(v) : (1 << 20); }();
+    p.wave_lag[0] = lag0; p.wave_lag[1] = lag1;
     p.dbg = g_dbg_buf;                      // vpb_debug_gemm(0, counters): [74 clusters][4 phases][8] int64, accumulated over launches
   };
   const int nD = D / bn, n4D = 4 * D / bn;                    // column tiles of the D-wide and 4D-wide phases
