@@ -166,16 +166,22 @@ __device__ __forceinline__ void chain_ln_rows(const ChainParams& p, const ChainL
     const bool two = R == 2 && r + 1 < r1;
     row[0].load(p.x + static_cast<size_t>(r) * D, lane);
     if constexpr (R == 2) { if (two) row[1].load(p.x + static_cast<size_t>(r + 1) * D, lane); }
+    // gamma / beta are requested together with the rows (one exposed memory latency per job instead of two: the SM's L1 is
+    // invalidated by every acquire fence of the CTA, so these are L2 round trips more often than not)
+    float4 g[V], b[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      g[i] = __ldg(reinterpret_cast<const float4*>(ln.gamma) + i * 32 + lane);
+      b[i] = __ldg(reinterpret_cast<const float4*>(ln.beta) + i * 32 + lane);
+    }
     row[0].stats(p.eps);
     if constexpr (R == 2) { if (two) row[1].stats(p.eps); }
     uint2* y0 = reinterpret_cast<uint2*>(p.xn + static_cast<size_t>(r) * D);
     uint2* y1 = reinterpret_cast<uint2*>(p.xn + static_cast<size_t>(r + 1) * D);
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(ln.gamma) + i * 32 + lane);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(ln.beta) + i * 32 + lane);
-      y0[i * 32 + lane] = row[0].out(i, g, b);
-      if constexpr (R == 2) { if (two) y1[i * 32 + lane] = row[1].out(i, g, b); }
+      y0[i * 32 + lane] = row[0].out(i, g[i], b[i]);
+      if constexpr (R == 2) { if (two) y1[i * 32 + lane] = row[1].out(i, g[i], b[i]); }
     }
   }
 }
@@ -318,12 +324,15 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
     // ------------------------------------------------------------ TMA producer (+ the waits that replace kernel boundaries)
     int stage = 0;
     uint32_t phase = 0;
+    int prev_ph = -1;
     for (int g = cluster; g < total_tiles; g += num_clusters) {
       int ph, mp, nb;
       locate(g, ph, mp, nb);
       const ChainPhase& P = p.ph[ph];
       const int mt = mp * GEMM_CL + cta_rank;
       const int m0 = mt * GEMM_BM, n0 = nb * BN;
+      const bool first_of_phase = ph != prev_ph;
+      prev_ph = ph;
       const int num_kb = P.K / GEMM_BK;
       long long c0 = p.dbg ? clock64() : 0, w_dep = 0, w_ring = 0;
       if (P.a_ready != nullptr && mt < num_m) {
@@ -346,6 +355,7 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       }
       if (p.dbg && cta_rank == 0 && lane == 0) {
         p.dbg[(cluster * CHAIN_MAX_PHASES + ph) * 12 + 3] += w_dep;
+        if (first_of_phase) p.dbg[(cluster * CHAIN_MAX_PHASES + ph) * 12 + 11] += w_dep;      // of which: this cluster's first tile of the phase
         p.dbg[(cluster * CHAIN_MAX_PHASES + ph) * 12 + 4] += w_ring;
       }
     }
@@ -458,14 +468,19 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
         }
         // one gpu-scope release per job and CTA (a MEMBAR.GPU on an SM with TMA traffic in flight costs thousands of cycles):
         // the four warps meet on a named barrier (orders their row stores before the releasing thread), warp 12 publishes
+        const long long l2 = p.dbg ? clock64() : 0;
         asm volatile("bar.sync 5, 128;" ::: "memory");
+        const long long l3 = p.dbg ? clock64() : 0;
         if (lw == 0 && lane == 0) {
           fence_proxy_async_all();                                     // consumed by TMA loads (async proxy) of other SMs
           red_release_gpu_add(L.ready + mt, 1);
         }
         if (p.dbg && lw == 0 && lane == 0 && cta_rank == 0) {
           long long* d = p.dbg + (cluster * CHAIN_MAX_PHASES + 2 * s) * 12;
-          d[8] += l1 - l0; d[9] += clock64() - l1; d[10] += 1;
+          const long long l4 = clock64();
+          d[8] += l1 - l0; d[9] += l4 - l1; d[10] += 1;
+          long long* e = d + 12;                                       // breakdown of the busy part, stored under the next phase's slots 8..10
+          e[8] += l2 - l1; e[9] += l3 - l2; e[10] += l4 - l3;         // own rows (loads, statistics, stores) | wait for the other warps | publish
         }
       }
     }

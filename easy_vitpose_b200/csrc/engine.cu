@@ -442,6 +442,8 @@ extern "C" int vpb_create(const vpb_config* cfg, vpb_engine** out) {
   {
     const char* env = getenv("VPB_CHAIN");
     if (env && env[0] == '0') e->use_chain = false;
+    const char* ge = getenv("VPB_GELU_ERF");
+    if (ge && ge[0] == '1') e->gelu_erf = true;
     const char* mb = getenv("VPB_CHAIN_MIN_BATCH");
     if (mb && atoi(mb) > 0) e->chain_min_batch = atoi(mb);
   }

@@ -245,3 +245,25 @@ def test_install_rebinds_a_vitinference_like_object():
     assert np.array_equal(vi.postprocess(hm, 207, 301)[..., 2], okp[..., 2])
     many = backend.inference_batch([img, img[:200, :150], img[50:, 20:]])
     assert many.shape == (3, K, 3) and np.array_equal(many[:1], out)
+
+
+def test_shard_pipeline_single_rank_matches_infer_crops(golden_dir):
+    """distributed.ShardPipeline (host crops in -> gathered host keypoints out, two batches in flight, three streams) with no
+    process group initialised = world size 1: every batch must come back equal to a plain infer_crops call, in order, including
+    when a slot is reused while the other is still in flight."""
+    from easy_vitpose_b200.distributed import ShardPipeline
+    g = np.load(os.path.join(golden_dir, "fwd_b_coco.npz"))
+    m, _ = _engine(g, max_batch=4)
+    B = 4
+    batches = [torch.from_numpy(O.make_crops(B, 700 + i)).pin_memory() for i in range(5)]
+    org = torch.tensor([[180 + 7 * i, 250 - 3 * i] for i in range(B)], dtype=torch.int32).pin_memory()
+    want = [m.infer_crops(b.cuda(), org)[0].cpu().numpy() for b in batches]
+    pipe = ShardPipeline(m, B, depth=2)
+    got = []
+    pipe.submit(0, batches[0], org)
+    for i in range(1, len(batches)):
+        pipe.submit(i % 2, batches[i], org)
+        got.append(pipe.wait((i - 1) % 2).numpy().copy())
+    got.append(pipe.wait((len(batches) - 1) % 2).numpy().copy())
+    for w, k in zip(want, got):
+        assert np.array_equal(w, k)

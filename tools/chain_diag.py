@@ -32,7 +32,9 @@ print(f"B={B}: MMA-thread cycles per cluster over one forward (13 chained launch
 for ph in range(4):
     t, wf, wa, dep, ring, eb, ew, n = d[:, ph, :8].mean(0)
     print(f"  {names[ph]:13s} tiles/cluster {n:5.1f}  mma {t:9.0f} cyc ({t / tot:5.1%}) = {t / max(n, 1):7.0f}/tile | wait operands {wf / max(t, 1):5.1%}  wait epilogue {wa / max(t, 1):5.1%} "
-          f"| producer: dependency wait {dep / max(n, 1):6.0f}/tile, ring wait {ring / max(n, 1):6.0f}/tile | epilogue warp 0: busy {eb / max(n, 1):6.0f}/tile, wait {ew / max(n, 1):6.0f}/tile")
+          f"| producer: dependency wait {dep / max(n, 1):6.0f}/tile ({d[:, ph, 11].mean() / max(dep, 1):.0%} of it on the cluster's first tile of the phase), ring wait {ring / max(n, 1):6.0f}/tile | epilogue warp 0: busy {eb / max(n, 1):6.0f}/tile, wait {ew / max(n, 1):6.0f}/tile")
 for st, ph in ((0, 0), (1, 2)):
     w, b, n = d[:, ph, 8:11].mean(0)
-    print(f"  LayerNorm stage {st} (warp 12 of the leader CTAs): jobs/CTA {n:5.1f}, busy {b / max(n, 1):7.0f} cyc/job, wait for the residual rows {w / max(n, 1):7.0f} cyc/job")
+    rows, other, pub = d[:, ph + 1, 8:11].mean(0)
+    print(f"  LayerNorm stage {st} (warp 12 of the leader CTAs): jobs/CTA {n:5.1f}, busy {b / max(n, 1):7.0f} cyc/job (own rows {rows / max(n, 1):.0f}, waiting for the other "
+          f"three warps {other / max(n, 1):.0f}, fence + release {pub / max(n, 1):.0f}), wait for the residual rows {w / max(n, 1):7.0f} cyc/job")
