@@ -307,6 +307,8 @@ struct LinearW {
   int n = 0, k = 0, bn = 0;
   CUtensorMap map;              // W boxes of bn / 2 rows (the standalone GEMM's tile width for this N)
   CUtensorMap map_c;            // W boxes of chain_bn / 2 rows (every phase of a chained launch uses one tile width)
+  CUtensorMap map128;           // W boxes of 64 rows: 128-wide tiles for small batches (pick_bn); valid when n_pad % 128 == 0
+  bool has128 = false;
 };
 struct BlockW {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
@@ -358,6 +360,10 @@ struct vpb_engine {
   // Chained launches (chain.cuh): patch -> LN -> qkv0, then per block proj -> LN -> fc1 -> fc2 -> LN -> qkv(next) as ONE persistent
   // kernel each; the counters that replace the kernel boundaries live in chain_counters (5 arrays of one int per 128-row
   // block per chained launch), zeroed by one memset at the start of every forward.
+  // Small batches (below chain_min_batch): LayerNorm + its consumer GEMM (qkv / fc1) as ONE two-stage chained launch -- the
+  // LayerNorm jobs start at once (their rows are complete), the GEMM tiles wait for their rows -- instead of a LayerNorm
+  // launch followed by a GEMM launch (option "ln_in_gemm").
+  bool ln_in_gemm = true;
   bool gelu_erf = false;           // option "gelu_erf": fc1 epilogue with the A&S-7.1.26 erf instead of the fitted tanh form (A/B)
   bool use_chain = true;
   // Batches below this take the one-kernel-per-GEMM path (option "chain_min_batch" / VPB_CHAIN_MIN_BATCH): measured on B200
@@ -505,6 +511,8 @@ static int pack_linear(vpb_engine* e, LinearW& L, const std::string& wkey, const
   VPB_TRY(make_map(&L.map, L.w, n_pad, k, k, bn / GEMM_CL));
   if (n_pad % e->chain_bn == 0) VPB_TRY(make_map(&L.map_c, L.w, n_pad, k, k, e->chain_bn / GEMM_CL));
   else L.map_c = L.map;                                        // never chained (final 1x1 conv)
+  L.has128 = (n_pad % 128 == 0);
+  if (L.has128) VPB_TRY(make_map(&L.map128, L.w, n_pad, k, k, 128 / GEMM_CL));
   return VPB_OK;
 }
 
@@ -768,6 +776,19 @@ static int backbone_chained(vpb_engine* e, int B, cudaStream_t st) {
   return VPB_OK;
 }
 
+// Tile width of a standalone GEMM launch.  A 256-wide tile is the efficient one (128 flop per byte of operand traffic), but a small
+// batch has few of them: 9 crops -> 7 row-block pairs -> proj / fc2 have 21 tiles for 74 SM pairs and the launch lasts one full
+// K loop of a single tile.  Halving the width doubles the tiles and halves every tile's K-loop time; taken while the 128-wide
+// tiles still fit one wave.  The accumulation order of an output element does not depend on the tile shape: bit-identical.
+static const CUtensorMap& pick_tile(const LinearW& L, int M, int* bn) {
+  *bn = L.bn;
+  if (L.bn == 256 && L.has128 && !(g_dbg_flags & 16)) {      // debug flag 16: never narrow
+    const int pairs256 = cdiv(cdiv(M, GEMM_BM), GEMM_CL) * (L.n / 256);
+    if (2 * pairs256 <= num_sms() / GEMM_CL) { *bn = 128; return L.map128; }
+  }
+  return L.map;
+}
+
 // everything after the patch gather, up to last_norm
 static int backbone(vpb_engine* e, int B, cudaStream_t st) {
   const int D = e->D, M = B * 192;
@@ -786,21 +807,50 @@ static int backbone(vpb_engine* e, int B, cudaStream_t st) {
     e->prof.end(st);
     return VPB_OK;
   };
+  // LayerNorm(x; g, b) -> xn followed by xn * W^T + bias (epilogue epi) as one chained launch: one LayerNorm stage whose source
+  // rows are already complete (target 0) and one GEMM phase that waits for the normalised rows of its tile
+  const bool mini = e->ln_in_gemm && !e->ln_fused && !stop;
+  const size_t nblk = e->chain_blocks;
+  if (mini) CU_TRY(cudaMemsetAsync(e->chain_counters, 0, static_cast<size_t>(e->depth + 1) * 5 * nblk * sizeof(int), st));
+  auto ln_gemm = [&](const float* g, const float* b, const LinearW& L, const CUtensorMap& out, int epi, int slot, int kclass) -> int {
+    ChainParams p; ChainMaps m;
+    memset(&p, 0, sizeof(p));
+    p.M = M; p.D = D; p.x = e->x; p.xn = e->xn; p.eps = 1e-6f; p.wave_lag[0] = p.wave_lag[1] = 1 << 20; p.dbg = nullptr;
+    int* ready = e->chain_counters + static_cast<size_t>(slot) * nblk;
+    p.ln[0] = {ready, 0, g, b, ready};                      // source counter: any valid address, target 0 = "already complete"
+    p.num_ln = 1; p.num_phases = 1;
+    for (int i = 0; i < CHAIN_MAX_PHASES; ++i) { m.a[i] = e->m_xn; m.w[i] = L.map_c; m.out[i] = out; }
+    p.ph[0].N = L.n; p.ph[0].K = L.k; p.ph[0].epi = epi; p.ph[0].bias = L.b; p.ph[0].a_ready = ready; p.ph[0].a_target = 0; p.ph[0].out_done = nullptr;
+    e->prof.begin(kclass, st);
+    VPB_TRY(chain_launch(e->chain_bn, m, p, st));
+    e->prof.end(st);
+    return VPB_OK;
+  };
   {  // tokens += rows * Wpatch^T; the stream was seeded with pos_embed[1+t] + pos_embed[0] + conv bias by the gather
     GemmParams p = gp(M, D, 768, e->patch.b, e->x, D);   // patch.b is a zero vector (the conv bias lives in pos_bias)
     fuse_ln(p, e->blocks[0].ln1_g, e->blocks[0].ln1_b);
     e->prof.begin(KC_GEMM_PATCH, st);
-    VPB_TRY(gemm_launch(e->patch.bn, EPI_F32_ADD, e->m_patch_rows, e->patch.map, e->o_x, p, st));
+    int bn;
+    const CUtensorMap& wm = pick_tile(e->patch, M, &bn);
+    VPB_TRY(gemm_launch(bn, EPI_F32_ADD, e->m_patch_rows, wm, e->o_x, p, st));
     e->prof.end(st);
   }
   if (stop == 2) return VPB_OK;
   for (int i = 0; i < e->depth; ++i) {
     BlockW& b = e->blocks[i];
+    if (mini) {
+      VPB_TRY(ln_gemm(b.ln1_g, b.ln1_b, b.qkv, e->o_qkv, EPI_BF16, i * 5 + 4, KC_GEMM_QKV));
+    } else {
     VPB_TRY(standalone_ln(b.ln1_g, b.ln1_b));
     if (stop == 3) return VPB_OK;
     e->prof.begin(KC_GEMM_QKV, st);
-    VPB_TRY(gemm_launch(b.qkv.bn, EPI_BF16, e->m_xn, b.qkv.map, e->o_qkv, gp(M, 3 * D, D, b.qkv.b, e->qkv, 3 * D), st));
+    {
+      int bn;
+      const CUtensorMap& wm = pick_tile(b.qkv, M, &bn);
+      VPB_TRY(gemm_launch(bn, EPI_BF16, e->m_xn, wm, e->o_qkv, gp(M, 3 * D, D, b.qkv.b, e->qkv, 3 * D), st));
+    }
     e->prof.end(st);
+    }
     if (stop == 4) return VPB_OK;
     {
       AttnParams ap;
@@ -814,21 +864,33 @@ static int backbone(vpb_engine* e, int B, cudaStream_t st) {
       GemmParams p = gp(M, D, D, b.proj.b, e->x, D);     // x += attn * Wproj^T + b   (TMA reduce-add into the fp32 stream) [+ norm2]
       fuse_ln(p, b.ln2_g, b.ln2_b);
       e->prof.begin(KC_GEMM_PROJ, st);
-      VPB_TRY(gemm_launch(b.proj.bn, EPI_F32_ADD, e->m_attn, b.proj.map, e->o_x, p, st));
+      int bn;
+      const CUtensorMap& wm = pick_tile(b.proj, M, &bn);
+      VPB_TRY(gemm_launch(bn, EPI_F32_ADD, e->m_attn, wm, e->o_x, p, st));
       e->prof.end(st);
     }
     if (stop == 6) return VPB_OK;
+    if (mini) {
+      VPB_TRY(ln_gemm(b.ln2_g, b.ln2_b, b.fc1, e->o_hid, e->gelu_erf ? EPI_BF16_GELU_ERF : EPI_BF16_GELU, (i + 1) * 5 + 1, KC_GEMM_FC1));
+    } else {
     VPB_TRY(standalone_ln(b.ln2_g, b.ln2_b));
     e->prof.begin(KC_GEMM_FC1, st);
-    VPB_TRY(gemm_launch(b.fc1.bn, e->gelu_erf ? EPI_BF16_GELU_ERF : EPI_BF16_GELU, e->m_xn, b.fc1.map, e->o_hid, gp(M, 4 * D, D, b.fc1.b, e->hid, 4 * D), st));
+    {
+      int bn;
+      const CUtensorMap& wm = pick_tile(b.fc1, M, &bn);
+      VPB_TRY(gemm_launch(bn, e->gelu_erf ? EPI_BF16_GELU_ERF : EPI_BF16_GELU, e->m_xn, wm, e->o_hid, gp(M, 4 * D, D, b.fc1.b, e->hid, 4 * D), st));
+    }
     e->prof.end(st);
+    }
     if (stop == 7) return VPB_OK;
     {
       GemmParams p = gp(M, D, 4 * D, b.fc2.b, e->x, D);  // [+ norm1 of the next block, or last_norm]
       if (i + 1 < e->depth) fuse_ln(p, e->blocks[i + 1].ln1_g, e->blocks[i + 1].ln1_b);
       else fuse_ln(p, e->lnf_g, e->lnf_b);
       e->prof.begin(KC_GEMM_FC2, st);
-      VPB_TRY(gemm_launch(b.fc2.bn, EPI_F32_ADD, e->m_hid, b.fc2.map, e->o_x, p, st));
+      int bn;
+      const CUtensorMap& wm = pick_tile(b.fc2, M, &bn);
+      VPB_TRY(gemm_launch(bn, EPI_F32_ADD, e->m_hid, wm, e->o_x, p, st));
       e->prof.end(st);
     }
     if (stop == 8) return VPB_OK;
@@ -1251,7 +1313,9 @@ extern "C" int vpb_kernel_launches(const vpb_engine* e, int32_t batch) {
   // patch im2col + patch GEMM + depth*(qkv, attention, proj, fc1, fc2) + 2 deconv GEMMs + 1x1 GEMM + decode; the 2*depth+1
   // LayerNorms ride in the tails of the patch / proj / fc2 GEMMs unless ln_fused is switched off
   if (e->use_chain && batch >= e->chain_min_batch && !e->ln_fused) return 1 + (1 + e->depth) + e->depth + 2 + 1 + 1;   // gather, chains, attention, deconvs, 1x1, decode
-  return 2 + e->depth * 5 + 2 + 1 + 1 + (e->ln_fused ? 0 : 2 * e->depth + 1);
+  // one kernel per GEMM: gather, patch GEMM, depth x (qkv, attention, proj, fc1, fc2), 2 deconvs, 1x1, decode; the LayerNorms are
+  // launches of their own (2 * depth + 1), or ride in front of qkv / fc1 (ln_in_gemm: only last_norm is left), or in the tails
+  return 2 + e->depth * 5 + 2 + 1 + 1 + (e->ln_fused ? 0 : e->ln_in_gemm ? 1 : 2 * e->depth + 1);
 }
 
 extern "C" int vpb_set_option(vpb_engine* e, const char* name, int32_t value) {
@@ -1260,8 +1324,9 @@ extern "C" int vpb_set_option(vpb_engine* e, const char* name, int32_t value) {
   else if (!strcmp(name, "profile")) e->prof.on = value != 0;
   else if (!strcmp(name, "pdl")) g_pdl = value != 0;
   else if (!strcmp(name, "graph")) e->use_graph = value != 0;
-  else if (!strcmp(name, "chain") || !strcmp(name, "chain_min_batch") || !strcmp(name, "gelu_erf")) {
+  else if (!strcmp(name, "chain") || !strcmp(name, "chain_min_batch") || !strcmp(name, "gelu_erf") || !strcmp(name, "ln_in_gemm")) {
     if (!strcmp(name, "gelu_erf")) e->gelu_erf = value != 0;
+    else if (!strcmp(name, "ln_in_gemm")) e->ln_in_gemm = value != 0;
     else if (!strcmp(name, "chain")) e->use_chain = value != 0;
     else e->chain_min_batch = value;
     for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);      // captured chains embed the choice

@@ -169,16 +169,23 @@ def test_chain_is_bit_identical(golden_dir, name, batches):
     m, _ = _engine(g, max_batch=max(batches))
     m.set_option("chain_min_batch", 1)                                # the default keeps small batches on the unchained path
     x = torch.from_numpy(O.make_crops(max(batches), 654)).cuda()
-    outs = {0: [], 1: []}
-    for chain in (1, 0, 1):
-        m.set_option("chain", chain)
+    outs = {0: [], 1: [], 2: []}
+    for chain in (1, 0, 1, 2):                                       # 2 = one kernel per GEMM with LayerNorm riding in front of qkv / fc1
+        m.set_option("chain", 1 if chain == 1 else 0)
+        m.set_option("ln_in_gemm", 1 if chain == 2 else 0)
         outs[chain].append([m(x[:n]).cpu().numpy() for n in batches])
+    m.set_option("ln_in_gemm", 1)
     for a, b in zip(outs[1][0], outs[0][0]):
         assert np.array_equal(a, b)
     for a, b in zip(outs[1][0], outs[1][1]):
         assert np.array_equal(a, b)
+    for a, b in zip(outs[2][0], outs[0][0]):
+        assert np.array_equal(a, b)
     depth = int(g["meta"][1])
+    m.set_option("chain", 1)
     assert m.kernel_launches(1) == 1 + (1 + depth) + depth + 4      # gather, chains, attention, 2 deconv + 1x1 + decode (ViT-B: 30)
+    m.set_option("chain", 0)
+    assert m.kernel_launches(1) == 2 + 5 * depth + 4 + 1            # + patch GEMM, 5 per block, last_norm (ViT-B: 67; round 1: 91)
 
 
 def test_gelu_erf_option_changes_nothing_visible(golden_dir):

@@ -1,26 +1,39 @@
 #!/usr/bin/env python
-"""Latency of small ragged batches (BASELINE configs[4]: a video stream's per-frame crop batch): chained launches (chain.cuh)
-against one kernel per GEMM / LayerNorm, CUDA-graph replay on.  Synchronous host-visible latency per call, and back-to-back
-throughput (no sync between calls) for the batch sizes around the chain's break-even point."""
+"""Latency of small ragged batches (BASELINE configs[4]: a video stream's per-frame crop batch), CUDA-graph replay on:
+  wide      one kernel per GEMM / LayerNorm, 256-wide tiles always (round 1)
+  narrow    the same with 128-wide tiles while they fit one wave (pick_tile, the default for small batches)
+  narrow+ln-in-gemm  narrow + LayerNorm and its consumer GEMM (qkv / fc1) as one two-stage chained launch (the default below 48 crops)
+  (LayerNorm in the TAIL of the residual GEMMs, option ln_fused, lost at every batch size: 1.03 vs 0.71 ms at 1 crop, 3.16 vs 2.73 at 64)
+  chained   chained launches (chain.cuh; the default from 48 crops on)
+Synchronous host-visible latency per call and back-to-back time per call (no sync between calls)."""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
-from easy_vitpose_b200 import ViTPose, dyn_model_import
+from easy_vitpose_b200 import ViTPose, dyn_model_import, _lib
 from easy_vitpose_b200.synthetic import random_state_dict
 m = ViTPose(dyn_model_import("ap10k", "b"), max_batch=64)
 m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in random_state_dict("b", 17, seed=1).items()}).to("cuda:0")
 m.set_option("chain_min_batch", 1)
+L = _lib.lib()
 side = torch.cuda.Stream()
-for n in (1, 2, 6, 12, 16, 24, 32, 48, 64):
+MODES = [("wide", 16 << 8, 0, 0, 0), ("narrow", 0, 0, 0, 0), ("narrow+ln-in-gemm", 0, 0, 0, 1), ("chained", 0, 0, 1, 0)]
+for n in (1, 2, 4, 6, 9, 12, 16, 24, 32, 48, 64):
     x = torch.randn(n, 3, 256, 192, device="cuda"); org = torch.tensor([[192, 256]] * n, dtype=torch.int32, device="cuda")
-    row = []
-    for chain in (0, 1):
-        m.set_option("chain", chain)
+    out = []
+    ref = None
+    for name, flags, lnf, chain, lig in MODES:
+        L.vpb_debug_gemm(flags, None)
+        m.set_option("ln_fused", lnf)
+        m.set_option("ln_in_gemm", lig)
+        m.set_option("chain", chain)            # also drops the captured graphs: they embed the choices above
         with torch.cuda.stream(side):
             for _ in range(5):
                 kp, _ = m.infer_crops(x, org)
             torch.cuda.synchronize()
+            if ref is None:
+                ref = kp.clone()
+            same = bool(torch.equal(ref, kp))
             t0 = time.perf_counter()
             for _ in range(30):
                 kp, _ = m.infer_crops(x, org); torch.cuda.synchronize()
@@ -30,7 +43,6 @@ for n in (1, 2, 6, 12, 16, 24, 32, 48, 64):
             for _ in range(30):
                 kp, _ = m.infer_crops(x, org)
             e1.record(); torch.cuda.synchronize()
-            thr = e0.elapsed_time(e1) / 30
-        row.append((lat * 1e3, thr))
-    print(f"crops/call={n:2d}: unchained latency {row[0][0]:.3f} ms, back-to-back {row[0][1]:.3f} ms | chained latency {row[1][0]:.3f} ms, back-to-back {row[1][1]:.3f} ms"
-          f" | chained/unchained back-to-back {row[1][1] / row[0][1]:.3f}")
+            out.append(f"{name} {lat * 1e3:.3f} / {e0.elapsed_time(e1) / 30:.3f}{'' if same else ' (DIFFERS!)'}")
+    print(f"crops/call={n:2d}  latency / back-to-back ms:  " + "  |  ".join(out))
+L.vpb_debug_gemm(0, None); m.set_option("ln_fused", 0); m.set_option("ln_in_gemm", 1); m.set_option("chain", 1)
