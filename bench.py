@@ -541,7 +541,6 @@ def run_gpu(args) -> None:
         # the chained launches hide the per-GEMM split: one more profiled pass with one kernel per GEMM / LayerNorm
         # (set_option("chain", 0)) for the per-class table and the attention-GEMM figure the north star asks for
         model.set_option("chain", 0)
-        model.set_option("ln_in_gemm", 0)                       # LayerNorm as launches of its own: a per-class figure for it
         for i in range(3):
             step(i)
         barrier()
@@ -550,7 +549,6 @@ def run_gpu(args) -> None:
             step(i)
         barrier()
         prof_unchained = model.profile_collect()
-        model.set_option("ln_in_gemm", 1)
         model.set_option("chain", 1)
     model.set_option("profile", 0)
 

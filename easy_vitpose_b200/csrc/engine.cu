@@ -362,8 +362,10 @@ struct vpb_engine {
   // block per chained launch), zeroed by one memset at the start of every forward.
   // Small batches (below chain_min_batch): LayerNorm + its consumer GEMM (qkv / fc1) as ONE two-stage chained launch -- the
   // LayerNorm jobs start at once (their rows are complete), the GEMM tiles wait for their rows -- instead of a LayerNorm
-  // launch followed by a GEMM launch (option "ln_in_gemm").
-  bool ln_in_gemm = true;
+  // launch followed by a GEMM launch (option "ln_in_gemm").  Bit-identical, but measured SLOWER than the two launches at every
+  // small batch (1 crop: 0.864 vs 0.711 ms per call; 9 crops: 0.884 vs 0.819; a LayerNorm job on the chain's spare warps takes
+  // ~5 us against 8.6 us for the whole LayerNorm launch, and the chained kernel cannot use the narrow tiles): off by default.
+  bool ln_in_gemm = false;
   bool gelu_erf = false;           // option "gelu_erf": fc1 epilogue with the A&S-7.1.26 erf instead of the fitted tanh form (A/B)
   bool use_chain = true;
   // Batches below this take the one-kernel-per-GEMM path (option "chain_min_batch" / VPB_CHAIN_MIN_BATCH): measured on B200

@@ -174,7 +174,7 @@ def test_chain_is_bit_identical(golden_dir, name, batches):
         m.set_option("chain", 1 if chain == 1 else 0)
         m.set_option("ln_in_gemm", 1 if chain == 2 else 0)
         outs[chain].append([m(x[:n]).cpu().numpy() for n in batches])
-    m.set_option("ln_in_gemm", 1)
+    m.set_option("ln_in_gemm", 0)
     for a, b in zip(outs[1][0], outs[0][0]):
         assert np.array_equal(a, b)
     for a, b in zip(outs[1][0], outs[1][1]):
@@ -185,7 +185,7 @@ def test_chain_is_bit_identical(golden_dir, name, batches):
     m.set_option("chain", 1)
     assert m.kernel_launches(1) == 1 + (1 + depth) + depth + 4      # gather, chains, attention, 2 deconv + 1x1 + decode (ViT-B: 30)
     m.set_option("chain", 0)
-    assert m.kernel_launches(1) == 2 + 5 * depth + 4 + 1            # + patch GEMM, 5 per block, last_norm (ViT-B: 67; round 1: 91)
+    assert m.kernel_launches(1) == 2 + 5 * depth + 4 + 2 * depth + 1      # one kernel per GEMM and per LayerNorm (ViT-B: 91)
 
 
 def test_gelu_erf_option_changes_nothing_visible(golden_dir):

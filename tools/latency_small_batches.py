@@ -2,7 +2,7 @@
 """Latency of small ragged batches (BASELINE configs[4]: a video stream's per-frame crop batch), CUDA-graph replay on:
   wide      one kernel per GEMM / LayerNorm, 256-wide tiles always (round 1)
   narrow    the same with 128-wide tiles while they fit one wave (pick_tile, the default for small batches)
-  narrow+ln-in-gemm  narrow + LayerNorm and its consumer GEMM (qkv / fc1) as one two-stage chained launch (the default below 48 crops)
+  narrow+ln-in-gemm  narrow + LayerNorm and its consumer GEMM (qkv / fc1) as one two-stage chained launch (option ln_in_gemm; slower, off)
   (LayerNorm in the TAIL of the residual GEMMs, option ln_fused, lost at every batch size: 1.03 vs 0.71 ms at 1 crop, 3.16 vs 2.73 at 64)
   chained   chained launches (chain.cuh; the default from 48 crops on)
 Synchronous host-visible latency per call and back-to-back time per call (no sync between calls)."""
@@ -45,4 +45,4 @@ for n in (1, 2, 4, 6, 9, 12, 16, 24, 32, 48, 64):
             e1.record(); torch.cuda.synchronize()
             out.append(f"{name} {lat * 1e3:.3f} / {e0.elapsed_time(e1) / 30:.3f}{'' if same else ' (DIFFERS!)'}")
     print(f"crops/call={n:2d}  latency / back-to-back ms:  " + "  |  ".join(out))
-L.vpb_debug_gemm(0, None); m.set_option("ln_fused", 0); m.set_option("ln_in_gemm", 1); m.set_option("chain", 1)
+L.vpb_debug_gemm(0, None); m.set_option("ln_fused", 0); m.set_option("ln_in_gemm", 0); m.set_option("chain", 1)
