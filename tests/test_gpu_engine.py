@@ -274,3 +274,28 @@ def test_shard_pipeline_single_rank_matches_infer_crops(golden_dir):
     got.append(pipe.wait((len(batches) - 1) % 2).numpy().copy())
     for w, k in zip(want, got):
         assert np.array_equal(w, k)
+
+
+def test_narrow_tiles_for_small_batches_are_bit_identical(golden_dir):
+    """Below ~16 crops the proj / fc2 / patch (and for <= 5 crops also qkv / fc1) GEMMs run 128-wide tiles instead of 256-wide ones
+    (engine.cu pick_tile: twice the tiles, half the K-loop time each).  The accumulation order of an output element does not depend
+    on the tile shape, so heatmaps, keypoints and argmax must not change by a bit (debug flag 16 forces the wide tiles)."""
+    import ctypes as C
+
+    from easy_vitpose_b200 import _lib
+    g = np.load(os.path.join(golden_dir, "fwd_b_coco.npz"))
+    m, _ = _engine(g, max_batch=9)
+    m.set_option("chain", 0)
+    x = torch.from_numpy(O.make_crops(9, 4711)).cuda()
+    org = torch.tensor([[200, 300]] * 9, dtype=torch.int32)
+    outs = {}
+    try:
+        for wide in (0, 1):
+            _lib.lib().vpb_debug_gemm((16 << 8) if wide else 0, None)
+            m.set_option("chain", 0)                                      # drops the captured graphs: they embed the tile choice
+            outs[wide] = [tuple(t.cpu().numpy() for t in m.infer_crops(x[:n], org[:n], return_heatmaps=True)) for n in (1, 4, 9)]
+    finally:
+        _lib.lib().vpb_debug_gemm(0, None)
+    for a, b in zip(outs[0], outs[1]):
+        for u, v in zip(a, b):
+            assert np.array_equal(u, v)
