@@ -22,6 +22,14 @@ constexpr int HM_H = 64, HM_W = 48, HM_PIX = HM_H * HM_W;
 __device__ __constant__ float c_gauss11[6] = {0x1.20c256p-7f, 0x1.bcb86ap-6f, 0x1.0ab50ap-4f,
                                               0x1.f2464cp-4f, 0x1.6a7e1ep-3f, 0x1.9ac20ap-3f};
 
+// Modulation kernels other than 11 (keypoints_from_heatmaps' `kernel` argument, top_down_eval.py:499; 17 for sigma = 3): taps by
+// distance from the centre, filled on the host (engine.cu: gauss_taps) the way cv2.getGaussianKernel(k, 0) computes them.
+constexpr int MAX_RADIUS = 17;                              // kernel sizes up to 35
+struct GaussTaps {
+  int radius = 5;
+  float t[MAX_RADIUS + 1] = {};                             // t[d] = tap at distance d from the centre
+};
+
 __device__ __forceinline__ int reflect101(int i, int n) {
   i = i < 0 ? -i : i;
   return i >= n ? 2 * (n - 1) - i : i;
@@ -47,6 +55,7 @@ struct DecodeParams {
   // (int64 / float64 arrays promote it to float64); both null = the VitInference form above (scale = org, centre = org // 2)
   const float* cs32 = nullptr;
   const double* cs64 = nullptr;
+  GaussTaps taps;          // read by the GENERIC instantiation only (kernel != 11)
 };
 
 // coords (heatmap pixels) -> image pixels: x * (scale / (W-1 or W)) + centre - scale * 0.5, evaluated left to right with one
@@ -70,9 +79,14 @@ __device__ __forceinline__ void transform_cs(float xr, float yr, int n_i, const 
 
 // warps (= maps) per CTA: 4 gives 272 CTAs for 64 x 17 maps (two per SM, 8 warps with 24 16-byte loads each in flight) where 8
 // left 12 of the 148 SMs idle and one CTA per SM
+// GENERIC = false: the 11x11 kernel every reference config uses, taps and trip counts compiled in (the engine's hot path);
+// GENERIC = true: radius and taps from p.taps.
 constexpr int DECODE_WARPS = 4;
+template <bool GENERIC>
 __global__ void __launch_bounds__(DECODE_WARPS * 32) decode_heatmaps(const DecodeParams p) {
-  __shared__ float s_rowpass[DECODE_WARPS][7][11];
+  __shared__ float s_rowpass[DECODE_WARPS][7][GENERIC ? 2 * MAX_RADIUS + 1 : 11];
+  const int R = GENERIC ? p.taps.radius : 5, KS = 2 * R + 1;
+  auto tap = [&](int d) { return GENERIC ? p.taps.t[d] : c_gauss11[5 - d]; };
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.x * DECODE_WARPS + wib;            // map index n*K + k
   const int total = p.n * p.k;
@@ -133,17 +147,17 @@ __global__ void __launch_bounds__(DECODE_WARPS * 32) decode_heatmaps(const Decod
   }
 
   // ---- row pass of the separable blur: 7 points x 11 rows, one (point,row) per lane per round
-  for (int tsk = lane; tsk < 77; tsk += 32) {
-    const int pt = tsk / 11, r = tsk % 11;
+  for (int tsk = lane; tsk < 7 * KS; tsk += 32) {
+    const int pt = tsk / KS, r = tsk % KS;
     const float* m = pmap[0];
     int cx = ptx[0], cy = pty[0];
 #pragma unroll
     for (int i = 1; i < 7; ++i)
       if (pt == i) { m = pmap[i]; cx = ptx[i]; cy = pty[i]; }
-    const float* rowp = m + reflect101(cy - 5 + r, HM_H) * HM_W;
+    const float* rowp = m + reflect101(cy - R + r, HM_H) * HM_W;
     float acc = 0.0f;
 #pragma unroll
-    for (int j = 0; j < 11; ++j) acc = __fmaf_rn(c_gauss11[j < 6 ? j : 10 - j], __ldg(rowp + reflect101(cx - 5 + j, HM_W)), acc);
+    for (int j = 0; j < KS; ++j) acc = __fmaf_rn(tap(j < R ? R - j : j - R), __ldg(rowp + reflect101(cx - R + j, HM_W)), acc);
     s_rowpass[wib][pt][r] = acc;
   }
   __syncwarp();
@@ -151,9 +165,9 @@ __global__ void __launch_bounds__(DECODE_WARPS * 32) decode_heatmaps(const Decod
   float l = 0.0f;
   if (lane < 7) {
     const float* rp = s_rowpass[wib][lane];
-    float acc = __fmul_rn(c_gauss11[5], rp[5]);
+    float acc = __fmul_rn(tap(0), rp[R]);
 #pragma unroll
-    for (int d = 1; d <= 5; ++d) acc = __fmaf_rn(c_gauss11[5 - d], __fadd_rn(rp[5 + d], rp[5 - d]), acc);
+    for (int d = 1; d <= R; ++d) acc = __fmaf_rn(tap(d), __fadd_rn(rp[R + d], rp[R - d]), acc);
     l = logf(fminf(fmaxf(acc, 1e-3f), 50.0f));
   }
   const float i_ = __shfl_sync(0xffffffffu, l, 0), ix1 = __shfl_sync(0xffffffffu, l, 1);
@@ -208,22 +222,29 @@ __global__ void __launch_bounds__(DECODE_WARPS * 32) decode_heatmaps(const Decod
 
 // ------------------------------------------------------------------------------------------------
 // The decode modes VitInference never selects, for mmpose-style callers of
-// keypoints_from_heatmaps (vit_utils/top_down_eval.py:493-641) with use_udp=False:
+// keypoints_from_heatmaps (vit_utils/top_down_eval.py:493-641):
 //   mode 0  post_process=None       argmax only                                           :598
 //   mode 1  'default'               +-0.25 px towards the higher neighbour                  :617-631
 //   mode 2  'unbiased'              zero-padded Gaussian modulation + log + _taylor          :600-607, :315-350, :416-456
 //   mode 3  'megvii'                modulation first, argmax of the modulated map, +-0.25 + 0.5, score / 255 + 0.5   :573-574,:629-639
+//   mode 5  use_udp + 'CombinedTarget'  (:580-593) maps come in triples (response, offset x, offset y): the response map is
+//           blurred with a (2*kernel+1)^2 Gaussian and arg-maxed, the two offset maps with kernel^2; the offsets at the arg-max,
+//           times valid_radius_factor * H, are added to the integer location; transform_preds in its UDP form.
 // One CTA per map (the modulation needs every pixel and the global maximum of the blurred map); the map lives in shared memory.
-// The blur is cv2's with a zero border (what `_gaussian_blur`'s padding amounts to), same accumulation order as above.
-enum : int { DECODE_NONE = 0, DECODE_DEFAULT = 1, DECODE_UNBIASED = 2, DECODE_MEGVII = 3, DECODE_DARK_UDP = 4 };
+// Modes 2/3 blur with a zero border (what `_gaussian_blur`'s padding amounts to), mode 5 with cv2's default BORDER_REFLECT_101;
+// same accumulation order as above.
+enum : int { DECODE_NONE = 0, DECODE_DEFAULT = 1, DECODE_UNBIASED = 2, DECODE_MEGVII = 3, DECODE_DARK_UDP = 4, DECODE_COMBINED = 5 };
 
 struct DecodeModesParams {
-  const float* heatmaps;   // [N,K,64,48]
+  const float* heatmaps;   // [N,K,64,48]; mode 5: [N,3K,64,48]
   const float* cs32;       // [N,4] (centre_x, centre_y, scale_x, scale_y) float32, or
   const double* cs64;      // the same as float64 (exactly one of the two is non-null)
   float* kpts;             // [N,K,3] (y, x, score)
   int* idx;                // [N,K] flat argmax of the map the coordinates were read from (may be nullptr)
   int n, k, mode;
+  GaussTaps taps;          // `kernel`
+  GaussTaps taps_wide;     // 2 * kernel + 1 (mode 5: the response map)
+  float valid_radius;      // mode 5: float32(valid_radius_factor * H)
 };
 
 // np.argmax / np.amax over the 3072 values in shared memory; result broadcast to every thread
@@ -247,6 +268,73 @@ __device__ __forceinline__ void block_argmax(const float* s_map, float* s_rv, in
     if (arg_better(s_rv[j], s_ri[j], bv, bi)) { bv = s_rv[j]; bi = s_ri[j]; }
 }
 
+// cv2.GaussianBlur(map, (k, k), 0) (BORDER_REFLECT_101) at one point, by one warp; the value is returned on every lane
+__device__ __forceinline__ float blur_point_reflect(const float* m, int cx, int cy, const GaussTaps& tp, float* s_rows) {
+  const int lane = threadIdx.x & 31, R = tp.radius;
+  for (int r = lane; r <= 2 * R; r += 32) {
+    const float* rowp = m + reflect101(cy - R + r, HM_H) * HM_W;
+    float acc = 0.0f;
+    for (int j = 0; j <= 2 * R; ++j) acc = __fmaf_rn(tp.t[j < R ? R - j : j - R], __ldg(rowp + reflect101(cx - R + j, HM_W)), acc);
+    s_rows[r] = acc;
+  }
+  __syncwarp();
+  float acc = __fmul_rn(tp.t[0], s_rows[R]);
+  for (int d = 1; d <= R; ++d) acc = __fmaf_rn(tp.t[d], __fadd_rn(s_rows[R + d], s_rows[R - d]), acc);
+  return acc;
+}
+
+// mode 5, one CTA per keypoint: g = n * K + k, maps 3g (response), 3g + 1 (offset x), 3g + 2 (offset y)
+__device__ __forceinline__ void decode_combined(const DecodeModesParams& p, float* s_a, float* s_b, float* s_rv, int* s_ri) {
+  __shared__ float s_rows[2][2 * MAX_RADIUS + 1];
+  __shared__ float s_off[2];
+  const int g = blockIdx.x, tid = threadIdx.x;
+  {
+    const float4* h4 = reinterpret_cast<const float4*>(p.heatmaps + static_cast<size_t>(3 * g) * HM_PIX);
+    for (int i = tid; i < HM_PIX / 4; i += 256) reinterpret_cast<float4*>(s_a)[i] = __ldg(h4 + i);
+  }
+  __syncthreads();
+  const int R = p.taps_wide.radius;
+  for (int i = tid; i < HM_PIX; i += 256) {
+    const int y = i / HM_W, x = i % HM_W;
+    float acc = 0.0f;
+    for (int j = 0; j <= 2 * R; ++j)
+      acc = __fmaf_rn(p.taps_wide.t[j < R ? R - j : j - R], s_a[y * HM_W + reflect101(x - R + j, HM_W)], acc);
+    s_b[i] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < HM_PIX; i += 256) {
+    const int y = i / HM_W, x = i % HM_W;
+    float acc = __fmul_rn(p.taps_wide.t[0], s_b[i]);
+    for (int d = 1; d <= R; ++d)
+      acc = __fmaf_rn(p.taps_wide.t[d], __fadd_rn(s_b[reflect101(y + d, HM_H) * HM_W + x], s_b[reflect101(y - d, HM_H) * HM_W + x]), acc);
+    s_a[i] = acc;
+  }
+  __syncthreads();
+  float mx; int amax;
+  block_argmax(s_a, s_rv, s_ri, mx, amax);
+  // offsets are read at flat index x + y*W + W*H*g of the [N*K, H*W] offset planes (:588-591); with the (-1,-1) sentinel that
+  // index is one row and one pixel before this keypoint's plane: pixel (W-1, H-2) of the previous keypoint's plane, and for
+  // g = 0 numpy's negative index wraps to the last plane of the call
+  int src = g, ox = amax % HM_W, oy = amax / HM_W;
+  float cx = static_cast<float>(ox), cy = static_cast<float>(oy);
+  if (!(mx > 0.0f)) {
+    cx = cy = -1.0f;
+    src = (g + p.n * p.k - 1) % (p.n * p.k); ox = HM_W - 1; oy = HM_H - 2;
+  }
+  const int w = tid >> 5;
+  if (w < 2) {
+    const float v = blur_point_reflect(p.heatmaps + static_cast<size_t>(3 * src + 1 + w) * HM_PIX, ox, oy, p.taps, s_rows[w]);
+    if ((tid & 31) == 0) s_off[w] = __fmul_rn(v, p.valid_radius);
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  float X, Y;
+  transform_cs(__fadd_rn(cx, s_off[0]), __fadd_rn(cy, s_off[1]), g / p.k, p.cs32, p.cs64, true, X, Y);
+  float* o = p.kpts + static_cast<size_t>(g) * 3;
+  o[0] = Y; o[1] = X; o[2] = mx;
+  if (p.idx != nullptr) p.idx[g] = amax;
+}
+
 __global__ void __launch_bounds__(256) decode_modes(const DecodeModesParams p) {
   __shared__ float s_a[HM_PIX];
   __shared__ float s_b[HM_PIX];
@@ -255,6 +343,7 @@ __global__ void __launch_bounds__(256) decode_modes(const DecodeModesParams p) {
   const int g = blockIdx.x, tid = threadIdx.x;
   pdl_launch_dependents();
   pdl_wait();
+  if (p.mode == DECODE_COMBINED) { decode_combined(p, s_a, s_b, s_rv, s_ri); return; }
   {
     const float4* h4 = reinterpret_cast<const float4*>(p.heatmaps + static_cast<size_t>(g) * HM_PIX);
     for (int i = tid; i < HM_PIX / 4; i += 256) reinterpret_cast<float4*>(s_a)[i] = __ldg(h4 + i);
@@ -263,25 +352,24 @@ __global__ void __launch_bounds__(256) decode_modes(const DecodeModesParams p) {
   float mx; int amax;
   block_argmax(s_a, s_rv, s_ri, mx, amax);                  // raw map: np.argmax, np.amax (= np.max: NaN wins both)
   if (p.mode == DECODE_UNBIASED || p.mode == DECODE_MEGVII) {
-    // _gaussian_blur (:416-456): zero-padded 11x11 blur, then *= origin_max / max(blurred)
+    // _gaussian_blur (:416-456): zero-padded kernel x kernel blur, then *= origin_max / max(blurred)
+    const int R = p.taps.radius;
     for (int i = tid; i < HM_PIX; i += 256) {
       const int y = i / HM_W, x = i % HM_W;
       float acc = 0.0f;
-#pragma unroll
-      for (int j = 0; j < 11; ++j) {
-        const int xx = x - 5 + j;
-        acc = __fmaf_rn(c_gauss11[j < 6 ? j : 10 - j], (xx >= 0 && xx < HM_W) ? s_a[y * HM_W + xx] : 0.0f, acc);
+      for (int j = 0; j <= 2 * R; ++j) {
+        const int xx = x - R + j;
+        acc = __fmaf_rn(p.taps.t[j < R ? R - j : j - R], (xx >= 0 && xx < HM_W) ? s_a[y * HM_W + xx] : 0.0f, acc);
       }
       s_b[i] = acc;
     }
     __syncthreads();
     for (int i = tid; i < HM_PIX; i += 256) {
       const int y = i / HM_W, x = i % HM_W;
-      float acc = __fmul_rn(c_gauss11[5], s_b[i]);
-#pragma unroll
-      for (int d = 1; d <= 5; ++d) {
+      float acc = __fmul_rn(p.taps.t[0], s_b[i]);
+      for (int d = 1; d <= R; ++d) {
         const float lo = y - d >= 0 ? s_b[(y - d) * HM_W + x] : 0.0f, hi = y + d < HM_H ? s_b[(y + d) * HM_W + x] : 0.0f;
-        acc = __fmaf_rn(c_gauss11[5 - d], __fadd_rn(hi, lo), acc);
+        acc = __fmaf_rn(p.taps.t[d], __fadd_rn(hi, lo), acc);
       }
       s_a[i] = acc;                                          // the raw map is no longer needed
     }

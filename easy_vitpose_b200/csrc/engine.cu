@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1018,7 +1019,7 @@ static int decode_launch(const float* d_heatmaps, int32_t n, int32_t k, const in
   DecodeParams p;
   p.heatmaps = d_heatmaps; p.org_wh = d_org_wh; p.kpts = d_kpts; p.idx = d_idx; p.n = n; p.k = k; p.wrap_batch = wrap_batch;
   p.offs_yx = d_offs_yx;
-  launch_k(decode_heatmaps, dim3(cdiv(static_cast<long long>(n) * k, DECODE_WARPS)), dim3(DECODE_WARPS * 32), 0, static_cast<cudaStream_t>(stream), p);
+  launch_k(decode_heatmaps<false>, dim3(cdiv(static_cast<long long>(n) * k, DECODE_WARPS)), dim3(DECODE_WARPS * 32), 0, static_cast<cudaStream_t>(stream), p);
   CU_TRY(cudaGetLastError());
   return VPB_OK;
 }
@@ -1048,25 +1049,56 @@ extern "C" int vpb_flip_back(const float* d_in, int32_t n, int32_t k, const int3
   CU_TRY(cudaGetLastError());
   return VPB_OK;
 }
-extern "C" int vpb_decode_modes(const float* d_heatmaps, int32_t n, int32_t k, int32_t mode, const float* d_cs32, const double* d_cs64,
-                                float* d_kpts, int32_t* d_idx, void* stream) {
+// cv2.getGaussianKernel(ksize, sigma <= 0) for a CV_32F image: sigma = 0.3 * ((ksize - 1) * 0.5 - 1) + 0.8, exp(-d^2 / (2 sigma^2))
+// normalised to sum 1 in double, stored as float; indexed by the distance from the centre.  ksize odd, 11..35 (cv2 switches to
+// fixed tables at 7 and below, and 9 does not come out bit-exact: oracle/make_golden_modes.py).
+static bool gauss_taps(int ksize, GaussTaps& tp) {
+  if (ksize < 11 || ksize > 2 * MAX_RADIUS + 1 || ksize % 2 == 0) return false;
+  const int r = ksize / 2;
+  const double sigma = 0.3 * ((ksize - 1) * 0.5 - 1.0) + 0.8;
+  double v[2 * MAX_RADIUS + 1], sum = 0.0;
+  for (int i = 0; i < ksize; ++i) {
+    const double x = i - (ksize - 1) / 2.0;
+    v[i] = std::exp(-(x * x) / (2.0 * sigma * sigma));
+    sum += v[i];
+  }
+  tp.radius = r;
+  for (int d = 0; d <= r; ++d) tp.t[d] = static_cast<float>(v[r + d] / sum);
+  return true;
+}
+
+extern "C" int vpb_decode_modes_ex(const float* d_heatmaps, int32_t n, int32_t k, int32_t mode, int32_t kernel, float valid_radius,
+                                   const float* d_cs32, const double* d_cs64, float* d_kpts, int32_t* d_idx, void* stream) {
   if (!d_heatmaps || !d_kpts || (d_cs32 == nullptr) == (d_cs64 == nullptr))
     return fail(VPB_ERR_ARG, "vpb_decode_modes: null pointer, or not exactly one of d_cs32 / d_cs64");
-  if (n < 0 || k < 1 || mode < DECODE_NONE || mode > DECODE_DARK_UDP) return fail(VPB_ERR_ARG, "vpb_decode_modes: n=%d k=%d mode=%d", n, k, mode);
+  if (n < 0 || k < 1 || mode < DECODE_NONE || mode > DECODE_COMBINED) return fail(VPB_ERR_ARG, "vpb_decode_modes: n=%d k=%d mode=%d", n, k, mode);
+  const bool blurs = mode >= DECODE_UNBIASED;
+  GaussTaps taps, wide;
+  if (blurs && !gauss_taps(kernel, taps)) return fail(VPB_ERR_ARG, "vpb_decode_modes: kernel=%d (odd, 11..%d)", kernel, 2 * MAX_RADIUS + 1);
+  if (mode == DECODE_COMBINED && !gauss_taps(2 * kernel + 1, wide))
+    return fail(VPB_ERR_ARG, "vpb_decode_modes: CombinedTarget blurs with 2*kernel+1 = %d (limit %d)", 2 * kernel + 1, 2 * MAX_RADIUS + 1);
   if (n == 0) return VPB_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (mode == DECODE_DARK_UDP) {                            // one reference call on the whole array: wrap_batch = 1
     DecodeParams p;
     p.heatmaps = d_heatmaps; p.org_wh = nullptr; p.kpts = d_kpts; p.idx = d_idx; p.n = n; p.k = k; p.wrap_batch = 1; p.offs_yx = nullptr;
-    p.cs32 = d_cs32; p.cs64 = d_cs64;
-    CU_TRY(launch_k(decode_heatmaps, dim3(cdiv(static_cast<long long>(n) * k, DECODE_WARPS)), dim3(DECODE_WARPS * 32), 0, st, p));
+    p.cs32 = d_cs32; p.cs64 = d_cs64; p.taps = taps;
+    const dim3 grid(cdiv(static_cast<long long>(n) * k, DECODE_WARPS)), block(DECODE_WARPS * 32);
+    if (kernel == 11) { CU_TRY(launch_k(decode_heatmaps<false>, grid, block, 0, st, p)); }
+    else              { CU_TRY(launch_k(decode_heatmaps<true>, grid, block, 0, st, p)); }
   } else {
     DecodeModesParams p;
     p.heatmaps = d_heatmaps; p.cs32 = d_cs32; p.cs64 = d_cs64; p.kpts = d_kpts; p.idx = d_idx; p.n = n; p.k = k; p.mode = mode;
+    p.taps = taps; p.taps_wide = wide; p.valid_radius = valid_radius;
     CU_TRY(launch_k(decode_modes, dim3(n * k), dim3(256), 0, st, p));
   }
   CU_TRY(cudaGetLastError());
   return VPB_OK;
+}
+extern "C" int vpb_decode_modes(const float* d_heatmaps, int32_t n, int32_t k, int32_t mode, const float* d_cs32, const double* d_cs64,
+                                float* d_kpts, int32_t* d_idx, void* stream) {
+  if (mode == DECODE_COMBINED) return fail(VPB_ERR_ARG, "vpb_decode_modes: CombinedTarget needs vpb_decode_modes_ex (valid_radius)");
+  return vpb_decode_modes_ex(d_heatmaps, n, k, mode, 11, 0.0f, d_cs32, d_cs64, d_kpts, d_idx, stream);
 }
 extern "C" int vpb_decode_frame(const float* d_heatmaps, int32_t n, int32_t k, const int32_t* d_org_wh, const int32_t* d_offs_yx,
                                 float* d_kpts, int32_t* d_idx, int32_t wrap_batch, void* stream) {

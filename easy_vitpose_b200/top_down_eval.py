@@ -4,7 +4,7 @@ reference function at easy_ViTPose/vit_utils/top_down_eval.py:493-641.
 `decode_heatmaps` is the fast form of the branch VitInference takes (unbiased=True, use_udp=True: DARK/UDP with
 centre = scale // 2, easy_ViTPose/inference.py:200-203).  `keypoints_from_heatmaps` covers every GaussianHeatmap
 branch of the reference function with general centre / scale; `decode_topdown` is
-TopdownHeatmapBaseHead.decode on top of it.  CombinedTarget and modulation kernels other than 11 raise.
+TopdownHeatmapBaseHead.decode on top of it, including modulation kernels 11..35 and target_type='CombinedTarget'.
 """
 from __future__ import annotations
 
@@ -59,9 +59,11 @@ def keypoints_from_heatmaps(heatmaps, center, scale, unbiased=False, post_proces
     (preds [N,K,2] (x,y) float32, maxvals [N,K,1] float32) as numpy arrays.  `heatmaps` may be a numpy array or a CUDA tensor
     [N,K,64,48] and is never modified (the reference works on a copy, :545).
 
-    Every GaussianHeatmap branch is built: post_process None / 'default' / 'unbiased' / 'megvii' with use_udp=False, and the
-    DARK/UDP branch (use_udp=True; the one VitInference.postprocess takes).  `kernel` must be 11 (what every reference config
-    uses: the tap table is compiled in); target_type='CombinedTarget' (:580-593) is not built and raises."""
+    Every branch is built: post_process None / 'default' / 'unbiased' / 'megvii' with use_udp=False, the DARK/UDP branch
+    (use_udp=True; the one VitInference.postprocess takes) and use_udp=True with target_type='CombinedTarget' (:580-593, heatmaps
+    [N,3K,64,48] -> K keypoints).  `kernel` is any odd size 11..35 (cv2 builds smaller kernels from fixed tables; not built);
+    CombinedTarget blurs the response maps with 2*kernel+1, so kernel <= 17 there.  Like the reference, CombinedTarget only
+    accepts N = 1: its index arithmetic (:589) does not broadcast for larger N."""
     # the reference's conflict checks (:548-553) and config normalisation (:556-579), deprecation warnings dropped
     if unbiased:
         assert post_process not in [False, None, "megvii"]
@@ -75,32 +77,39 @@ def keypoints_from_heatmaps(heatmaps, center, scale, unbiased=False, post_proces
         post_process = "unbiased" if unbiased is True else "default"
     elif post_process == "default" and unbiased is True:
         post_process = "unbiased"
-    if str(target_type).lower() == "combinedtarget" and use_udp:
-        raise NotImplementedError("target_type='CombinedTarget' is not built (no reference config uses it)")
-    if use_udp and str(target_type).lower() != "gaussianheatmap":
+    combined = bool(use_udp) and str(target_type).lower() == "combinedtarget"
+    if use_udp and not combined and str(target_type).lower() != "gaussianheatmap":
         raise ValueError("target_type should be either 'GaussianHeatmap' or 'CombinedTarget'")
     if post_process not in _MODES:
         raise ValueError(f"unknown post_process {post_process!r}")
-    if kernel != 11 and (use_udp or post_process in ("unbiased", "megvii")):
-        raise NotImplementedError("only the 11x11 modulation kernel (every reference config: modulate_kernel=11) is built")
+    blurs = use_udp or post_process in ("unbiased", "megvii")
+    if blurs and (int(kernel) != kernel or kernel % 2 == 0 or not 11 <= kernel <= (17 if combined else 35)):
+        raise NotImplementedError(f"modulation kernel {kernel}: odd sizes 11..{17 if combined else 35} are built")
 
+    if len(heatmaps.shape) != 4 or tuple(heatmaps.shape[2:]) != (64, 48):
+        raise ValueError(f"expected [N,K,64,48], got {tuple(heatmaps.shape)}")
+    N, K = (int(v) for v in heatmaps.shape[:2])
+    valid_radius = 0.0
+    if combined:
+        if N != 1 or K % 3:
+            # the reference adds an arange of N*K/3 plane offsets to an [N, K/3] index array (:589) and reshapes to K // 3 (:590)
+            raise ValueError(f"CombinedTarget: operands could not be broadcast together for N={N}, K={K} (reference :589-590)")
+        K //= 3
+        valid_radius = float(np.float32(valid_radius_factor * heatmaps.shape[2]))
     hm = heatmaps if isinstance(heatmaps, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(heatmaps, np.float32))
     if not hm.is_cuda:
         hm = hm.cuda()
-    if hm.dim() != 4 or tuple(hm.shape[2:]) != (64, 48):
-        raise ValueError(f"expected [N,K,64,48], got {tuple(hm.shape)}")
     hm = hm.to(torch.float32).contiguous()
-    N, K = hm.shape[:2]
     cs32, cs64 = _centre_scale(center, scale, N, hm.device)
     kp = torch.empty((N, K, 3), dtype=torch.float32, device=hm.device)
     idx = torch.empty((N, K), dtype=torch.int32, device=hm.device)
-    mode = 4 if use_udp else _MODES[post_process]
+    mode = (5 if combined else 4) if use_udp else _MODES[post_process]
     with torch.cuda.device(hm.device):
         st = C.c_void_p(torch.cuda.current_stream(hm.device).cuda_stream)
-        _lib.check(_lib.lib().vpb_decode_modes(C.c_void_p(hm.data_ptr()), N, K, mode,
-                                               C.c_void_p(cs32.data_ptr()) if cs32 is not None else None,
-                                               C.c_void_p(cs64.data_ptr()) if cs64 is not None else None,
-                                               C.c_void_p(kp.data_ptr()), C.c_void_p(idx.data_ptr()), st))
+        _lib.check(_lib.lib().vpb_decode_modes_ex(C.c_void_p(hm.data_ptr()), N, K, mode, int(kernel) if blurs else 11, valid_radius,
+                                                  C.c_void_p(cs32.data_ptr()) if cs32 is not None else None,
+                                                  C.c_void_p(cs64.data_ptr()) if cs64 is not None else None,
+                                                  C.c_void_p(kp.data_ptr()), C.c_void_p(idx.data_ptr()), st))
     kp = kp.cpu().numpy()
     out = (np.ascontiguousarray(kp[:, :, 1::-1]), kp[:, :, 2:3].copy())
     return out + (idx.cpu().numpy(),) if return_idx else out

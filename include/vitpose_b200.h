@@ -95,14 +95,23 @@ int vpb_flip_back(const float* d_in, int32_t n, int32_t k, const int32_t* d_perm
  * and 4 = use_udp=True DARK (:576-579) with arbitrary centre / scale.  Exactly one of d_cs32 (f32 [n,4]) / d_cs64 (f64 [n,4]) holds
  * (centre_x, centre_y, scale_x, scale_y) per crop: float32 arrays keep numpy's arithmetic in float32, int64 / float64 arrays
  * promote it to float64.  Output layout as vpb_decode: d_kpts f32 [n,k,3] (y, x, score), d_idx i32 [n,k] or NULL.
- * CombinedTarget (:580-593) is not built: no reference config uses it. */
+ * vpb_decode_modes is the kernel = 11 form (every reference config: modulate_kernel=11).  vpb_decode_modes_ex adds
+ *   kernel        the `kernel` argument (:499): odd, 11..35 (17 for sigma = 3); used by modes 2-5;
+ *   mode 5        use_udp=True with target_type='CombinedTarget' (:580-593): d_heatmaps is f32 [n,3k,64,48], triples of
+ *                 (response, offset x, offset y); 2*kernel+1 <= 35; valid_radius = (float)(valid_radius_factor * 64) (:586);
+ *                 the (-1,-1) sentinel reads its offsets one row and one pixel before the keypoint's plane, wrapping to the
+ *                 last plane of the call for the first keypoint, as numpy's flat index does.  (The reference's own index
+ *                 arithmetic (:589) only broadcasts for n = 1; n > 1 here is that formula with the intended shape.) */
 #define VPB_DECODE_NONE 0
 #define VPB_DECODE_DEFAULT 1
 #define VPB_DECODE_UNBIASED 2
 #define VPB_DECODE_MEGVII 3
 #define VPB_DECODE_DARK_UDP 4
+#define VPB_DECODE_COMBINED 5
 int vpb_decode_modes(const float* d_heatmaps, int32_t n, int32_t k, int32_t mode, const float* d_cs32, const double* d_cs64,
                      float* d_kpts, int32_t* d_idx, void* stream);
+int vpb_decode_modes_ex(const float* d_heatmaps, int32_t n, int32_t k, int32_t mode, int32_t kernel, float valid_radius,
+                        const float* d_cs32, const double* d_cs64, float* d_kpts, int32_t* d_idx, void* stream);
 
 /* Replaces the model + postprocess part of VitInference._inference_torch (easy_ViTPose/inference.py:320-328)
  * for a whole batch of crops resident on the device.  d_heatmaps may be NULL. */

@@ -1,7 +1,7 @@
 """CPU restatement of the OTHER decode modes of keypoints_from_heatmaps  --  TEST INFRASTRUCTURE ONLY.
 
 SURVEY.md section 8 row f4.  The mode VitInference selects (unbiased=True, use_udp=True: DARK/UDP) lives in
-oracle/vitpose_oracle.py::decode_maps; this file restates the remaining non-CombinedTarget branches of
+oracle/vitpose_oracle.py::decode_maps; this file restates the remaining branches of
 easy_ViTPose/vit_utils/top_down_eval.py:493-641 and the general (float centre / scale) form of transform_preds:
 
   post_process=None                :598 `_get_max_preds` only                                  (:82-114)
@@ -10,11 +10,13 @@ easy_ViTPose/vit_utils/top_down_eval.py:493-641 and the general (float centre / 
                                    log, second-order Taylor step (`_taylor`, :315-350)
   post_process='megvii'            :573-574 blur first, then argmax of the BLURRED maps, +-0.25, +0.5, scores / 255 + 0.5
   use_udp=True (GaussianHeatmap)   :576-579 DARK/UDP with any centre / scale (decode_maps restricts centre to scale // 2)
+  use_udp=True (CombinedTarget)    :580-593 response maps blurred with 2*kernel+1, offset maps with kernel, offsets at the arg-max
+  kernel                           any odd modulation kernel 11..35 (cv2.getGaussianKernel computes those; <= 7 are fixed tables)
   transform_preds                  post_processing/post_transforms.py:150-194, both the /W (:186-187) and /(W-1) (:183-184) forms
 
 Parity: PINNED.  oracle/make_golden_modes.py runs the unmodified reference function on seeded maps for every mode and both
 centre/scale dtypes and stores its outputs in tests/golden/decode_modes.npz; tests/test_decode_modes_oracle.py holds this file
-to them (argmax, scores, 'default'/'megvii'/None coordinates bit-exact; Taylor modes to 1e-3 px).
+to them (argmax, scores, 'default'/'megvii'/None/CombinedTarget coordinates bit-exact; Taylor modes to 1e-3 px).
 
 Arithmetic types follow numpy >= 2 (NEP 50: python scalars are weak), which is what the reference runs under here:
 float32 centre/scale keep transform_preds in float32; int64 / float64 centre/scale promote it to float64.
@@ -44,6 +46,73 @@ def blur_zero_padded(h: np.ndarray, taps: np.ndarray) -> np.ndarray:
         pair = (rowpass[r + d:r + d + H] + rowpass[r - d:r - d + H]).astype(np.float32)
         acc = O._fma32(np.broadcast_to(taps[r + d], acc.shape), pair, acc)
     return acc
+
+
+def blur_reflect101(h: np.ndarray, taps: np.ndarray) -> np.ndarray:
+    """cv2.GaussianBlur(h, (k, k), 0) with its default BORDER_REFLECT_101 on the whole map (what CombinedTarget does in place,
+    :582-584); vitpose_oracle.blur_at is the same thing at single points."""
+    H, W = h.shape
+    r = (len(taps) - 1) // 2
+    p = np.pad(h.astype(np.float32), r, mode="reflect")
+    rowpass = np.zeros((H + 2 * r, W), np.float32)
+    for j in range(2 * r + 1):
+        rowpass = O._fma32(np.broadcast_to(taps[j], rowpass.shape), p[:, j:j + W], rowpass)
+    acc = (taps[r] * rowpass[r:r + H]).astype(np.float32)
+    for d in range(1, r + 1):
+        pair = (rowpass[r + d:r + d + H] + rowpass[r - d:r - d + H]).astype(np.float32)
+        acc = O._fma32(np.broadcast_to(taps[r + d], acc.shape), pair, acc)
+    return acc
+
+
+def combined_target(heatmaps: np.ndarray, center, scale, kernel: int = 11, valid_radius_factor: float = 0.0546875):
+    """use_udp=True, target_type='CombinedTarget' (:580-593): heatmaps [N,3K,H,W] -> (preds [N,K,2], maxvals [N,K,1], idx [N,K]).
+    The reference's `index += W * H * np.arange(0, N * K / 3)` (:589) only broadcasts for N = 1; for N > 1 this is the same
+    formula on the flattened [N*K] index (the shape the following reshape implies).  The flat index is formed in float32 like
+    the reference's (`index` inherits preds' dtype) and the (-1,-1) sentinel lands W + 1 elements before the keypoint's plane,
+    wrapping numpy-style for the very first one."""
+    N, K3, H, W = heatmaps.shape
+    if K3 % 3:
+        raise ValueError("CombinedTarget needs triples of maps")
+    K = K3 // 3
+    wide, narrow = O.gaussian_taps(2 * kernel + 1), O.gaussian_taps(kernel)
+    hm = np.empty((N, K3, H, W), np.float32)
+    for n in range(N):
+        for i in range(K3):
+            hm[n, i] = blur_reflect101(heatmaps[n, i], wide if i % 3 == 0 else narrow)
+    valid_radius = valid_radius_factor * H
+    offset_x = (hm[:, 1::3].reshape(-1) * np.float32(valid_radius)).astype(np.float32)
+    offset_y = (hm[:, 2::3].reshape(-1) * np.float32(valid_radius)).astype(np.float32)
+    preds = np.empty((N, K, 2), np.float32)
+    maxvals = np.empty((N, K, 1), np.float32)
+    idxs = np.empty((N, K), np.int32)
+    for n in range(N):
+        for k in range(K):
+            preds[n, k], maxvals[n, k, 0], idxs[n, k] = max_preds(hm[n, 3 * k])
+    index = (preds[..., 0] + preds[..., 1] * np.float32(W)).astype(np.float32).reshape(-1)
+    index = (index + (W * H * np.arange(0, N * K)).astype(np.float32)).astype(np.float32)
+    index = index.astype(int).reshape(N, K, 1)
+    preds = (preds + np.concatenate((offset_x[index], offset_y[index]), axis=2)).astype(np.float32)
+    for n in range(N):
+        preds[n] = transform(preds[n], center[n], scale[n], W, H, True)
+    return preds, maxvals, idxs
+
+
+def make_combined_maps(n: int, k: int, seed: int) -> np.ndarray:
+    """[n,3k,64,48] CombinedTarget-style input: response maps from vitpose_oracle.make_decode_maps (blobs, sentinels, ties, ...)
+    interleaved with smooth + noisy offset fields in about [-1, 1]."""
+    resp = O.make_decode_maps(n, k, seed)
+    rs = np.random.RandomState(seed + 7)
+    H, W = resp.shape[2:]
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    out = np.empty((n, 3 * k, H, W), np.float32)
+    out[:, 0::3] = resp
+    for i in range(n):
+        for j in range(k):
+            for c in (1, 2):
+                a, b, ph = rs.uniform(-0.2, 0.2, 3)
+                out[i, 3 * j + c] = (np.sin(a * xx + b * yy + ph * 10) * rs.uniform(0.2, 1.0)
+                                     + rs.standard_normal((H, W)) * 0.05).astype(np.float32)
+    return out
 
 
 def gaussian_modulate(h: np.ndarray, taps: np.ndarray) -> np.ndarray:
@@ -99,8 +168,11 @@ def transform(coords: np.ndarray, center, scale, W: int, H: int, use_udp: bool) 
 
 
 def keypoints_from_heatmaps(heatmaps: np.ndarray, center: np.ndarray, scale: np.ndarray, post_process="default",
-                            use_udp: bool = False, kernel: int = 11):
+                            use_udp: bool = False, kernel: int = 11, target_type: str = "GaussianHeatmap",
+                            valid_radius_factor: float = 0.0546875):
     """-> (preds [N,K,2] (x, y) float32, maxvals [N,K,1] float32, idx [N,K] int32 of the map the argmax was taken on)."""
+    if use_udp and target_type.lower() == "combinedtarget":
+        return combined_target(heatmaps, center, scale, kernel, valid_radius_factor)
     N, K, H, W = heatmaps.shape
     taps = O.gaussian_taps(kernel)
     preds = np.empty((N, K, 2), np.float32)

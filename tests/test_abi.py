@@ -104,11 +104,16 @@ def test_decode_api_fails_loudly_without_cuda_and_checks_its_config():
         keypoints_from_heatmaps(hm, c, s, post_process="megvii", use_udp=True)
     with pytest.raises(AssertionError):
         keypoints_from_heatmaps(hm, c, s, unbiased=True, post_process="megvii")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                                   # 17 maps are not triples (reference: reshape fails, :590)
         keypoints_from_heatmaps(hm, c, s, use_udp=True, target_type="CombinedTarget")
+    with pytest.raises(ValueError):                                   # N > 1: the reference's index arithmetic does not broadcast (:589)
+        keypoints_from_heatmaps(np.zeros((2, 18, 64, 48), np.float32), np.tile(c, (2, 1)), np.tile(s, (2, 1)), use_udp=True,
+                                target_type="CombinedTarget")
     with pytest.raises(ValueError):
         keypoints_from_heatmaps(hm, c, s, use_udp=True, target_type="nonsense")
-    with pytest.raises(NotImplementedError):
-        keypoints_from_heatmaps(hm, c, s, post_process="unbiased", kernel=17)
+    with pytest.raises(NotImplementedError):                          # cv2 builds kernels <= 7 from fixed tables: not built
+        keypoints_from_heatmaps(hm, c, s, post_process="unbiased", kernel=7)
+    with pytest.raises(NotImplementedError):                          # CombinedTarget blurs with 2 * kernel + 1 <= 35
+        keypoints_from_heatmaps(hm[:, :15], c, s, use_udp=True, kernel=19, target_type="CombinedTarget")
     with pytest.raises(ValueError):
         keypoints_from_heatmaps(hm, c, s, post_process="fancy")

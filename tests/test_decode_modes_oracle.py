@@ -33,6 +33,48 @@ def test_modes_match_reference(golden, pp, udp, tag):
         assert np.nanmax(np.abs(preds - ref)) < 1e-3                # Taylor modes: float32 inverse
 
 
+@pytest.mark.parametrize("pp,udp", [("unbiased", False), ("megvii", False), ("default", True)])
+@pytest.mark.parametrize("tag", ["f32", "i64"])
+def test_kernel_17_matches_reference(golden, pp, udp, tag):
+    g, maps = golden
+    c, s = (g["center32"], g["scale32"]) if tag == "f32" else (g["center64"], g["scale64"])
+    preds, maxvals, _ = M.keypoints_from_heatmaps(maps, c, s, post_process=pp, use_udp=udp, kernel=17)
+    key = f"k17_{pp}_{'udp' if udp else 'std'}_{tag}"
+    assert np.array_equal(maxvals, g[key + "_maxvals"], equal_nan=True)
+    ref = g[key + "_preds"]
+    if pp == "megvii":
+        assert np.array_equal(preds, ref, equal_nan=True)
+    else:
+        assert np.array_equal(np.isnan(preds), np.isnan(ref)) and np.nanmax(np.abs(preds - ref)) < 1e-3
+
+
+@pytest.mark.parametrize("kernel", [11, 17])
+@pytest.mark.parametrize("tag", ["f32", "i64"])
+def test_combined_target_matches_reference(golden, kernel, tag):
+    """One reference call per crop (the only batch size its index arithmetic accepts): bit-exact, sentinels included."""
+    g, _ = golden
+    N, KC, seed = (int(v) for v in g["meta_combined"])
+    cmaps = M.make_combined_maps(N, KC, seed)
+    c, s = (g["center32"], g["scale32"]) if tag == "f32" else (g["center64"], g["scale64"])
+    sentinels = 0
+    for n in range(N):
+        preds, maxvals, _ = M.combined_target(cmaps[n:n + 1], c[n:n + 1], s[n:n + 1], kernel)
+        assert np.array_equal(maxvals[0], g[f"comb_k{kernel}_{tag}_maxvals"][n], equal_nan=True)
+        assert np.array_equal(preds[0], g[f"comb_k{kernel}_{tag}_preds"][n], equal_nan=True)
+        sentinels += int((maxvals <= 0).sum())
+    assert sentinels >= 2                                          # the fixture exercises the (-1,-1) offset lookup
+
+
+def test_reflect_blur_is_blur_at_everywhere():
+    """The whole-map reflect-101 blur and the point form the DARK decode uses are the same arithmetic."""
+    maps = O.make_decode_maps(1, 3, 77)
+    for ks in (11, 23, 35):
+        taps = O.gaussian_taps(ks)
+        full = M.blur_reflect101(maps[0, 1], taps)
+        xs = np.array([0, 47, 5, 20, 47, 0]); ys = np.array([0, 63, 1, 30, 0, 63])
+        assert np.array_equal(O.blur_at(maps[0, 1], xs, ys, taps), full[ys, xs])
+
+
 def test_zero_padded_blur_properties():
     taps = O.gaussian_taps(11)
     h = np.zeros((64, 48), np.float32); h[30, 20] = 1.0

@@ -52,6 +52,79 @@ def test_modes_vs_oracle_on_more_maps(pp, udp):
     _check(preds, maxvals, op, om, exact=pp in (None, "default", "megvii") and not udp)
 
 
+@pytest.mark.parametrize("pp,udp", [("unbiased", False), ("megvii", False), ("default", True)])
+@pytest.mark.parametrize("tag", ["f32", "i64"])
+def test_kernel_17_vs_reference_fixture(golden_dir, pp, udp, tag):
+    """modulate_kernel = 17 (sigma = 3 configs): taps computed on the host like cv2.getGaussianKernel, same accumulation order."""
+    from easy_vitpose_b200 import keypoints_from_heatmaps
+    g = np.load(os.path.join(golden_dir, "decode_modes.npz"))
+    N, K, seed = (int(v) for v in g["meta"])
+    maps = O.make_decode_maps(N, K, seed)
+    c, s = (g["center32"], g["scale32"]) if tag == "f32" else (g["center64"], g["scale64"])
+    preds, maxvals = keypoints_from_heatmaps(maps, c, s, post_process=pp, use_udp=udp, kernel=17)
+    key = f"k17_{pp}_{'udp' if udp else 'std'}_{tag}"
+    _check(preds, maxvals, g[key + "_preds"], g[key + "_maxvals"], exact=pp == "megvii")
+
+
+@pytest.mark.parametrize("kernel", [13, 23, 35])
+def test_other_kernels_vs_oracle(kernel):
+    """Blurred values are bit-exact for every kernel size: megvii's scores and quarter-pixel coordinates come straight from them."""
+    from easy_vitpose_b200 import keypoints_from_heatmaps
+    N, K = 3, 10
+    maps = O.make_decode_maps(N, K, 1200 + kernel)
+    rs = np.random.RandomState(kernel)
+    c = rs.uniform(10, 800, (N, 2)).astype(np.float32); s = rs.uniform(40, 500, (N, 2)).astype(np.float32)
+    for pp, udp in (("megvii", False), ("unbiased", False), ("default", True)):
+        preds, maxvals, idx = keypoints_from_heatmaps(maps, c, s, post_process=pp, use_udp=udp, kernel=kernel, return_idx=True)
+        op, om, oi = M.keypoints_from_heatmaps(maps, c, s, post_process=pp, use_udp=udp, kernel=kernel)
+        assert np.array_equal(idx, oi)
+        _check(preds, maxvals, op, om, exact=pp == "megvii")
+
+
+@pytest.mark.parametrize("kernel", [11, 17])
+@pytest.mark.parametrize("tag", ["f32", "i64"])
+def test_combined_target_vs_reference_fixture(golden_dir, kernel, tag):
+    """use_udp=True, target_type='CombinedTarget' (top_down_eval.py:580-593), one call per crop like the fixture: blurred response
+    maximum, its index and the blurred offsets are bit-exact, so the keypoints are too."""
+    from easy_vitpose_b200 import keypoints_from_heatmaps
+    g = np.load(os.path.join(golden_dir, "decode_modes.npz"))
+    N, KC, seed = (int(v) for v in g["meta_combined"])
+    cmaps = M.make_combined_maps(N, KC, seed)
+    c, s = (g["center32"], g["scale32"]) if tag == "f32" else (g["center64"], g["scale64"])
+    for n in range(N):
+        preds, maxvals = keypoints_from_heatmaps(cmaps[n:n + 1], c[n:n + 1], s[n:n + 1], kernel=kernel, use_udp=True, target_type="CombinedTarget")
+        assert preds.shape == (1, KC, 2) and maxvals.shape == (1, KC, 1)
+        assert np.array_equal(maxvals[0], g[f"comb_k{kernel}_{tag}_maxvals"][n], equal_nan=True)
+        assert np.array_equal(preds[0], g[f"comb_k{kernel}_{tag}_preds"][n], equal_nan=True)
+
+
+def test_combined_target_batched_through_the_c_abi():
+    """The C ABI takes any n for mode 5 (the reference's formula on the flattened index): against the oracle, including the
+    sentinel's wrap to the last plane of the call."""
+    import ctypes as C
+    from easy_vitpose_b200 import _lib
+    N, KC = 3, 7
+    cmaps = M.make_combined_maps(N, KC, 4242)
+    cmaps[0, 0] = -np.abs(cmaps[0, 0]) - 0.1                                           # first keypoint of the call: sentinel
+    rs = np.random.RandomState(8)
+    c = rs.uniform(10, 800, (N, 2)).astype(np.float32); s = rs.uniform(40, 500, (N, 2)).astype(np.float32)
+    hm = torch.from_numpy(cmaps).cuda()
+    cs = torch.from_numpy(np.concatenate([c, s], 1)).cuda()
+    kp = torch.empty((N, KC, 3), dtype=torch.float32, device="cuda"); idx = torch.empty((N, KC), dtype=torch.int32, device="cuda")
+    for kernel in (11, 17):
+        _lib.check(_lib.lib().vpb_decode_modes_ex(C.c_void_p(hm.data_ptr()), N, KC, 5, kernel, float(np.float32(0.0546875 * 64)),
+                                                  C.c_void_p(cs.data_ptr()), None, C.c_void_p(kp.data_ptr()), C.c_void_p(idx.data_ptr()),
+                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        op, om, oi = M.combined_target(cmaps, c, s, kernel)
+        k = kp.cpu().numpy()
+        assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(k[..., 2:3], om, equal_nan=True)
+        assert np.array_equal(k[..., 1::-1], op, equal_nan=True)
+    assert _lib.lib().vpb_decode_modes_ex(C.c_void_p(hm.data_ptr()), N, KC, 5, 19, 3.5, C.c_void_p(cs.data_ptr()), None,
+                                          C.c_void_p(kp.data_ptr()), None, None) != 0   # 2 * 19 + 1 > 35
+    assert _lib.lib().vpb_decode_modes_ex(C.c_void_p(hm.data_ptr()), N, KC, 2, 12, 0.0, C.c_void_p(cs.data_ptr()), None,
+                                          C.c_void_p(kp.data_ptr()), None, None) != 0   # even kernel
+
+
 def test_config_normalisation_and_errors():
     from easy_vitpose_b200 import decode_topdown, keypoints_from_heatmaps
     maps = O.make_decode_maps(2, 17, 5)
@@ -64,10 +137,10 @@ def test_config_normalisation_and_errors():
     assert all(np.array_equal(x, y, equal_nan=True) for x, y in zip(d, e))
     with pytest.raises(AssertionError):
         keypoints_from_heatmaps(maps, c, s, post_process="megvii", use_udp=True)
+    with pytest.raises(ValueError):
+        keypoints_from_heatmaps(maps, c, s, use_udp=True, target_type="CombinedTarget")   # N = 2, 17 maps: as in the reference
     with pytest.raises(NotImplementedError):
-        keypoints_from_heatmaps(maps, c, s, use_udp=True, target_type="CombinedTarget")
-    with pytest.raises(NotImplementedError):
-        keypoints_from_heatmaps(maps, c, s, post_process="unbiased", kernel=17)
+        keypoints_from_heatmaps(maps, c, s, post_process="unbiased", kernel=9)
     # TopdownHeatmapBaseHead.decode with the reference's test_cfg (configs/ViTPose_common.py:123-129)
     metas = [{"center": [96.5, 128.0], "scale": [192.0, 256.0], "image_file": "a.jpg", "bbox_score": 0.9, "bbox_id": 7},
              {"center": [50.0, 60.0], "scale": [120.0, 160.0], "image_file": "b.jpg", "bbox_id": 8}]
