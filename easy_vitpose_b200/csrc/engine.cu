@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -382,7 +383,7 @@ struct vpb_engine {
   cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   // One activation workspace per engine: calls on DIFFERENT streams are ordered against each other by an event recorded
-  // after every enqueue (ws_release) and waited on when the stream changes (ws_acquire); calls on one stream order themselves.
+  // after every enqueue (WsScope::end) and waited on when the stream changes (WsScope::begin); calls on one stream order themselves.
   cudaEvent_t ev_ws = nullptr;
   cudaStream_t ws_last = nullptr;
   bool ws_used = false;
@@ -462,6 +463,11 @@ extern "C" int vpb_create(const vpb_config* cfg, vpb_engine** out) {
 
 extern "C" void vpb_destroy(vpb_engine* e) {
   if (!e) return;
+  int prev = -1;
+  if (cudaGetDevice(&prev) == cudaSuccess && prev != e->cfg.device) cudaSetDevice(e->cfg.device); else prev = -1;
+  cudaDeviceSynchronize();
+  for (auto& r : e->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto& ev : e->prof.pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   for (auto& kv : e->staged) cudaFree(kv.second.first);
   for (void* p : e->allocs) cudaFree(p);
   for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -474,6 +480,7 @@ extern "C" void vpb_destroy(vpb_engine* e) {
   if (e->compute_stream) cudaStreamDestroy(e->compute_stream);
   for (int s = 0; s < 2; ++s) if (e->frame_stage[s]) cudaFree(e->frame_stage[s]);
   delete e;
+  if (prev >= 0) cudaSetDevice(prev);
 }
 
 extern "C" int vpb_load_tensor(vpb_engine* e, const char* key, const float* data, int64_t numel) {
@@ -955,16 +962,52 @@ static bool stream_is_capturing(cudaStream_t st) {
 // Workspace hand-over between streams (see vpb_engine::ev_ws).  Inside a caller-side stream capture the events are left
 // alone (a wait on an event recorded outside the capture would be a cross-capture dependency): the caller then owns the
 // ordering of that graph against the engine's other users.
-static int ws_acquire(vpb_engine* e, cudaStream_t st) {
-  if (e->ws_used && e->ws_last != st && !stream_is_capturing(st)) CU_TRY(cudaStreamWaitEvent(st, e->ev_ws, 0));
-  return VPB_OK;
-}
-static int ws_release(vpb_engine* e, cudaStream_t st) {
-  if (stream_is_capturing(st)) return VPB_OK;
-  CU_TRY(cudaEventRecord(e->ev_ws, st));
-  e->ws_last = st; e->ws_used = true;
-  return VPB_OK;
-}
+//
+// Chained launches add a per-DEVICE rule.  A chained kernel (chain.cuh) spins on counters that other clusters of the same
+// launch advance, so every cluster of its grid has to become resident; two chained kernels of two engines sharing one GPU on
+// two streams could each hold part of the SMs and wait for the rest forever.  Calls that may launch chained kernels are
+// therefore serialised per device: the enqueue runs under the device's gate mutex (engines driven from different host
+// threads) and waits for the event the previous chained call on that device recorded when it came from another engine or
+// stream.  Other processes on the same GPU (MPS) are outside this gate: run chained engines with the GPU to themselves, or
+// switch the chain off (option "chain" = 0).
+struct ChainGate {
+  std::mutex mu;
+  cudaEvent_t ev = nullptr;
+  const vpb_engine* owner = nullptr;
+  cudaStream_t st = nullptr;
+};
+static ChainGate g_gates[kMaxDevices];
+
+struct WsScope {
+  vpb_engine* e;
+  cudaStream_t st;
+  bool capturing = false;
+  ChainGate* gate = nullptr;
+  std::unique_lock<std::mutex> lk;
+  WsScope(vpb_engine* e_, cudaStream_t st_) : e(e_), st(st_) {}
+  int begin(int batch) {
+    capturing = stream_is_capturing(st);
+    if (e->ws_used && e->ws_last != st && !capturing) CU_TRY(cudaStreamWaitEvent(st, e->ev_ws, 0));
+    if (e->use_chain && batch >= e->chain_min_batch && !e->ln_fused && !e->stop_after) {
+      const int dev = e->cfg.device;
+      gate = &g_gates[dev >= 0 && dev < kMaxDevices ? dev : 0];
+      lk = std::unique_lock<std::mutex>(gate->mu);
+      if (!capturing && gate->ev && (gate->owner != e || gate->st != st)) CU_TRY(cudaStreamWaitEvent(st, gate->ev, 0));
+    }
+    return VPB_OK;
+  }
+  int end() {
+    if (capturing) return VPB_OK;
+    CU_TRY(cudaEventRecord(e->ev_ws, st));
+    e->ws_last = st; e->ws_used = true;
+    if (gate) {
+      if (!gate->ev) CU_TRY(cudaEventCreateWithFlags(&gate->ev, cudaEventDisableTiming));
+      CU_TRY(cudaEventRecord(gate->ev, st));
+      gate->owner = e; gate->st = st;
+    }
+    return VPB_OK;
+  }
+};
 
 // Makes the engine's device current for the scope of an entry point and restores the caller's afterwards, so engines on
 // different GPUs can be driven from one thread (the stream argument must belong to the engine's device).
@@ -990,11 +1033,12 @@ extern "C" int vpb_forward(vpb_engine* e, const float* d_crops, int32_t batch, f
   if (!d_crops || !d_heatmaps) return fail(VPB_ERR_ARG, "vpb_forward: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VPB_TRY(apply_l2_policy(e, st));
-  VPB_TRY(ws_acquire(e, st));
+  WsScope ws(e, st);
+  VPB_TRY(ws.begin(batch));
   VPB_TRY(patch_gather(e, d_crops, batch, st));
   VPB_TRY(backbone(e, batch, st));
   if (!(e->stop_after && e->stop_after <= 10)) VPB_TRY(head(e, batch, d_heatmaps, st));
-  return ws_release(e, st);
+  return ws.end();
 }
 
 extern "C" int vpb_forward_features(vpb_engine* e, const float* d_crops, int32_t batch, float* d_features, void* stream) {
@@ -1002,13 +1046,14 @@ extern "C" int vpb_forward_features(vpb_engine* e, const float* d_crops, int32_t
   DeviceGuard dev_guard(e);
   if (!d_crops || !d_features) return fail(VPB_ERR_ARG, "vpb_forward_features: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  VPB_TRY(ws_acquire(e, st));
+  WsScope ws(e, st);
+  VPB_TRY(ws.begin(batch));
   VPB_TRY(patch_gather(e, d_crops, batch, st));
   VPB_TRY(backbone(e, batch, st));
   const long long tot = static_cast<long long>(batch) * e->D * 192;
   tokens_to_nchw<<<cdiv(tot, 256), 256, 0, st>>>(e->xn, d_features, batch, e->D);
   CU_TRY(cudaGetLastError());
-  return ws_release(e, st);
+  return ws.end();
 }
 
 static int decode_launch(const float* d_heatmaps, int32_t n, int32_t k, const int32_t* d_org_wh, const int32_t* d_offs_yx, float* d_kpts,
@@ -1034,11 +1079,12 @@ extern "C" int vpb_head(vpb_engine* e, const float* d_features, int32_t batch, f
   if (!d_features || !d_heatmaps) return fail(VPB_ERR_ARG, "vpb_head: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long tot = static_cast<long long>(batch) * e->D * 192;
-  VPB_TRY(ws_acquire(e, st));
+  WsScope ws(e, st);
+  VPB_TRY(ws.begin(0));                                     // the head launches no chained kernel
   nchw_to_tokens<<<cdiv(tot, 256), 256, 0, st>>>(d_features, e->xn, batch, e->D);
   CU_TRY(cudaGetLastError());
   VPB_TRY(head(e, batch, d_heatmaps, st));
-  return ws_release(e, st);
+  return ws.end();
 }
 extern "C" int vpb_flip_back(const float* d_in, int32_t n, int32_t k, const int32_t* d_perm, int32_t shift, float* d_out, void* stream) {
   if (!d_in || !d_out || !d_perm || d_in == d_out) return fail(VPB_ERR_ARG, "vpb_flip_back: null or aliased pointers");
@@ -1126,9 +1172,10 @@ static int infer_core(vpb_engine* e, const Source& src, const int32_t* d_org_wh,
                       float* d_kpts, int32_t* d_idx, float* d_heatmaps, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   VPB_TRY(apply_l2_policy(e, st));
-  VPB_TRY(ws_acquire(e, st));
+  WsScope ws(e, st);
+  VPB_TRY(ws.begin(batch));
   VPB_TRY(infer_core_locked(e, src, d_org_wh, d_offs_yx, batch, d_kpts, d_idx, d_heatmaps, stream));
-  return ws_release(e, st);
+  return ws.end();
 }
 static int infer_core_locked(vpb_engine* e, const Source& src, const int32_t* d_org_wh, const int32_t* d_offs_yx, int32_t batch,
                              float* d_kpts, int32_t* d_idx, float* d_heatmaps, void* stream) {

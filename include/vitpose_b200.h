@@ -18,6 +18,11 @@
  *     submit(0) is ordered after them;
  *   - if `stream` is being captured by the caller, the engine launches its kernels eagerly into that capture (no nested
  *     graph) and leaves its cross-stream ordering to the caller;
+ *   - several engines may share one GPU.  Calls that launch the chained persistent GEMM kernels (batch >= the "chain_min_batch"
+ *     option, 48 by default) are serialised per device across engines and streams (a device-side event wait plus a host mutex
+ *     around the enqueue): such a kernel needs all of its thread-block clusters resident at once and must not share the SMs
+ *     with a second one.  Another PROCESS running chained launches on the same GPU (MPS) is outside that gate: give chained
+ *     engines the GPU to themselves or set option "chain" = 0;
  *   - engines on different devices may live in one process: each entry point makes its engine's device current for the
  *     duration of the call and restores the caller's; `stream` must belong to the engine's device.
  *

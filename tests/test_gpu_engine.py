@@ -299,3 +299,30 @@ def test_narrow_tiles_for_small_batches_are_bit_identical(golden_dir):
     for a, b in zip(outs[0], outs[1]):
         for u, v in zip(a, b):
             assert np.array_equal(u, v)
+
+
+def test_two_engines_share_one_gpu_on_two_streams(golden_dir):
+    """Two engines on one device, driven on two streams without any host synchronisation in between, both with batches that take
+    the chained persistent launches.  A chained kernel needs all of its clusters resident, so two of them must never share the
+    SMs (each would wait for clusters that cannot start): the engine serialises such calls per device (engine.cu: ChainGate).
+    Results must equal each engine's solo run, bit for bit, and nothing may hang (the in-kernel spin guard would trap)."""
+    g = np.load(os.path.join(golden_dir, "fwd_s_coco.npz"))
+    B = 48
+    a, _ = _engine(g, max_batch=B)
+    b, _ = _engine(g, max_batch=B)
+    assert a.kernel_launches(B) == b.kernel_launches(B) == 1 + (1 + int(g["meta"][1])) + int(g["meta"][1]) + 4   # the chained count
+    xs = [torch.from_numpy(O.make_crops(B, 900 + i)).cuda() for i in range(3)]
+    org = torch.tensor([[190, 260]] * B, dtype=torch.int32).cuda()
+    want = [a.infer_crops(x, org)[0].clone() for x in xs]
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    got_a, got_b = [], []
+    for rnd in range(4):
+        for x in xs:
+            with torch.cuda.stream(s1):
+                got_a.append(a.infer_crops(x, org)[0])
+            with torch.cuda.stream(s2):
+                got_b.append(b.infer_crops(x, org)[0])
+    torch.cuda.synchronize()
+    for i, (ka, kb) in enumerate(zip(got_a, got_b)):
+        assert torch.equal(ka, want[i % 3]) and torch.equal(kb, want[i % 3])
