@@ -556,6 +556,7 @@ def run_gpu(args) -> None:
     e_steps = max(5, args.steps // 2)
     h_org = torch.tensor([[192, 256]] * B, dtype=torch.int32).pin_memory()
     e2e_sync_value = None
+    frame_latency = None
     if streams:
         # host uint8 frames + boxes in, host frame keypoints out, two frames in flight (vpb_submit_frame_host / vpb_wait_host)
         pin = [torch.from_numpy(im).pin_memory().numpy() for im in imgs]
@@ -582,6 +583,18 @@ def run_gpu(args) -> None:
         api = "vpb_submit_frame_host / vpb_wait_host (C ABI), 2 frames in flight, pinned host frames"
         h2d = int(1080 * 1920 * 3 * streams + crops_per_step * 16)
         d2h = int(crops_per_step * K * 16)
+        # per-frame latency: one synchronous call per frame -- host frame + boxes in, H2D, the path, D2H,
+        # stream sync, keypoints in host memory -- nothing else in flight
+        lat = []
+        for i in range(max(3, e_steps // 2)):
+            for f in range(streams):
+                t1 = time.perf_counter()
+                model.infer_frame_host(pin[(i * streams + f) % 4], boxes[f])
+                lat.append((time.perf_counter() - t1) * 1e3)
+        lat = np.sort(np.asarray(lat))
+        frame_latency = {"api": "vpb_infer_frame_host (synchronous, one frame in flight)", "frames": int(lat.size),
+                         "mean_ms": float(lat.mean()), "p50_ms": float(lat[lat.size // 2]), "p90_ms": float(lat[int(lat.size * 0.9)]),
+                         "p99_ms": float(lat[min(lat.size - 1, int(lat.size * 0.99))]), "max_ms": float(lat[-1])}
     elif world == 1:
         h_crops = [torch.randn((B, 3, 256, 192), dtype=torch.float32).pin_memory() for _ in range(2)]
         h_kp = [torch.empty((B, K, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -699,6 +712,7 @@ def run_gpu(args) -> None:
             "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps, "api": api,
                     "single_call_value": e2e_sync_value, "single_call_api": "vpb_infer_host (H2D, path, D2H, sync per call)"},
             "gpu_launches": (model.kernel_launches(B) * (streams or 1)) * args.steps,
+            "frame_latency": frame_latency,
             "roofline": roofline,
             "parity_check": parity,
             "profiled_pass_ms_per_step": ms_prof_total / args.steps,

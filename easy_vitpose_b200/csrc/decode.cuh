@@ -95,19 +95,29 @@ __global__ void __launch_bounds__(DECODE_WARPS * 32) decode_heatmaps(const Decod
   if (g >= total) return;
   const float* hm = p.heatmaps + static_cast<size_t>(g) * HM_PIX;
 
-  // ---- first-index argmax over 3072 values
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
+  // ---- first-index argmax over 3072 values.  The scan is branch-free so that the loads can run ahead of it (ptxas keeps a
+  // rolling window of seven 16-byte loads per lane in flight): the first version's early-return comparison compiled to
+  // divergent branches between the loads, which left ONE load in flight per lane (ncu source view: 24 serial DRAM round
+  // trips = 19 of the kernel's 23 us).  A lane sees its elements in increasing index order, so "first index wins"
+  // is "replace only when strictly better"; a NaN replaces a number and is never replaced (np.argmax: the first NaN).
+  float bv;
+  int bi;
   {
     const float4* h4 = reinterpret_cast<const float4*>(hm);
-#pragma unroll 12
-    for (int j = 0; j < HM_PIX / 128; ++j) {
-      const float4 v = __ldg(h4 + j * 32 + lane);
+    constexpr int NL = HM_PIX / 128;                         // 24 float4 per lane
+    float4 v[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) v[j] = __ldg(h4 + j * 32 + lane);
+    bv = v[0].x; bi = lane * 4;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
       const int base = (j * 32 + lane) * 4;
-      const float vv[4] = {v.x, v.y, v.z, v.w};
+      const float vv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        if (arg_better(vv[e], base + e, bv, bi)) { bv = vv[e]; bi = base + e; }   // bi starts at INT_MAX: the first element always wins
+        const bool take = (vv[e] > bv) | ((vv[e] != vv[e]) & (bv == bv));   // bitwise: no short-circuit branches
+        bv = take ? vv[e] : bv;
+        bi = take ? base + e : bi;
       }
     }
   }

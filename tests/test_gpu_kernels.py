@@ -63,6 +63,25 @@ def test_decode_nan_and_ties_first_index():
     _, idx = decode_heatmaps(torch.from_numpy(m).to(_dev()), torch.tensor([[192, 256]], dtype=torch.int32))
     assert idx.cpu().numpy().tolist() == [[100, 77, 0]]
     assert np.argmax(m.reshape(3, -1), -1).tolist() == [100, 77, 0]
+    # the lane-local scan (one lane owns elements 4l..4l+3 of every 128): same-lane and cross-lane orderings of NaN, +-inf, +-0
+    rs = np.random.RandomState(5)
+    cases = []
+    for trial in range(40):
+        h = rs.standard_normal(3072).astype(np.float32)
+        kind = trial % 8
+        a, b = sorted(rs.choice(3072, 2, replace=False))
+        if kind == 0: h[a] = h[b] = np.nan                           # two NaNs: the first
+        elif kind == 1: h[b] = np.nan; h[a] = 100.0                  # number first, NaN later: the NaN
+        elif kind == 2: h[:] = -np.inf                               # all -inf: index 0
+        elif kind == 3: h[:] = -np.inf; h[b] = -1e30
+        elif kind == 4: h[0] = np.nan                                # NaN in the very first element
+        elif kind == 5: h[:] = -0.0; h[b] = 0.0                      # +0 == -0: index 0
+        elif kind == 6: h[a] = h[a + 128 if a + 128 < 3072 else a] = 50.0   # tie inside one lane (stride 128)
+        else: h[a] = np.inf; h[b] = np.inf
+        cases.append(h.reshape(64, 48))
+    mm = np.stack(cases)[None]
+    _, idx = decode_heatmaps(torch.from_numpy(mm).to(_dev()), torch.tensor([[192, 256]], dtype=torch.int32))
+    assert np.array_equal(idx.cpu().numpy()[0], np.argmax(mm.reshape(40, -1), -1))
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
