@@ -10,7 +10,7 @@ import tempfile
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libvitpose_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["ptx.cuh", "gemm.cuh", "chain.cuh", "attention.cuh", "pointwise.cuh", "decode.cuh", "preprocess.cuh",
+HEADERS = ["ptx.cuh", "gemm.cuh", "chain.cuh", "attention.cuh", "attention_pack.cuh", "pointwise.cuh", "decode.cuh", "preprocess.cuh",
            os.path.join("..", "..", "include", "vitpose_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]

@@ -19,6 +19,7 @@
 
 #include "../../include/vitpose_b200.h"
 #include "attention.cuh"
+#include "attention_pack.cuh"
 #include "chain.cuh"
 #include "decode.cuh"
 #include "gemm.cuh"
@@ -190,6 +191,10 @@ static int device_check(int device) {
   CU_TRY(cudaFuncSetAttribute(attention_tcgen05<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<32>::SMEM));
   CU_TRY(cudaFuncSetAttribute(attention_tcgen05<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<64>::SMEM));
   CU_TRY(cudaFuncSetAttribute(attention_tcgen05<80, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<80>::SMEM));
+  CU_TRY(cudaFuncSetAttribute(attention_pack_tcgen05<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttPackCfg<32>::SMEM));
+  CU_TRY(cudaFuncSetAttribute(attention_pack_tcgen05<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttPackCfg<64>::SMEM));
+  CU_TRY(cudaFuncSetAttribute(attention_pack_tcgen05<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttPackCfg<32>::SMEM));
+  CU_TRY(cudaFuncSetAttribute(attention_pack_tcgen05<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttPackCfg<64>::SMEM));
   ds->attn_attr = true;
   ds->sms = prop.multiProcessorCount;
   return VPB_OK;
@@ -239,10 +244,22 @@ static int chain_launch(int bn, const ChainMaps& maps, const ChainParams& p, cud
 }
 
 // ------------------------------------------------------------------------------------------------ attention dispatch
-// Every 4th softmax exponential on the FMA pipe (ex2_poly) instead of the MUFU.  Process-wide switch: VPB_ATT_POLY=0/1 in the
-// environment at load time, or vpb_debug_attention() (A/B measurements in one process).
-static int g_att_poly = [] { const char* e = getenv("VPB_ATT_POLY"); return (e && e[0] == '1') ? 1 : 0; }();
-extern "C" int vpb_debug_attention(int32_t poly) { g_att_poly = poly ? 1 : 0; return VPB_OK; }
+// Attention variants (process-wide switches; environment at load time, or vpb_debug_attention() for A/B runs in one process):
+//   pack  attention_pack.cuh: the 64-row half tiles of two heads share one 128-lane pass (head_dim 32 / 64, an even number of
+//         items).  Default ON (VPB_ATT_PACK=0 switches it off): bit-identical to attention.cuh with the same exponentials.
+//   poly  every 4th softmax exponential on the FMA pipe (ex2_poly, 7.5e-5 relative error, far below P's bf16 rounding) instead
+//         of the MUFU.  Default: ON in the packed kernel, where both softmax groups are always live and the MUFU bounds the
+//         exponential phase (ViT-B, 64 crops: 22.3 -> 17.8 us per launch), OFF in attention.cuh (no gain inside the step);
+//         VPB_ATT_POLY=0/1 forces it for both.
+static int g_att_poly = [] { const char* e = getenv("VPB_ATT_POLY"); return !e ? -1 : (e[0] == '1' ? 1 : 0); }();    // -1 = per kernel default
+static int g_att_pack = [] { const char* e = getenv("VPB_ATT_PACK"); return (e && e[0] == '0') ? 0 : 1; }();
+static const int g_att_poly_env = g_att_poly, g_att_pack_env = g_att_pack;
+// flags < 0: back to the defaults (environment); else bit 0 = poly, bit 1 = pack
+extern "C" int vpb_debug_attention(int32_t flags) {
+  if (flags < 0) { g_att_poly = g_att_poly_env; g_att_pack = g_att_pack_env; }
+  else { g_att_poly = (flags & 1) ? 1 : 0; g_att_pack = (flags & 2) ? 1 : 0; }
+  return VPB_OK;
+}
 
 // qkv bf16 [rows, 3*D]: main operand boxes [192 x 64] (128B swizzle) or [192 x 32] (64B swizzle, head_dim 32), plus a
 // [192 x 16] 32B-swizzled box for the last 16 dims of head_dim 80.
@@ -257,7 +274,14 @@ static int attention_launch(int hd, const CUtensorMap& main, const CUtensorMap& 
   const int sms = num_sms();
   const dim3 grid(items < sms ? items : sms);      // one CTA per SM (512 TMEM columns each)
   cudaError_t err;
-  if (g_att_poly) {
+  const bool pack = g_att_pack && hd <= 64 && items % 2 == 0;
+  const bool poly = g_att_poly < 0 ? pack : g_att_poly != 0;
+  if (pack) {
+    if (hd == 64) err = poly ? launch_k(attention_pack_tcgen05<64, 8>, grid, dim3(ATT_THREADS), AttPackCfg<64>::SMEM, st, main, ap)
+                                   : launch_k(attention_pack_tcgen05<64>, grid, dim3(ATT_THREADS), AttPackCfg<64>::SMEM, st, main, ap);
+    else err = poly ? launch_k(attention_pack_tcgen05<32, 8>, grid, dim3(ATT_THREADS), AttPackCfg<32>::SMEM, st, main, ap)
+                          : launch_k(attention_pack_tcgen05<32>, grid, dim3(ATT_THREADS), AttPackCfg<32>::SMEM, st, main, ap);
+  } else if (poly) {
     switch (hd) {
       case 32: err = launch_k(attention_tcgen05<32, 8>, grid, dim3(ATT_THREADS), AttCfg<32>::SMEM, st, main, tail, ap); break;
       case 64: err = launch_k(attention_tcgen05<64, 8>, grid, dim3(ATT_THREADS), AttCfg<64>::SMEM, st, main, tail, ap); break;

@@ -189,9 +189,10 @@ int vpb_gemm(const void* d_a, const void* d_w, const float* d_bias, void* d_out,
 /* Debug: limit the GEMM smem ring depth and/or collect per-CTA cycle counters (int64 [grid*8]) for following GEMM launches. */
 int vpb_debug_gemm(int32_t stages_limit, void* d_counters);
 int vpb_attention(const void* d_qkv, int32_t batch, int32_t heads, int32_t head_dim, void* d_out, void* stream);
-/* Debug / measurement switch (process-wide): 1 = every 4th softmax exponential of the attention kernel is evaluated by a
- * polynomial on the FMA pipe instead of the MUFU (also VPB_ATT_POLY=1 in the environment). */
-int vpb_debug_attention(int32_t poly);
+/* Debug / measurement switch (process-wide) for the attention variants.  flags < 0: the defaults (packed half tiles for
+ * head_dim 32 / 64 with every 4th softmax exponential evaluated by a polynomial on the FMA pipe; VPB_ATT_PACK / VPB_ATT_POLY = 0 / 1
+ * in the environment change them); otherwise bit 0 = polynomial exponentials, bit 1 = packed half tiles. */
+int vpb_debug_attention(int32_t flags);
 int vpb_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_y, int32_t rows, int32_t dim,
                   float eps, void* stream);
 

@@ -84,6 +84,38 @@ def test_decode_nan_and_ties_first_index():
     assert np.array_equal(idx.cpu().numpy()[0], np.argmax(mm.reshape(40, -1), -1))
 
 
+@pytest.mark.parametrize("B,heads,hd", [(1, 2, 64), (1, 12, 64), (3, 12, 64), (7, 16, 64), (40, 16, 64), (64, 12, 64), (1, 2, 32), (5, 12, 32), (64, 12, 32)])
+def test_attention_packed_half_tiles(B, heads, hd):
+    """attention_pack.cuh: the 64-row half tiles of two heads share one 128-lane pass (M = 64 UMMAs at TMEM lane offsets 0 / 16).
+    Against the fp32 reference and against the unpacked kernel; small shapes give CTAs that start or end inside a pair
+    (one step only, a packed step only, kind 1 then the packed step)."""
+    from easy_vitpose_b200 import _lib
+    from gpu_util import attention
+    torch.manual_seed(B * 100 + heads + hd + 1)
+    D = heads * hd
+    qkv = torch.randn(B * 192, 3 * D, device=_dev())
+    qkv[:, :D] *= (hd ** -0.5) * 2.0
+    qkv = qkv.bfloat16()
+    try:
+        _lib.lib().vpb_debug_attention(0)                            # one step per half tile, all exponentials on the MUFU
+        plain = attention(qkv, B, heads, hd).float()
+        _lib.lib().vpb_debug_attention(2)                            # packed, same exponentials: bit-identical
+        out = attention(qkv, B, heads, hd).float()
+        again = attention(qkv, B, heads, hd).float()
+        _lib.lib().vpb_debug_attention(3)                            # packed + every 4th exponential as a polynomial (the default)
+        fast = attention(qkv, B, heads, hd).float()
+    finally:
+        _lib.lib().vpb_debug_attention(-1)
+    q, k, v = (qkv.float().reshape(B, 192, 3, heads, hd)[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    ref = (torch.softmax(q @ k.transpose(-1, -2), -1) @ v).permute(0, 2, 1, 3).reshape(B * 192, D)
+    r = _rel(out, ref)
+    print("packed attention rel err", r, "hd", hd, "| max |packed - plain|", float((out - plain).abs().max()), "identical:", bool(torch.equal(out, plain)))
+    assert torch.equal(out, again)                                   # deterministic
+    assert r < 2e-2
+    assert torch.equal(out, plain)                                   # same arithmetic per row, M = 64 instead of M = 128 tiles
+    assert _rel(fast, ref) < 2e-2 and (fast - out).abs().max() < 2e-2
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm
 @pytest.mark.parametrize("D", [384, 768, 1024, 1280])
 def test_layernorm(D):

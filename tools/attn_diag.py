@@ -11,9 +11,12 @@ from gpu_util import attention
 dev = torch.device("cuda", 0)
 L = _lib.lib()
 import itertools
-for (heads, hd, B), poly in itertools.product(((12, 64, 64), (16, 80, 32), (12, 32, 64)), (0, 1)):
-    L.vpb_debug_attention(poly)
-    print("--- exponentials:", "every 4th on the FMA pipe (ex2_poly)" if poly else "all on the MUFU")
+for (heads, hd, B), flags in itertools.product(((12, 64, 64), (16, 64, 64), (16, 80, 32), (12, 32, 64)), (0, 1, 2, 3)):
+    if hd == 80 and flags >= 2:
+        continue
+    L.vpb_debug_attention(flags)
+    print("--- exponentials:", "every 4th on the FMA pipe (ex2_poly)" if flags & 1 else "all on the MUFU", "| half tiles:",
+          "PACKED (attention_pack.cuh)" if flags & 2 else "one step each")
     D = heads * hd
     qkv = (torch.randn(B * 192, 3 * D, device=dev) * 0.5).bfloat16()
     for _ in range(3):
@@ -38,4 +41,4 @@ for (heads, hd, B), poly in itertools.product(((12, 64, 64), (16, 80, 32), (12, 
           f"{steps:.2f} tile steps (max {d[:,7].max():.0f}) -> {m[0]/steps:.0f} cyc/step")
     print(f"   softmax group A warp 0 (per step of the CTA): wait S {m[1]/steps:.0f} busy {m[2]/steps:.0f} | group B warp 4: wait S {m[5]/steps:.0f} busy {m[6]/steps:.0f} "
           f"| epilogue warp 8: wait {m[3]/steps:.0f} busy {m[4]/steps:.0f}")
-L.vpb_debug_attention(0)
+L.vpb_debug_attention(-1)

@@ -5,14 +5,17 @@
 set -u
 out=gpurun_out/r2_ncu; mkdir -p $out
 BENCH="python bench.py --config b17x64 --steps 2 --warmup 3 --no-cpu-baseline --no-frame-path"
+# ONLY="decode launches" restricts the run to the named captures (default: all, plus the ViT-H threshold study)
+want() { [ -z "${ONLY:-}" ] || [[ " $ONLY " == *" $1 "* ]]; }
 cap() {   # name, kernel regex, launches to skip, extra env
   name=$1; pat=$2; skip=$3; shift 3
+  want $name || return 0
   env "$@" timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k "regex:$pat" -s $skip -c 1 -f -o $out/$name $BENCH > $out/$name.log 2>&1
   echo "$name rc=$? $(ls -la $out/$name.ncu-rep 2>/dev/null | awk '{print $5}') bytes"
 }
 # chained build: one warm forward = 1 gather + 13 chains + 12 attention + 2 deconv + 1 final + 1 decode
 cap chain_block   'gemm_chain_tcgen05'          20 VPB_CHAIN=1     # a full block chain: proj -> LN -> fc1 -> fc2 -> LN -> qkv
-cap attention     'attention_tcgen05'           20 VPB_CHAIN=1
+cap attention     'attention_pack_tcgen05'      20 VPB_CHAIN=1
 cap deconv        'gemm_bf16_tcgen05ILi256ELi2E'   4  VPB_CHAIN=1
 cap final_conv    'gemm_bf16_tcgen05ILi32ELi4E'    2  VPB_CHAIN=1
 cap decode        'decode_heatmaps'             2  VPB_CHAIN=1
@@ -22,9 +25,12 @@ cap gemm_qkv      'gemm_bf16_tcgen05ILi256ELi0E'   14 VPB_CHAIN=0
 cap gemm_fc1      'gemm_bf16_tcgen05ILi256ELi1E'   14 VPB_CHAIN=0
 cap gemm_fc2_proj 'gemm_bf16_tcgen05ILi256ELi5E'   29 VPB_CHAIN=0     # skip 29 -> an fc2 launch (patch, then proj/fc2 alternate)
 cap layernorm     'layernorm_f32_to_bf16'       30 VPB_CHAIN=0
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv $BENCH > $out/launches.log 2>&1
-echo "launch list rc=$?"
+if want launches; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv $BENCH > $out/launches.log 2>&1
+  echo "launch list rc=$?"
+fi
 ls -la $out
+[ -n "${ONLY:-}" ] && exit 0
 # ViT-H wholebody B=32: chained vs one kernel per GEMM (threshold study), burst-length runs
 for mb in 1 999; do
   VPB_CHAIN_MIN_BATCH=$mb timeout 600 python bench.py --config h133x32 --steps 30 --warmup 5 --no-cpu-baseline --no-frame-path > $out/bench_h_minbatch$mb.json 2>/dev/null

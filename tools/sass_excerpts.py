@@ -9,7 +9,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "easy_vitpose_b200", "csrc", "libvitpose_b200.so")
-WANT = ["gemm_chain_tcgen05ILi256", "gemm_bf16_tcgen05ILi256ELi2", "gemm_bf16_tcgen05ILi256ELi0", "gemm_bf16_tcgen05ILi32ELi4", "attention_tcgen05ILi64ELi0",
+WANT = ["gemm_chain_tcgen05ILi256", "gemm_bf16_tcgen05ILi256ELi2", "gemm_bf16_tcgen05ILi256ELi0", "gemm_bf16_tcgen05ILi32ELi4", "attention_pack_tcgen05ILi64ELi8", "attention_tcgen05ILi64ELi0",
         "attention_tcgen05ILi80ELi0", "decode_heatmaps", "frame_to_patch_rows"]
 MNEM = ["UTCHMMA", "UTCBAR", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "LDTM", "STTM", "HMMA", "MUFU.EX2", "MUFU.TANH", "FMNMX3", "SYNCS", "ELECT", "BRA.U.ANY",
         "ACQBULK", "UCGABAR", "LDG.E.128", "STG.E.128", "RED", "NANOSLEEP"]
