@@ -225,7 +225,7 @@ attention_pack_tcgen05(const __grid_constant__ CUtensorMap tmap_main, const Attn
         for (int j = 0; j < 32; j += 2) {
           const float a0 = fmaf(__uint_as_float(r[j]), kLog2e, -mscaled), a1 = fmaf(__uint_as_float(r[j + 1]), kLog2e, -mscaled);
           const float e0 = ex2_approx(a0);
-          const float e1 = (NPOLY > 0 && ((j >> 1) % (16 / (NPOLY > 0 ? NPOLY : 1)) == 0)) ? ex2_poly(a1) : ex2_approx(a1);
+          const float e1 = (NPOLY > 0 && (((j >> 1) * NPOLY) % 16 < NPOLY)) ? ex2_poly(a1) : ex2_approx(a1);   // NPOLY of every 32
           sum += e0 + e1;
           pk[j >> 1] = pack_bf16(e0, e1);
         }
