@@ -254,10 +254,12 @@ static int chain_launch(int bn, const ChainMaps& maps, const ChainParams& p, cud
 static int g_att_poly = [] { const char* e = getenv("VPB_ATT_POLY"); return !e ? -1 : (e[0] == '1' ? 1 : 0); }();    // -1 = per kernel default
 static int g_att_pack = [] { const char* e = getenv("VPB_ATT_PACK"); return (e && e[0] == '0') ? 0 : 1; }();
 static const int g_att_poly_env = g_att_poly, g_att_pack_env = g_att_pack;
-// flags < 0: back to the defaults (environment); else bit 0 = poly, bit 1 = pack
+static int g_att_grid_cap = 0;      // tests: launch the attention kernels with at most this many CTAs (0 = one per SM)
+// flags < 0: back to the defaults (environment); else bit 0 = poly, bit 1 = pack, bits 8.. = grid cap (how a device with fewer
+// SMs would split the steps: other range boundaries inside the pairs of the packed kernel)
 extern "C" int vpb_debug_attention(int32_t flags) {
-  if (flags < 0) { g_att_poly = g_att_poly_env; g_att_pack = g_att_pack_env; }
-  else { g_att_poly = (flags & 1) ? 1 : 0; g_att_pack = (flags & 2) ? 1 : 0; }
+  if (flags < 0) { g_att_poly = g_att_poly_env; g_att_pack = g_att_pack_env; g_att_grid_cap = 0; }
+  else { g_att_poly = (flags & 1) ? 1 : 0; g_att_pack = (flags & 2) ? 1 : 0; g_att_grid_cap = flags >> 8; }
   return VPB_OK;
 }
 
@@ -271,7 +273,7 @@ static int make_attn_maps(CUtensorMap* main, CUtensorMap* tail, const void* qkv,
 }
 static int attention_launch(int hd, const CUtensorMap& main, const CUtensorMap& tail, const AttnParams& ap, cudaStream_t st) {
   const int items = ap.batch * ap.heads;
-  const int sms = num_sms();
+  const int sms = (g_att_grid_cap > 0 && g_att_grid_cap < num_sms()) ? g_att_grid_cap : num_sms();
   const dim3 grid(items < sms ? items : sms);      // one CTA per SM (512 TMEM columns each)
   cudaError_t err;
   const bool pack = g_att_pack && hd <= 64 && items % 2 == 0;

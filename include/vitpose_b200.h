@@ -191,7 +191,8 @@ int vpb_debug_gemm(int32_t stages_limit, void* d_counters);
 int vpb_attention(const void* d_qkv, int32_t batch, int32_t heads, int32_t head_dim, void* d_out, void* stream);
 /* Debug / measurement switch (process-wide) for the attention variants.  flags < 0: the defaults (packed half tiles for
  * head_dim 32 / 64 with every 4th softmax exponential evaluated by a polynomial on the FMA pipe; VPB_ATT_PACK / VPB_ATT_POLY = 0 / 1
- * in the environment change them); otherwise bit 0 = polynomial exponentials, bit 1 = packed half tiles. */
+ * in the environment change them); otherwise bit 0 = polynomial exponentials, bit 1 = packed half tiles, bits 8.. = cap on the
+ * number of CTAs (0 = one per SM; tests use it to move the boundaries of the per-CTA step ranges). */
 int vpb_debug_attention(int32_t flags);
 int vpb_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, void* d_y, int32_t rows, int32_t dim,
                   float eps, void* stream);

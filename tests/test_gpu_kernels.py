@@ -116,6 +116,31 @@ def test_attention_packed_half_tiles(B, heads, hd):
     assert _rel(fast, ref) < 2e-2 and (fast - out).abs().max() < 2e-2
 
 
+@pytest.mark.parametrize("B,heads,cap", [(1, 8, 7), (1, 10, 9), (1, 16, 11), (1, 6, 5), (2, 10, 19), (2, 11, 17), (3, 12, 1), (6, 12, 5)])
+def test_attention_packed_other_grids(B, heads, cap):
+    """The packed kernel with fewer CTAs than SMs (what a smaller / partitioned device would launch): the per-CTA step ranges then
+    start and end at other places inside the pairs, including a CTA whose only step is a pair's kind 1 (it must load item B alone)
+    and one whose only step is a packed step (tests/test_attention_pack_schedule.py enumerates them)."""
+    from easy_vitpose_b200 import _lib
+    from gpu_util import attention
+    hd = 64
+    torch.manual_seed(B * 1000 + heads * 10 + cap)
+    D = heads * hd
+    qkv = torch.randn(B * 192, 3 * D, device=_dev())
+    qkv[:, :D] *= (hd ** -0.5) * 2.0
+    qkv = qkv.bfloat16()
+    try:
+        _lib.lib().vpb_debug_attention(0)
+        plain = attention(qkv, B, heads, hd)
+        _lib.lib().vpb_debug_attention(2 | (cap << 8))
+        out = attention(qkv, B, heads, hd)
+        _lib.lib().vpb_debug_attention(0 | (cap << 8))
+        plain_capped = attention(qkv, B, heads, hd)
+    finally:
+        _lib.lib().vpb_debug_attention(-1)
+    assert torch.equal(out, plain) and torch.equal(plain_capped, plain)
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm
 @pytest.mark.parametrize("D", [384, 768, 1024, 1280])
 def test_layernorm(D):
