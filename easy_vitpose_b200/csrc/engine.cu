@@ -1014,7 +1014,7 @@ struct WsScope {
   int begin(int batch) {
     capturing = stream_is_capturing(st);
     if (e->ws_used && e->ws_last != st && !capturing) CU_TRY(cudaStreamWaitEvent(st, e->ev_ws, 0));
-    if (e->use_chain && batch >= e->chain_min_batch && !e->ln_fused && !e->stop_after) {
+    if (!e->ln_fused && !e->stop_after && ((e->use_chain && batch >= e->chain_min_batch) || e->ln_in_gemm)) {   // any chained kernel ahead
       const int dev = e->cfg.device;
       gate = &g_gates[dev >= 0 && dev < kMaxDevices ? dev : 0];
       lk = std::unique_lock<std::mutex>(gate->mu);
