@@ -23,6 +23,7 @@
 //
 //   warps 0..7   epilogue (tcgen05.ld -> bias / GELU -> swizzled smem staging -> TMA store or TMA reduce-add)
 //   warp  8      TMEM allocator            warp 10  TMA producer (+ dependency waits)      warp 11  tcgen05.mma issuer (leader CTA)
+//   warp  9      LayerNorm control (ln_ctl): polls the residual counters / publishes the jobs for warps 12..15
 //   warps 12..15 LayerNorm jobs
 #pragma once
 #include "gemm.cuh"
@@ -59,6 +60,8 @@ struct ChainParams {
   __nv_bfloat16* xn;        // LayerNorm output [M, D]
   float eps;
   int wave_lag[2];          // tile order: lag (in 256-row pairs) of the second phase behind the first inside wavefronts {0,1} and {2,3}
+  int ln_ctl;               // 1 = the counter polls / publishes of the LayerNorm jobs run on a control warp (warp 9), 0 = on warp 12
+  int rmw;                  // fp32 residual phases: 1 = load + add + TMA store (gemm.cuh: epilogue_f32_rmw), 0 = TMA reduce-add
   int dbg_nowait;           // measurement only (results may be wrong): publish tiles without waiting for their stores to complete
   long long* dbg;           // measurement: per cluster [CHAIN_MAX_PHASES][12] cycle counters (leader CTA) or nullptr (8..10: LayerNorm
                             //   stage s under phase 2s, warp 12: wait for the residual rows, busy, jobs):
@@ -257,6 +260,8 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
   uint64_t* acc_full = empty_bar + Cfg::STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;               // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* ln_ready = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // [2] control warp -> LayerNorm warps: the job's source rows are complete
+  uint64_t* ln_done = ln_ready + 2;                                  // [2] LayerNorm warps -> control warp: the job's rows are written
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -309,6 +314,8 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], GEMM_CL * GEMM_EPI_WARPS);
+      mbar_init(&ln_ready[s], 1);
+      mbar_init(&ln_done[s], CHAIN_LN_WARPS);
     }
     fence_mbar_init();
   }
@@ -414,11 +421,22 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       const int mt = mp * GEMM_CL + cta_rank;
       const int row0 = mt * GEMM_BM + quarter * 32;
       const long long e0 = p.dbg ? clock64() : 0;
+      // load + add + store form of the residual phases: this lane's first 32 fp32 of x.  Rows last written by an earlier launch
+      // (no residual phase before this one in the launch) are requested before the accumulator is ready.
+      const bool rmw = p.rmw != 0 && P.epi == EPI_F32_ADD;
+      const int x_col0 = nb * BN + half * Cfg::HALF;
+      bool x_early = rmw;
+      for (int j = 0; j < ph; ++j) x_early = x_early && p.ph[j].epi != EPI_F32_ADD;
+      float4 xr[8];
+      if (x_early) rmw_load_row(xr, p.x, p.D, row0 + lane, p.M, x_col0);
       mbar_wait(&acc_full[acc], acc_phase);
       const long long e1 = p.dbg ? clock64() : 0;
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE;
-      if (P.epi == EPI_F32_ADD) chain_epilogue_tile<BN, EPI_F32_ADD>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
+      if (rmw) {
+        if (!x_early) rmw_load_row(xr, p.x, p.D, row0 + lane, p.M, x_col0);
+        epilogue_f32_rmw<Cfg::HALF / 32>(t_row + half * Cfg::HALF, x_col0, row0, p.M, P.bias, p.x, p.D, xr, stile, lane, &maps.out[ph]);
+      } else if (P.epi == EPI_F32_ADD) chain_epilogue_tile<BN, EPI_F32_ADD>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
       else if (P.epi == EPI_BF16_GELU) chain_epilogue_tile<BN, EPI_BF16_GELU>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
       else if (P.epi == EPI_BF16_GELU_ERF) chain_epilogue_tile<BN, EPI_BF16_GELU_ERF>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
       else chain_epilogue_tile<BN, EPI_BF16>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
@@ -444,19 +462,73 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       }
     }
     if (elect_one()) tma_store_wait_all<0>();
+  } else if (warp == 9 && p.ln_ctl != 0) {
+    // ------------------------------------------------------------ LayerNorm control warp
+    // The gpu-scope fences around a job -- the acquire after the poll of the residual phase's counter, fence.proxy.async +
+    // red.release to publish the normalised rows -- cost the LayerNorm warps ~3 k of the ~10.5 k cycles a job takes them
+    // (tools/chain_diag.py), and the LayerNorm stages are what the consumer phases wait for (fc1 / qkv dependency waits: a quarter
+    // of a chained launch).  This warp takes both over: it walks the CTA's job list (job j -> CTA j mod grid, stage-major), polls
+    // job i + 1 while the LayerNorm warps work on job i and publishes job i when they have arrived on ln_done.  Two mbarrier
+    // slots each way (slot = job sequence number & 1); "ready" for job i + 2 is only signalled after "done" of job i was seen,
+    // so neither barrier can run a phase ahead.  Neither probe blocks: the first job of stage 1 waits for fc2 tiles that may
+    // themselves wait for this CTA's last job of stage 0, which must be publishable in the meantime.
+    const int jobs = (p.M + CHAIN_LN_JOB_ROWS - 1) / CHAIN_LN_JOB_ROWS;
+    const int first = static_cast<int>(blockIdx.x), step = static_cast<int>(gridDim.x);
+    const int end_s = first < jobs ? p.num_ln : 0;
+    int a_s = 0, a_job = first, a_seq = 0;            // poll cursor
+    int b_s = 0, b_job = first, b_seq = 0;            // publish cursor
+    uint32_t idle = 0;
+    while (b_s < end_s) {
+      bool progressed = false;
+      // neither probe blocks: a job that is done is published even while the next one's source rows are still outstanding
+      if (a_s < end_s && a_seq <= b_seq + 1) {
+        const ChainLn& L = p.ln[a_s];
+        if (__shfl_sync(0xffffffffu, ld_relaxed_gpu(L.src_done + (a_job * CHAIN_LN_JOB_ROWS) / GEMM_BM), 0) >= L.src_target) {
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ln_ready[a_seq & 1]);
+          ++a_seq;
+          a_job += step;
+          if (a_job >= jobs) { ++a_s; a_job = first; }
+          progressed = true;
+        }
+      }
+      if (b_seq < a_seq && __shfl_sync(0xffffffffu, mbar_test_wait(&ln_done[b_seq & 1], (b_seq >> 1) & 1) ? 1 : 0, 0)) {
+        if (lane == 0) {
+          fence_proxy_async_all();                    // consumed by TMA loads (async proxy) of other SMs
+          red_release_gpu_add(p.ln[b_s].ready + (b_job * CHAIN_LN_JOB_ROWS) / GEMM_BM, 1);
+        }
+        __syncwarp();
+        ++b_seq;
+        b_job += step;
+        if (b_job >= jobs) { ++b_s; b_job = first; }
+        progressed = true;
+      }
+      if (progressed) idle = 0;
+      else {
+        __nanosleep(32);
+        if (++idle > (VPB_HANG_TRAP_SPINS >> 3)) __trap();
+      }
+    }
   } else if (warp >= 12) {
     // ------------------------------------------------------------ LayerNorm jobs
     const int lw = warp - 12;
     const int jobs = (p.M + CHAIN_LN_JOB_ROWS - 1) / CHAIN_LN_JOB_ROWS;
     constexpr int ROWS_PER_WARP = CHAIN_LN_JOB_ROWS / CHAIN_LN_WARPS;
+    const bool ctl = p.ln_ctl != 0;                  // polls / publishes on the control warp (warp 9)
+    uint32_t seq = 0;                                 // job sequence number of this CTA over both stages (mbarrier slot / parity)
     for (int s = 0; s < p.num_ln; ++s) {
       const ChainLn& L = p.ln[s];
-      for (int job = blockIdx.x; job < jobs; job += gridDim.x) {
+      for (int job = blockIdx.x; job < jobs; job += gridDim.x, ++seq) {
         const int mt = (job * CHAIN_LN_JOB_ROWS) / GEMM_BM;
         const long long l0 = p.dbg ? clock64() : 0;
-        // one warp polls the counter, the other three sleep on a named barrier (bar.sync carries the acquired state over)
-        if (lw == 0) wait_counter(L.src_done + mt, L.src_target);
-        asm volatile("bar.sync 4, 128;" ::: "memory");
+        if (ctl) {
+          mbar_wait(&ln_ready[seq & 1], (seq >> 1) & 1);             // the control warp has acquired the rows at gpu scope
+        } else {
+          // one warp polls the counter, the other three sleep on a named barrier (bar.sync carries the acquired state over)
+          if (lw == 0) wait_counter(L.src_done + mt, L.src_target);
+          asm volatile("bar.sync 4, 128;" ::: "memory");
+        }
         const long long l1 = p.dbg ? clock64() : 0;
         const int r0 = job * CHAIN_LN_JOB_ROWS + lw * ROWS_PER_WARP;
         const int r1 = min(r0 + ROWS_PER_WARP, p.M);
@@ -469,9 +541,14 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
         // one gpu-scope release per job and CTA (a MEMBAR.GPU on an SM with TMA traffic in flight costs thousands of cycles):
         // the four warps meet on a named barrier (orders their row stores before the releasing thread), warp 12 publishes
         const long long l2 = p.dbg ? clock64() : 0;
-        asm volatile("bar.sync 5, 128;" ::: "memory");
+        if (ctl) {
+          __syncwarp();                                                // every lane's row stores precede the arrive
+          if (lane == 0) mbar_arrive(&ln_done[seq & 1]);              // the control warp publishes the job
+        } else {
+          asm volatile("bar.sync 5, 128;" ::: "memory");
+        }
         const long long l3 = p.dbg ? clock64() : 0;
-        if (lw == 0 && lane == 0) {
+        if (!ctl && lw == 0 && lane == 0) {
           fence_proxy_async_all();                                     // consumed by TMA loads (async proxy) of other SMs
           red_release_gpu_add(L.ready + mt, 1);
         }

@@ -103,6 +103,17 @@ static int make_map_nhwc(CUtensorMap* m, const void* base, uint64_t B, uint64_t 
 static int g_dbg_stages = 0, g_dbg_flags = 0;      // debug knobs set by vpb_debug_gemm
 static long long* g_dbg_buf = nullptr;
 
+// Residual epilogues (patch embed, proj, fc2: x += acc + bias): 1 = load + add + TMA store (gemm.cuh: epilogue_f32_rmw), 0 = TMA
+// reduce-add.  Bit-identical; process default from VPB_RESID_RMW, per engine through option "resid_rmw"; the debug flags 32 / 64
+// of vpb_debug_gemm force one form for every following launch (kernel-level tests).
+constexpr int kResidRmwDefault = 0;
+constexpr int kLnCtlDefault = 0;
+static int resid_rmw_default() {
+  static const int v = [] { const char* s = getenv("VPB_RESID_RMW"); return s ? (s[0] != '0') : kResidRmwDefault; }();
+  return v;
+}
+static int resid_rmw(int engine_choice) { return (g_dbg_flags & 32) ? 1 : (g_dbg_flags & 64) ? 0 : engine_choice; }
+
 // ------------------------------------------------------------------------------------------------ launches
 // Every kernel of the chain is launched with programmatic stream serialization (see ptx.cuh: pdl_wait).
 static bool g_pdl = true;
@@ -400,6 +411,8 @@ struct vpb_engine {
   // (tools/latency_small_batches.py, ViT-B) the chained launches lose 3-8 % up to 32 crops per call (few row blocks: the
   // dependent phases cannot overlap and every CTA spins) and win from 48 crops on.
   int chain_min_batch = 48;
+  int resid_rmw = 0;               // residual epilogues as load + add + store instead of TMA reduce-add (see resid_rmw_default)
+  int ln_ctl = 0;                  // chained launches: LayerNorm polls / publishes on a control warp (chain.cuh); option "ln_ctl", VPB_LN_CTL
   int chain_bn = 256;
   int* chain_counters = nullptr;
   size_t chain_blocks = 0;         // 128-row blocks at max_batch
@@ -482,6 +495,11 @@ extern "C" int vpb_create(const vpb_config* cfg, vpb_engine** out) {
     if (ge && ge[0] == '1') e->gelu_erf = true;
     const char* mb = getenv("VPB_CHAIN_MIN_BATCH");
     if (mb && atoi(mb) > 0) e->chain_min_batch = atoi(mb);
+  }
+  e->resid_rmw = resid_rmw_default();
+  {
+    const char* lc = getenv("VPB_LN_CTL");
+    e->ln_ctl = lc ? (lc[0] != '0') : kLnCtlDefault;
   }
   *out = e;
   return VPB_OK;
@@ -703,6 +721,7 @@ static GemmParams gp(int M, int N, int K, const float* bias, void* out, int ldc)
   memset(&p, 0, sizeof(p));
   p.stages_limit = g_dbg_stages; p.dbg = g_dbg_buf; p.dbg_flags = g_dbg_flags;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldc = ldc;
+  p.rmw = resid_rmw(resid_rmw_default());
   return p;
 }
 
@@ -755,6 +774,8 @@ static int backbone_chained(vpb_engine* e, int B, cudaStream_t st) {
     p.M = M; p.D = D; p.x = e->x; p.xn = e->xn; p.eps = 1e-6f;
     static const int nowait = [] { const char* v = getenv("VPB_CHAIN_NOWAIT"); return (v && v[0] == '1') ? 1 : 0; }();
     p.dbg_nowait = nowait;
+    p.rmw = resid_rmw(e->resid_rmw);
+    p.ln_ctl = e->ln_ctl;
     // tile order inside a chained launch: phase-major by default (lag >= number of row-block pairs).  Interleaving the
     // reduce-add phases with their consumers (VPB_CHAIN_LAG0/1 = lag in 256-row pairs) was measured slower at every lag tried
     // (B = 64: 27.4 k crops/s phase-major, 25.2 k at 24/32, 23.4 k at 16/22, 20.1 k at 8/12): a consumer tile needs the
@@ -852,6 +873,7 @@ static int backbone(vpb_engine* e, int B, cudaStream_t st) {
     ChainParams p; ChainMaps m;
     memset(&p, 0, sizeof(p));
     p.M = M; p.D = D; p.x = e->x; p.xn = e->xn; p.eps = 1e-6f; p.wave_lag[0] = p.wave_lag[1] = 1 << 20; p.dbg = nullptr;
+    p.ln_ctl = e->ln_ctl;
     int* ready = e->chain_counters + static_cast<size_t>(slot) * nblk;
     p.ln[0] = {ready, 0, g, b, ready};                      // source counter: any valid address, target 0 = "already complete"
     p.num_ln = 1; p.num_phases = 1;
@@ -868,6 +890,7 @@ static int backbone(vpb_engine* e, int B, cudaStream_t st) {
     e->prof.begin(KC_GEMM_PATCH, st);
     int bn;
     const CUtensorMap& wm = pick_tile(e->patch, M, &bn);
+    p.rmw = resid_rmw(e->resid_rmw);
     VPB_TRY(gemm_launch(bn, EPI_F32_ADD, e->m_patch_rows, wm, e->o_x, p, st));
     e->prof.end(st);
   }
@@ -902,6 +925,7 @@ static int backbone(vpb_engine* e, int B, cudaStream_t st) {
       e->prof.begin(KC_GEMM_PROJ, st);
       int bn;
       const CUtensorMap& wm = pick_tile(b.proj, M, &bn);
+      p.rmw = resid_rmw(e->resid_rmw);
       VPB_TRY(gemm_launch(bn, EPI_F32_ADD, e->m_attn, wm, e->o_x, p, st));
       e->prof.end(st);
     }
@@ -926,6 +950,7 @@ static int backbone(vpb_engine* e, int B, cudaStream_t st) {
       e->prof.begin(KC_GEMM_FC2, st);
       int bn;
       const CUtensorMap& wm = pick_tile(b.fc2, M, &bn);
+      p.rmw = resid_rmw(e->resid_rmw);
       VPB_TRY(gemm_launch(bn, EPI_F32_ADD, e->m_hid, wm, e->o_x, p, st));
       e->prof.end(st);
     }
@@ -1431,8 +1456,11 @@ extern "C" int vpb_set_option(vpb_engine* e, const char* name, int32_t value) {
   else if (!strcmp(name, "profile")) e->prof.on = value != 0;
   else if (!strcmp(name, "pdl")) g_pdl = value != 0;
   else if (!strcmp(name, "graph")) e->use_graph = value != 0;
-  else if (!strcmp(name, "chain") || !strcmp(name, "chain_min_batch") || !strcmp(name, "gelu_erf") || !strcmp(name, "ln_in_gemm")) {
+  else if (!strcmp(name, "chain") || !strcmp(name, "chain_min_batch") || !strcmp(name, "gelu_erf") || !strcmp(name, "ln_in_gemm") ||
+           !strcmp(name, "resid_rmw") || !strcmp(name, "ln_ctl")) {
     if (!strcmp(name, "gelu_erf")) e->gelu_erf = value != 0;
+    else if (!strcmp(name, "resid_rmw")) e->resid_rmw = value != 0;
+    else if (!strcmp(name, "ln_ctl")) e->ln_ctl = value != 0;
     else if (!strcmp(name, "ln_in_gemm")) e->ln_in_gemm = value != 0;
     else if (!strcmp(name, "chain")) e->use_chain = value != 0;
     else e->chain_min_batch = value;

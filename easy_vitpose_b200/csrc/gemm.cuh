@@ -54,6 +54,7 @@ struct GemmParams {
   __nv_bfloat16* ln_out;  // [M, N] or nullptr
   int* ln_counters;       // [ceil(M/128)] zero before the first launch; the last arriver resets its entry
   float ln_eps;
+  int rmw;                // EPI_F32_ADD: 1 = load + add + TMA store (epilogue_f32_rmw; needs out = the fp32 stream, ldc = N), 0 = TMA reduce-add
   int stages_limit;       // debug: use at most this many ring stages (0 = all)
   int dbg_flags;          // debug (results become wrong!): 1 = every pair loads the SAME A rows, 2 = the same W rows
                           //        (probes whether L2 reads or SM-side delivery bound the loop); 4 = m-fastest tile order
@@ -97,6 +98,65 @@ __device__ __forceinline__ float gelu_fast(float x) { return gelu_erf_as(x); }
 #else
 __device__ __forceinline__ float gelu_fast(float x) { return gelu_tanh_fit(x); }
 #endif
+
+// ---------------------------------------------------------------- fp32 residual epilogue as LOAD + ADD + STORE
+// x[tile] += acc + bias without the L2 reduction path.  A TMA reduce-add round of one epilogue warp (4 KB) takes ~3.1 k cycles
+// against ~1.9 k for a plain TMA store round of the same size, whatever the contention (tools/chain_diag.py: proj 12.4 k,
+// fc2 13.8 k cycles per tile for four rounds): cp.reduce.async.bulk is throttled per SM, not by the chip's L2 bandwidth, and
+// a K = 768 residual phase (patch embed, proj) is epilogue-bound at half the tensor rate.  Every element of the stream has
+// exactly ONE writer per phase (no split-K), so that writer can do the add itself: each lane reads its own row's 32 fp32 of
+// x straight out of L2 (ld.global.cg, 128 contiguous bytes; the rows were written by other SMs' TMA stores), adds in registers
+// -- fl(x + fl(acc + bias)), the very two roundings of the reduce-add form, hence bit-identical -- and the tile leaves through
+// the same staging buffer as a plain TMA store.  The loads of box c + 1 are issued as soon as box c's registers are consumed,
+// so their latency runs under the wait for the previous store to release the staging buffer.  Box 0 may be requested before
+// the accumulator is ready whenever the rows were last written by an EARLIER launch (proj, patch embed); inside a chained
+// launch the rows of a later residual phase (fc2) are complete once the tile's A operand is (proj -> LayerNorm -> fc1 ->
+// this tile), so they are requested after acc_full.
+__device__ __forceinline__ void rmw_load_row(float4 (&xr)[8], const float* __restrict__ x, int ldx, int row, int M, int n) {
+  if (row < M && n < ldx) {                          // boxes are 32 columns wide and ldx % 32 == 0: inside or outside as a whole
+    const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx + n);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) xr[q] = __ldcg(src + q);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);      // clipped by the store
+  }
+}
+// NCH boxes of 32 columns from column n_first / TMEM address t_col0 on; xr holds box 0 of this lane's row (row0 + lane).
+template <int NCH>
+__device__ __forceinline__ void epilogue_f32_rmw(uint32_t t_col0, int n_first, int row0, int M, const float* __restrict__ bias,
+                                                 const float* __restrict__ x, int ldx, float4 (&xr)[8], uint8_t* stile, int lane,
+                                                 const CUtensorMap* tmap) {
+  const int sw = lane & 7;
+  uint8_t* srow = stile + lane * 128;               // staging row = lane, 16-byte chunk index XOR (lane % 8): SWIZZLE_128B
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    const int n = n_first + 32 * c;
+    uint32_t r[32];
+    tmem_ld32(t_col0 + 32 * c, r);
+    tmem_ld_wait();
+    float4 o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + 4 * q));
+      o[q].x = xr[q].x + (__uint_as_float(r[4 * q]) + b4.x);
+      o[q].y = xr[q].y + (__uint_as_float(r[4 * q + 1]) + b4.y);
+      o[q].z = xr[q].z + (__uint_as_float(r[4 * q + 2]) + b4.z);
+      o[q].w = xr[q].w + (__uint_as_float(r[4 * q + 3]) + b4.w);
+    }
+    if (c + 1 < NCH) rmw_load_row(xr, x, ldx, row0 + lane, M, n + 32);          // in flight under the wait below
+    if (elect_one()) tma_store_wait_read<0>();      // previous store has finished reading the staging tile
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(srow + ((q ^ sw) << 4)) = o[q];
+    fence_proxy_async_smem();                       // staging writes -> visible to the TMA engine
+    __syncwarp();
+    if (n < ldx && elect_one()) {                   // (a column tile may overhang N when N % BN != 0)
+      tma_store_2d(tmap, stile, n, row0);           // rows past M are clipped by the tensor map
+      tma_store_commit();
+    }
+  }
+}
 
 // One warp normalises one row of the fp32 stream (D = 128*V columns) straight out of L2 (ld.global.cg: the row was just
 // written by other SMs' TMA reduce-adds / stores) -> bf16.  nn.LayerNorm(eps), biased variance (backbone/vit.py:190,198,304).
@@ -298,12 +358,26 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = kDeconv ? (quarter * 32 + lane < up_pos && mt < num_m) : (row < p.M);
       const long long w0 = clock64();
+      // load + add + store form of the residual epilogue: the rows were completed by an earlier launch, so this lane's first
+      // 32 fp32 of x are requested before the accumulator is ready
+      [[maybe_unused]] float4 xr[8];
+      [[maybe_unused]] bool rmw = false;
+      if constexpr (EPI == EPI_F32_ADD) {
+        rmw = p.rmw != 0;
+        if (rmw) rmw_load_row(xr, reinterpret_cast<const float*>(p.out), p.ldc, row, p.M, n0 + half * Cfg::HALF);
+      }
       mbar_wait(&acc_full[acc], acc_phase);
       t_wfull += clock64() - w0;
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE;
 
+      if constexpr (EPI == EPI_F32_ADD) {
+        if (rmw)
+          epilogue_f32_rmw<Cfg::HALF / 32>(t_row + half * Cfg::HALF, n0 + half * Cfg::HALF, m0 + quarter * 32, p.M, p.bias,
+                                           reinterpret_cast<const float*>(p.out), p.ldc, xr, stile, lane, &tmap_out);
+      }
       if constexpr (epi_uses_tma(EPI)) {
+        if (!rmw) {
         // 64 bf16 or 32 f32 output columns (= one 128-byte staging row) per round
         constexpr int COLS = (EPI == EPI_F32_ADD) ? 32 : 64;
 #pragma unroll 1
@@ -356,6 +430,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             else tma_store_2d(&tmap_out, stile, n, m0 + quarter * 32);   // rows past M are clipped by the tensor map
             tma_store_commit();
           }
+        }
         }
       } else {
         // ---- direct epilogues (scattered / transposed outputs)

@@ -188,6 +188,34 @@ def test_chain_is_bit_identical(golden_dir, name, batches):
     assert m.kernel_launches(1) == 2 + 5 * depth + 4 + 2 * depth + 1      # one kernel per GEMM and per LayerNorm (ViT-B: 91)
 
 
+@pytest.mark.parametrize("name,batches", [("b_coco", (5, 3, 1)), ("s_coco", (4, 1)), ("h_wholebody", (3,)), ("l_coco_25", (2,))])
+def test_residual_rmw_and_ln_control_warp_are_bit_identical(golden_dir, name, batches):
+    """Two restructurings of the chained launches that must not change a bit.  Option "resid_rmw": the residual epilogues (patch
+    embed, proj, fc2) as load + add + TMA store instead of TMA reduce-add -- in the chained launches (x of the proj phase requested
+    before the accumulator is ready, x of the fc2 phase after it) and in the one-kernel-per-GEMM path (256- and 128-wide tiles).
+    Option "ln_ctl": the counter polls / publishes of the LayerNorm jobs on a control warp (two-slot mbarrier hand-off) instead
+    of on the first LayerNorm warp -- also for the LayerNorm + GEMM mini-chains (ln_in_gemm).  Every combination twice."""
+    g = np.load(os.path.join(golden_dir, f"fwd_{name}.npz"))
+    m, _ = _engine(g, max_batch=max(batches))
+    m.set_option("chain_min_batch", 1)
+    x = torch.from_numpy(O.make_crops(max(batches), 655)).cuda()
+    outs = {}
+    combos = [(1, 0, 0), (1, 1, 0), (1, 0, 1), (1, 1, 1), (0, 0, 0), (0, 1, 0), (2, 0, 1), (2, 1, 1)]     # (chain, rmw, ctl); chain 2 = ln_in_gemm
+    for rep in range(2):
+        for chain, rmw, ctl in combos:
+            m.set_option("chain", 1 if chain == 1 else 0)
+            m.set_option("ln_in_gemm", 1 if chain == 2 else 0)
+            m.set_option("resid_rmw", rmw)
+            m.set_option("ln_ctl", ctl)
+            outs.setdefault((chain, rmw, ctl), []).append([m(x[:n]).cpu().numpy() for n in batches])
+    m.set_option("ln_in_gemm", 0)
+    base = outs[(0, 0, 0)][0]
+    for key, runs in outs.items():
+        for run in runs:
+            for a, b in zip(run, base):
+                assert np.array_equal(a, b), f"(chain, rmw, ln_ctl) = {key}: {int((a != b).sum())} of {a.size} heatmap values differ"
+
+
 def test_gelu_erf_option_changes_nothing_visible(golden_dir):
     """Option "gelu_erf": fc1 epilogue with an erf accurate to 1.5e-7 instead of the fitted tanh form (max error 2.6e-5 before
     the bf16 rounding).  Both must sit at the same distance from the fp32 reference; the heatmaps may differ by rounding noise."""

@@ -244,6 +244,40 @@ def test_gemm_reduce_add_into_fp32_stream():
     assert _rel(x, ref) < 2e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(576, 768, 768), (12288, 768, 768), (1000, 384, 1536), (200, 1280, 320), (129, 1024, 4096)])
+def test_gemm_residual_rmw_equals_reduce_add(M, N, K):
+    """The residual epilogue as load + add + TMA store (gemm.cuh: epilogue_f32_rmw) against the TMA reduce-add form: every
+    element has one writer per launch and both forms round fl(x + fl(acc + bias)) -> bit-identical, ragged row blocks, the
+    128-wide tiles (N = 384) and subnormal / zero / huge stream values included."""
+    from gpu_util import EPI_F32_ADD, gemm
+    from easy_vitpose_b200 import _lib
+    torch.manual_seed(M + N)
+    a = (torch.randn(M, K, device=_dev()) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=_dev()) * 0.05).bfloat16()
+    bias = torch.randn(N, device=_dev())
+    x0 = torch.randn(M, N, device=_dev())
+    x0[::7, ::5] = 0.0
+    x0[3::11, 1::9] *= 1e30
+    x0[5::13, 2::3] *= 1e-30
+    x0[6::17, 4::7] = 1e-40                                          # subnormal stream values
+    outs = []
+    L = _lib.lib()
+    try:
+        for flag in (64, 32, 64, 32):                                # 64 = force reduce-add, 32 = force load + add + store
+            L.vpb_debug_gemm(flag << 8, None)
+            x = x0.clone()
+            gemm(a, w, bias, x, EPI_F32_ADD)
+            outs.append(x)
+    finally:
+        L.vpb_debug_gemm(0, None)
+    ref = x0 + a.float() @ w.float().T + bias
+    ok = torch.isfinite(ref) & (ref.abs() < 1e20)
+    assert _rel(outs[0][ok], ref[ok]) < 2e-3
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[3])
+    assert torch.equal(outs[0].view(torch.int32), outs[1].view(torch.int32)), \
+        f"{int((outs[0].view(torch.int32) != outs[1].view(torch.int32)).sum())} of {M * N} elements differ"
+
+
 @pytest.mark.parametrize("B,H,W,C,TR,TW", [(3, 16, 12, 768, 8, 12), (2, 32, 24, 256, 16, 8), (5, 16, 12, 384, 8, 12), (3, 32, 24, 256, 4, 24)])
 def test_gemm_implicit_deconv_bn_relu(B, H, W, C, TR, TW):
     """ConvTranspose2d(k4,s2,p1) + eval BatchNorm + ReLU as ONE implicit-GEMM launch (4 phases, shifted 4-D TMA boxes)
