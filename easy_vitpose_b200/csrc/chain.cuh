@@ -34,7 +34,7 @@ constexpr int CHAIN_MAX_PHASES = 4;
 constexpr int CHAIN_MAX_LN = 2;
 constexpr int CHAIN_THREADS = 512;
 constexpr int CHAIN_LN_WARPS = 4;
-constexpr int CHAIN_LN_JOB_ROWS = 16;      // rows per LayerNorm job: 4 per warp
+constexpr int CHAIN_LN_JOB_ROWS = 16;      // default rows per LayerNorm job (ChainParams::ln_job_rows: 8 or 16): 4 per warp
 
 struct ChainPhase {
   int N, K;                 // W is [N,K]; N % BN == 0, K % 64 == 0
@@ -60,6 +60,7 @@ struct ChainParams {
   __nv_bfloat16* xn;        // LayerNorm output [M, D]
   float eps;
   int wave_lag[2];          // tile order: lag (in 256-row pairs) of the second phase behind the first inside wavefronts {0,1} and {2,3}
+  int ln_job_rows;          // rows per LayerNorm job: 16 (two 2-row iterations per warp) or 8 (one)
   int ln_ctl;               // 1 = the counter polls / publishes of the LayerNorm jobs run on a control warp (warp 9), 0 = on warp 12
   int rmw;                  // fp32 residual phases: 1 = load + add + TMA store (gemm.cuh: epilogue_f32_rmw), 0 = TMA reduce-add
   int dbg_nowait;           // measurement only (results may be wrong): publish tiles without waiting for their stores to complete
@@ -117,9 +118,9 @@ __device__ __forceinline__ void wait_counter(const int* p, int target) {
   }
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
-__host__ __device__ __forceinline__ int chain_ln_jobs_in_block(int M, int mt) {
+__host__ __device__ __forceinline__ int chain_ln_jobs_in_block(int M, int mt, int job_rows) {
   const int rows = M - mt * GEMM_BM < GEMM_BM ? M - mt * GEMM_BM : GEMM_BM;
-  return (rows + CHAIN_LN_JOB_ROWS - 1) / CHAIN_LN_JOB_ROWS;
+  return (rows + job_rows - 1) / job_rows;
 }
 
 // ---------------------------------------------------------------- LayerNorm rows (same arithmetic, same order as
@@ -343,7 +344,7 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       const int num_kb = P.K / GEMM_BK;
       long long c0 = p.dbg ? clock64() : 0, w_dep = 0, w_ring = 0;
       if (P.a_ready != nullptr && mt < num_m) {
-        wait_counter(P.a_ready + mt, P.a_target > 0 ? P.a_target : chain_ln_jobs_in_block(p.M, mt));
+        wait_counter(P.a_ready + mt, P.a_target > 0 ? P.a_target : chain_ln_jobs_in_block(p.M, mt, p.ln_job_rows));
         fence_proxy_async_all();                    // the rows were written through the generic / async proxy of other SMs
       }
       if (p.dbg) w_dep = clock64() - c0;
@@ -421,20 +422,20 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       const int mt = mp * GEMM_CL + cta_rank;
       const int row0 = mt * GEMM_BM + quarter * 32;
       const long long e0 = p.dbg ? clock64() : 0;
-      // load + add + store form of the residual phases: this lane's first 32 fp32 of x.  Rows last written by an earlier launch
+      // load + add + store form of the residual phases: the warp's first 32 x 32 box of x.  Rows last written by an earlier launch
       // (no residual phase before this one in the launch) are requested before the accumulator is ready.
       const bool rmw = p.rmw != 0 && P.epi == EPI_F32_ADD;
       const int x_col0 = nb * BN + half * Cfg::HALF;
       bool x_early = rmw;
       for (int j = 0; j < ph; ++j) x_early = x_early && p.ph[j].epi != EPI_F32_ADD;
       float4 xr[8];
-      if (x_early) rmw_load_row(xr, p.x, p.D, row0 + lane, p.M, x_col0);
+      if (x_early) rmw_load_box(xr, p.x, p.D, row0, lane, p.M, x_col0);
       mbar_wait(&acc_full[acc], acc_phase);
       const long long e1 = p.dbg ? clock64() : 0;
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE;
       if (rmw) {
-        if (!x_early) rmw_load_row(xr, p.x, p.D, row0 + lane, p.M, x_col0);
+        if (!x_early) rmw_load_box(xr, p.x, p.D, row0, lane, p.M, x_col0);
         epilogue_f32_rmw<Cfg::HALF / 32>(t_row + half * Cfg::HALF, x_col0, row0, p.M, P.bias, p.x, p.D, xr, stile, lane, &maps.out[ph]);
       } else if (P.epi == EPI_F32_ADD) chain_epilogue_tile<BN, EPI_F32_ADD>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
       else if (P.epi == EPI_BF16_GELU) chain_epilogue_tile<BN, EPI_BF16_GELU>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
@@ -472,7 +473,7 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
     // slots each way (slot = job sequence number & 1); "ready" for job i + 2 is only signalled after "done" of job i was seen,
     // so neither barrier can run a phase ahead.  Neither probe blocks: the first job of stage 1 waits for fc2 tiles that may
     // themselves wait for this CTA's last job of stage 0, which must be publishable in the meantime.
-    const int jobs = (p.M + CHAIN_LN_JOB_ROWS - 1) / CHAIN_LN_JOB_ROWS;
+    const int jobs = (p.M + p.ln_job_rows - 1) / p.ln_job_rows;
     const int first = static_cast<int>(blockIdx.x), step = static_cast<int>(gridDim.x);
     const int end_s = first < jobs ? p.num_ln : 0;
     int a_s = 0, a_job = first, a_seq = 0;            // poll cursor
@@ -483,7 +484,7 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       // neither probe blocks: a job that is done is published even while the next one's source rows are still outstanding
       if (a_s < end_s && a_seq <= b_seq + 1) {
         const ChainLn& L = p.ln[a_s];
-        if (__shfl_sync(0xffffffffu, ld_relaxed_gpu(L.src_done + (a_job * CHAIN_LN_JOB_ROWS) / GEMM_BM), 0) >= L.src_target) {
+        if (__shfl_sync(0xffffffffu, ld_relaxed_gpu(L.src_done + (a_job * p.ln_job_rows) / GEMM_BM), 0) >= L.src_target) {
           asm volatile("fence.acq_rel.gpu;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(&ln_ready[a_seq & 1]);
@@ -496,7 +497,7 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       if (b_seq < a_seq && __shfl_sync(0xffffffffu, mbar_test_wait(&ln_done[b_seq & 1], (b_seq >> 1) & 1) ? 1 : 0, 0)) {
         if (lane == 0) {
           fence_proxy_async_all();                    // consumed by TMA loads (async proxy) of other SMs
-          red_release_gpu_add(p.ln[b_s].ready + (b_job * CHAIN_LN_JOB_ROWS) / GEMM_BM, 1);
+          red_release_gpu_add(p.ln[b_s].ready + (b_job * p.ln_job_rows) / GEMM_BM, 1);
         }
         __syncwarp();
         ++b_seq;
@@ -513,14 +514,14 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
   } else if (warp >= 12) {
     // ------------------------------------------------------------ LayerNorm jobs
     const int lw = warp - 12;
-    const int jobs = (p.M + CHAIN_LN_JOB_ROWS - 1) / CHAIN_LN_JOB_ROWS;
-    constexpr int ROWS_PER_WARP = CHAIN_LN_JOB_ROWS / CHAIN_LN_WARPS;
+    const int jobs = (p.M + p.ln_job_rows - 1) / p.ln_job_rows;
+    const int ROWS_PER_WARP = p.ln_job_rows / CHAIN_LN_WARPS;
     const bool ctl = p.ln_ctl != 0;                  // polls / publishes on the control warp (warp 9)
     uint32_t seq = 0;                                 // job sequence number of this CTA over both stages (mbarrier slot / parity)
     for (int s = 0; s < p.num_ln; ++s) {
       const ChainLn& L = p.ln[s];
       for (int job = blockIdx.x; job < jobs; job += gridDim.x, ++seq) {
-        const int mt = (job * CHAIN_LN_JOB_ROWS) / GEMM_BM;
+        const int mt = (job * p.ln_job_rows) / GEMM_BM;
         const long long l0 = p.dbg ? clock64() : 0;
         if (ctl) {
           mbar_wait(&ln_ready[seq & 1], (seq >> 1) & 1);             // the control warp has acquired the rows at gpu scope
@@ -530,7 +531,7 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
           asm volatile("bar.sync 4, 128;" ::: "memory");
         }
         const long long l1 = p.dbg ? clock64() : 0;
-        const int r0 = job * CHAIN_LN_JOB_ROWS + lw * ROWS_PER_WARP;
+        const int r0 = job * p.ln_job_rows + lw * ROWS_PER_WARP;
         const int r1 = min(r0 + ROWS_PER_WARP, p.M);
         switch (p.D) {
           case 384: chain_ln_rows<3>(p, L, r0, r1, lane); break;

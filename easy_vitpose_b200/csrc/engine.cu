@@ -107,7 +107,7 @@ static long long* g_dbg_buf = nullptr;
 // reduce-add.  Bit-identical; process default from VPB_RESID_RMW, per engine through option "resid_rmw"; the debug flags 32 / 64
 // of vpb_debug_gemm force one form for every following launch (kernel-level tests).
 constexpr int kResidRmwDefault = 0;
-constexpr int kLnCtlDefault = 0;
+constexpr int kLnCtlDefault = 1;      // measured on B200 (ViT-B, 64 crops): 2.308 -> 2.245 ms per step, bit-identical
 static int resid_rmw_default() {
   static const int v = [] { const char* s = getenv("VPB_RESID_RMW"); return s ? (s[0] != '0') : kResidRmwDefault; }();
   return v;
@@ -412,6 +412,7 @@ struct vpb_engine {
   // dependent phases cannot overlap and every CTA spins) and win from 48 crops on.
   int chain_min_batch = 48;
   int resid_rmw = 0;               // residual epilogues as load + add + store instead of TMA reduce-add (see resid_rmw_default)
+  int ln_job_rows = CHAIN_LN_JOB_ROWS;   // rows per LayerNorm job of the chained launches (8 or 16); option "ln_job_rows", VPB_LN_JOB_ROWS
   int ln_ctl = 0;                  // chained launches: LayerNorm polls / publishes on a control warp (chain.cuh); option "ln_ctl", VPB_LN_CTL
   int chain_bn = 256;
   int* chain_counters = nullptr;
@@ -500,6 +501,8 @@ extern "C" int vpb_create(const vpb_config* cfg, vpb_engine** out) {
   {
     const char* lc = getenv("VPB_LN_CTL");
     e->ln_ctl = lc ? (lc[0] != '0') : kLnCtlDefault;
+    const char* jr = getenv("VPB_LN_JOB_ROWS");
+    if (jr && (atoi(jr) == 8 || atoi(jr) == 16)) e->ln_job_rows = atoi(jr);
   }
   *out = e;
   return VPB_OK;
@@ -775,7 +778,7 @@ static int backbone_chained(vpb_engine* e, int B, cudaStream_t st) {
     static const int nowait = [] { const char* v = getenv("VPB_CHAIN_NOWAIT"); return (v && v[0] == '1') ? 1 : 0; }();
     p.dbg_nowait = nowait;
     p.rmw = resid_rmw(e->resid_rmw);
-    p.ln_ctl = e->ln_ctl;
+    p.ln_ctl = e->ln_ctl; p.ln_job_rows = e->ln_job_rows;
     // tile order inside a chained launch: phase-major by default (lag >= number of row-block pairs).  Interleaving the
     // reduce-add phases with their consumers (VPB_CHAIN_LAG0/1 = lag in 256-row pairs) was measured slower at every lag tried
     // (B = 64: 27.4 k crops/s phase-major, 25.2 k at 24/32, 23.4 k at 16/22, 20.1 k at 8/12): a consumer tile needs the
@@ -873,7 +876,7 @@ static int backbone(vpb_engine* e, int B, cudaStream_t st) {
     ChainParams p; ChainMaps m;
     memset(&p, 0, sizeof(p));
     p.M = M; p.D = D; p.x = e->x; p.xn = e->xn; p.eps = 1e-6f; p.wave_lag[0] = p.wave_lag[1] = 1 << 20; p.dbg = nullptr;
-    p.ln_ctl = e->ln_ctl;
+    p.ln_ctl = e->ln_ctl; p.ln_job_rows = e->ln_job_rows;
     int* ready = e->chain_counters + static_cast<size_t>(slot) * nblk;
     p.ln[0] = {ready, 0, g, b, ready};                      // source counter: any valid address, target 0 = "already complete"
     p.num_ln = 1; p.num_phases = 1;
@@ -1457,10 +1460,12 @@ extern "C" int vpb_set_option(vpb_engine* e, const char* name, int32_t value) {
   else if (!strcmp(name, "pdl")) g_pdl = value != 0;
   else if (!strcmp(name, "graph")) e->use_graph = value != 0;
   else if (!strcmp(name, "chain") || !strcmp(name, "chain_min_batch") || !strcmp(name, "gelu_erf") || !strcmp(name, "ln_in_gemm") ||
-           !strcmp(name, "resid_rmw") || !strcmp(name, "ln_ctl")) {
+           !strcmp(name, "resid_rmw") || !strcmp(name, "ln_ctl") || !strcmp(name, "ln_job_rows")) {
+    if (!strcmp(name, "ln_job_rows") && value != 8 && value != 16) return fail(VPB_ERR_ARG, "ln_job_rows must be 8 or 16");
     if (!strcmp(name, "gelu_erf")) e->gelu_erf = value != 0;
     else if (!strcmp(name, "resid_rmw")) e->resid_rmw = value != 0;
     else if (!strcmp(name, "ln_ctl")) e->ln_ctl = value != 0;
+    else if (!strcmp(name, "ln_job_rows")) e->ln_job_rows = value;
     else if (!strcmp(name, "ln_in_gemm")) e->ln_in_gemm = value != 0;
     else if (!strcmp(name, "chain")) e->use_chain = value != 0;
     else e->chain_min_batch = value;

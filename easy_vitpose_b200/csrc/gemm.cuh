@@ -104,51 +104,61 @@ __device__ __forceinline__ float gelu_fast(float x) { return gelu_tanh_fit(x); }
 // against ~1.9 k for a plain TMA store round of the same size, whatever the contention (tools/chain_diag.py: proj 12.4 k,
 // fc2 13.8 k cycles per tile for four rounds): cp.reduce.async.bulk is throttled per SM, not by the chip's L2 bandwidth, and
 // a K = 768 residual phase (patch embed, proj) is epilogue-bound at half the tensor rate.  Every element of the stream has
-// exactly ONE writer per phase (no split-K), so that writer can do the add itself: each lane reads its own row's 32 fp32 of
-// x straight out of L2 (ld.global.cg, 128 contiguous bytes; the rows were written by other SMs' TMA stores), adds in registers
-// -- fl(x + fl(acc + bias)), the very two roundings of the reduce-add form, hence bit-identical -- and the tile leaves through
-// the same staging buffer as a plain TMA store.  The loads of box c + 1 are issued as soon as box c's registers are consumed,
-// so their latency runs under the wait for the previous store to release the staging buffer.  Box 0 may be requested before
-// the accumulator is ready whenever the rows were last written by an EARLIER launch (proj, patch embed); inside a chained
-// launch the rows of a later residual phase (fc2) are complete once the tile's A operand is (proj -> LayerNorm -> fc1 ->
-// this tile), so they are requested after acc_full.
-__device__ __forceinline__ void rmw_load_row(float4 (&xr)[8], const float* __restrict__ x, int ldx, int row, int M, int n) {
-  if (row < M && n < ldx) {                          // boxes are 32 columns wide and ldx % 32 == 0: inside or outside as a whole
-    const float4* src = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx + n);
+// exactly ONE writer per phase (no split-K), so that writer can do the add itself: the warp reads its 32 x 32 fp32 box of x
+// out of L2 with COALESCED 16-byte loads (ld.global.cg; eight lanes per 128-byte row segment, four rows per instruction --
+// one lane per row was measured 2.6 times slower than the reduce-add: 256 partial-sector requests per box), parks the box in
+// its staging buffer in the tensor map's swizzled layout, each lane then adds its own row in place -- fl(x + fl(acc + bias)),
+// the very two roundings of the reduce-add form, hence bit-identical -- and the buffer leaves as a plain TMA store.  The loads
+// of box c + 1 are issued as soon as box c's registers are parked, so their latency runs under the adds, the store and the
+// next round's wait for the staging buffer.  Box 0 may be requested before the accumulator is ready whenever the rows were last
+// written by an EARLIER launch (proj, patch embed); inside a chained launch the rows of a later residual phase (fc2) are
+// complete once the tile's A operand is (proj -> LayerNorm -> fc1 -> this tile), so they are requested after acc_full.
+//
+// xr[i]: lane l holds the 16-byte chunk (l & 7) of row 4 i + (l >> 3) of the box whose first row is row0, first column n.
+__device__ __forceinline__ void rmw_load_box(float4 (&xr)[8], const float* __restrict__ x, int ldx, int row0, int lane, int M, int n) {
+  const float* src = x + static_cast<size_t>(row0 + (lane >> 3)) * ldx + n + 4 * (lane & 7);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) xr[q] = __ldcg(src + q);
-  } else {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);      // clipped by the store
+  for (int i = 0; i < 8; ++i) {
+    // boxes are 32 columns wide and ldx % 32 == 0: a box lies inside or outside [0, ldx) as a whole
+    if (row0 + 4 * i + (lane >> 3) < M && n < ldx) xr[i] = __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(4 * i) * ldx));
+    else xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);                             // clipped by the store
   }
 }
-// NCH boxes of 32 columns from column n_first / TMEM address t_col0 on; xr holds box 0 of this lane's row (row0 + lane).
+// NCH boxes of 32 columns from column n_first / TMEM address t_col0 on; xr holds box 0.
 template <int NCH>
 __device__ __forceinline__ void epilogue_f32_rmw(uint32_t t_col0, int n_first, int row0, int M, const float* __restrict__ bias,
                                                  const float* __restrict__ x, int ldx, float4 (&xr)[8], uint8_t* stile, int lane,
                                                  const CUtensorMap* tmap) {
   const int sw = lane & 7;
-  uint8_t* srow = stile + lane * 128;               // staging row = lane, 16-byte chunk index XOR (lane % 8): SWIZZLE_128B
+  uint8_t* srow = stile + lane * 128;               // staging row = lane, 16-byte chunk index XOR (row % 8): SWIZZLE_128B
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
     const int n = n_first + 32 * c;
     uint32_t r[32];
     tmem_ld32(t_col0 + 32 * c, r);
     tmem_ld_wait();
-    float4 o[8];
+    float v[32];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + 4 * q));
-      o[q].x = xr[q].x + (__uint_as_float(r[4 * q]) + b4.x);
-      o[q].y = xr[q].y + (__uint_as_float(r[4 * q + 1]) + b4.y);
-      o[q].z = xr[q].z + (__uint_as_float(r[4 * q + 2]) + b4.z);
-      o[q].w = xr[q].w + (__uint_as_float(r[4 * q + 3]) + b4.w);
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + j));
+      v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+      v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
     }
-    if (c + 1 < NCH) rmw_load_row(xr, x, ldx, row0 + lane, M, n + 32);          // in flight under the wait below
     if (elect_one()) tma_store_wait_read<0>();      // previous store has finished reading the staging tile
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(srow + ((q ^ sw) << 4)) = o[q];
+    for (int i = 0; i < 8; ++i) {                   // park the box: row 4 i + lane / 8, chunk lane % 8
+      const int row = 4 * i + (lane >> 3);
+      *reinterpret_cast<float4*>(stile + row * 128 + (((lane & 7) ^ (row & 7)) << 4)) = xr[i];
+    }
+    __syncwarp();
+    if (c + 1 < NCH) rmw_load_box(xr, x, ldx, row0, lane, M, n + 32);           // in flight until the next round parks it
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4* cell = reinterpret_cast<float4*>(srow + ((q ^ sw) << 4));
+      const float4 x4 = *cell;
+      *cell = make_float4(x4.x + v[4 * q], x4.y + v[4 * q + 1], x4.z + v[4 * q + 2], x4.w + v[4 * q + 3]);
+    }
     fence_proxy_async_smem();                       // staging writes -> visible to the TMA engine
     __syncwarp();
     if (n < ldx && elect_one()) {                   // (a column tile may overhang N when N % BN != 0)
@@ -364,7 +374,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       [[maybe_unused]] bool rmw = false;
       if constexpr (EPI == EPI_F32_ADD) {
         rmw = p.rmw != 0;
-        if (rmw) rmw_load_row(xr, reinterpret_cast<const float*>(p.out), p.ldc, row, p.M, n0 + half * Cfg::HALF);
+        if (rmw) rmw_load_box(xr, reinterpret_cast<const float*>(p.out), p.ldc, m0 + quarter * 32, lane, p.M, n0 + half * Cfg::HALF);
       }
       mbar_wait(&acc_full[acc], acc_phase);
       t_wfull += clock64() - w0;

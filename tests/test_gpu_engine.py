@@ -194,26 +194,30 @@ def test_residual_rmw_and_ln_control_warp_are_bit_identical(golden_dir, name, ba
     embed, proj, fc2) as load + add + TMA store instead of TMA reduce-add -- in the chained launches (x of the proj phase requested
     before the accumulator is ready, x of the fc2 phase after it) and in the one-kernel-per-GEMM path (256- and 128-wide tiles).
     Option "ln_ctl": the counter polls / publishes of the LayerNorm jobs on a control warp (two-slot mbarrier hand-off) instead
-    of on the first LayerNorm warp -- also for the LayerNorm + GEMM mini-chains (ln_in_gemm).  Every combination twice."""
+    of on the first LayerNorm warp -- also for the LayerNorm + GEMM mini-chains (ln_in_gemm).  Option "ln_job_rows": 8-row
+    instead of 16-row LayerNorm jobs.  Every combination twice."""
     g = np.load(os.path.join(golden_dir, f"fwd_{name}.npz"))
     m, _ = _engine(g, max_batch=max(batches))
     m.set_option("chain_min_batch", 1)
     x = torch.from_numpy(O.make_crops(max(batches), 655)).cuda()
     outs = {}
-    combos = [(1, 0, 0), (1, 1, 0), (1, 0, 1), (1, 1, 1), (0, 0, 0), (0, 1, 0), (2, 0, 1), (2, 1, 1)]     # (chain, rmw, ctl); chain 2 = ln_in_gemm
+    # (chain, rmw, ctl, rows per LayerNorm job); chain 2 = ln_in_gemm
+    combos = [(1, 0, 0, 16), (1, 1, 0, 16), (1, 0, 1, 16), (1, 1, 1, 16), (1, 1, 1, 8), (1, 0, 0, 8), (0, 0, 0, 16), (0, 1, 0, 16), (2, 0, 1, 16), (2, 1, 1, 8)]
     for rep in range(2):
-        for chain, rmw, ctl in combos:
+        for chain, rmw, ctl, rows in combos:
             m.set_option("chain", 1 if chain == 1 else 0)
             m.set_option("ln_in_gemm", 1 if chain == 2 else 0)
             m.set_option("resid_rmw", rmw)
             m.set_option("ln_ctl", ctl)
-            outs.setdefault((chain, rmw, ctl), []).append([m(x[:n]).cpu().numpy() for n in batches])
+            m.set_option("ln_job_rows", rows)
+            outs.setdefault((chain, rmw, ctl, rows), []).append([m(x[:n]).cpu().numpy() for n in batches])
     m.set_option("ln_in_gemm", 0)
-    base = outs[(0, 0, 0)][0]
+    m.set_option("ln_job_rows", 16)
+    base = outs[(0, 0, 0, 16)][0]
     for key, runs in outs.items():
         for run in runs:
             for a, b in zip(run, base):
-                assert np.array_equal(a, b), f"(chain, rmw, ln_ctl) = {key}: {int((a != b).sum())} of {a.size} heatmap values differ"
+                assert np.array_equal(a, b), f"(chain, rmw, ln_ctl, ln_job_rows) = {key}: {int((a != b).sum())} of {a.size} heatmap values differ"
 
 
 def test_gelu_erf_option_changes_nothing_visible(golden_dir):

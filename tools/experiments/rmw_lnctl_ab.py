@@ -25,30 +25,33 @@ m = ViTPose(model_cfg(size, K), max_batch=B)
 m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in random_state_dict(size, K, seed=1).items()}).to("cuda:0")
 xs = [torch.randn(B, 3, 256, 192, device="cuda") for _ in range(4)]          # 4 x 37.7 MB (B = 64): rotated, like bench.py
 org = torch.tensor([[192, 256]] * B, dtype=torch.int32)
-combos = [(0, 0), (1, 0), (0, 1), (1, 1)]
+# (resid_rmw, ln_ctl, ln_job_rows); the first one is the reference for the bit-identity check
+combos = [tuple(int(v) for v in c.split(",")) for c in sys.argv[6].split(";")] if len(sys.argv) > 6 else \
+    [(0, 0, 16), (1, 0, 16), (0, 1, 16), (1, 1, 16), (0, 1, 8), (1, 1, 8)]
 
 
-def setopt(rmw, ctl):
+def setopt(rmw, ctl, rows):
     m.set_option("resid_rmw", rmw)
     m.set_option("ln_ctl", ctl)
+    m.set_option("ln_job_rows", rows)
 
 
 base = None
-for rmw, ctl in combos:
-    setopt(rmw, ctl)
+for rmw, ctl, rows in combos:
+    setopt(rmw, ctl, rows)
     hm = m(xs[0]).cpu().numpy()
     kp, idx = m.infer_crops(xs[0], org)
     kp, idx = kp.cpu().numpy(), idx.cpu().numpy()
     if base is None:
         base = (hm, kp, idx)
     same = np.array_equal(hm, base[0]) and np.array_equal(kp, base[1]) and np.array_equal(idx, base[2])
-    print(f"resid_rmw={rmw} ln_ctl={ctl}: heatmaps / keypoints / argmax bit-identical to (0, 0): {same}", flush=True)
+    print(f"resid_rmw={rmw} ln_ctl={ctl} ln_job_rows={rows}: heatmaps / keypoints / argmax bit-identical to {combos[0]}: {same}", flush=True)
     assert same
 
 res = {c: [] for c in combos}
 for rep in range(reps):
-    for rmw, ctl in combos:
-        setopt(rmw, ctl)
+    for rmw, ctl, rows in combos:
+        setopt(rmw, ctl, rows)
         for i in range(5):
             m.infer_crops(xs[i % 4], org)
         torch.cuda.synchronize()
@@ -59,9 +62,9 @@ for rep in range(reps):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        res[(rmw, ctl)].append(ms)
+        res[(rmw, ctl, rows)].append(ms)
         time.sleep(0.3)
 for c in combos:
     v = res[c]
-    print(f"ViT-{size} K={K} B={B} resid_rmw={c[0]} ln_ctl={c[1]}: ms/step {' '.join(f'{t:.4f}' for t in v)}  -> best {min(v):.4f} ms = {B / min(v) * 1e3:.0f} crops/s, "
+    print(f"ViT-{size} K={K} B={B} resid_rmw={c[0]} ln_ctl={c[1]} ln_job_rows={c[2]}: ms/step {' '.join(f'{t:.4f}' for t in v)}  -> best {min(v):.4f} ms = {B / min(v) * 1e3:.0f} crops/s, "
           f"median {sorted(v)[len(v) // 2]:.4f} ms = {B / sorted(v)[len(v) // 2] * 1e3:.0f} crops/s", flush=True)
