@@ -62,7 +62,7 @@ struct ChainParams {
   int wave_lag[2];          // tile order: lag (in 256-row pairs) of the second phase behind the first inside wavefronts {0,1} and {2,3}
   int ln_job_rows;          // rows per LayerNorm job: 16 (two 2-row iterations per warp) or 8 (one)
   int ln_ctl;               // 1 = the counter polls / publishes of the LayerNorm jobs run on a control warp (warp 9), 0 = on warp 12
-  int rmw;                  // fp32 residual phases: 1 = load + add + TMA store (gemm.cuh: epilogue_f32_rmw), 0 = TMA reduce-add
+  int rmw;                  // fp32 residual phases: 1 = load + add + store in the generic proxy (gemm.cuh: epilogue_f32_rmw), 0 = TMA reduce-add
   int dbg_nowait;           // measurement only (results may be wrong): publish tiles without waiting for their stores to complete
   long long* dbg;           // measurement: per cluster [CHAIN_MAX_PHASES][12] cycle counters (leader CTA) or nullptr (8..10: LayerNorm
                             //   stage s under phase 2s, warp 12: wait for the residual rows, busy, jobs):
@@ -261,8 +261,7 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
   uint64_t* acc_full = empty_bar + Cfg::STAGES;     // [2]
   uint64_t* acc_empty = acc_full + 2;               // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint64_t* ln_ready = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // [2] control warp -> LayerNorm warps: the job's source rows are complete
-  uint64_t* ln_done = ln_ready + 2;                                  // [2] LayerNorm warps -> control warp: the job's rows are written
+  uint64_t* ln_done = reinterpret_cast<uint64_t*>(tmem_slot + 2);    // [2] LayerNorm warps -> control warp: the job's rows are written
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -315,7 +314,6 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], GEMM_CL * GEMM_EPI_WARPS);
-      mbar_init(&ln_ready[s], 1);
       mbar_init(&ln_done[s], CHAIN_LN_WARPS);
     }
     fence_mbar_init();
@@ -436,7 +434,7 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::ACC_STRIDE;
       if (rmw) {
         if (!x_early) rmw_load_box(xr, p.x, p.D, row0, lane, p.M, x_col0);
-        epilogue_f32_rmw<Cfg::HALF / 32>(t_row + half * Cfg::HALF, x_col0, row0, p.M, P.bias, p.x, p.D, xr, stile, lane, &maps.out[ph]);
+        epilogue_f32_rmw<Cfg::HALF / 32>(t_row + half * Cfg::HALF, x_col0, row0, p.M, P.bias, const_cast<float*>(p.x), p.D, xr, stile, lane);
       } else if (P.epi == EPI_F32_ADD) chain_epilogue_tile<BN, EPI_F32_ADD>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
       else if (P.epi == EPI_BF16_GELU) chain_epilogue_tile<BN, EPI_BF16_GELU>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
       else if (P.epi == EPI_BF16_GELU_ERF) chain_epilogue_tile<BN, EPI_BF16_GELU_ERF>(t_row, half, nb * BN, row0, P.bias, stile, lane, &maps.out[ph]);
@@ -469,9 +467,9 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
     // red.release to publish the normalised rows -- cost the LayerNorm warps ~3 k of the ~10.5 k cycles a job takes them
     // (tools/chain_diag.py), and the LayerNorm stages are what the consumer phases wait for (fc1 / qkv dependency waits: a quarter
     // of a chained launch).  This warp takes both over: it walks the CTA's job list (job j -> CTA j mod grid, stage-major), polls
-    // job i + 1 while the LayerNorm warps work on job i and publishes job i when they have arrived on ln_done.  Two mbarrier
-    // slots each way (slot = job sequence number & 1); "ready" for job i + 2 is only signalled after "done" of job i was seen,
-    // so neither barrier can run a phase ahead.  Neither probe blocks: the first job of stage 1 waits for fc2 tiles that may
+    // job i + 1 while the LayerNorm warps work on job i and publishes job i when they have arrived on ln_done.  Two slots each
+    // way (slot = job sequence number & 1; "ready": named barriers 4 / 5, "done": mbarriers); "ready" for job i + 2 is only
+    // signalled after "done" of job i was seen, so neither barrier can run a phase ahead.  Neither probe blocks: the first job of stage 1 waits for fc2 tiles that may
     // themselves wait for this CTA's last job of stage 0, which must be publishable in the meantime.
     const int jobs = (p.M + p.ln_job_rows - 1) / p.ln_job_rows;
     const int first = static_cast<int>(blockIdx.x), step = static_cast<int>(gridDim.x);
@@ -487,7 +485,12 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
         if (__shfl_sync(0xffffffffu, ld_relaxed_gpu(L.src_done + (a_job * p.ln_job_rows) / GEMM_BM), 0) >= L.src_target) {
           asm volatile("fence.acq_rel.gpu;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(&ln_ready[a_seq & 1]);
+          // "ready" is a NAMED barrier (ids 4 / 5 by slot, 4 LayerNorm warps + this one): the LayerNorm warps sleep in
+          // bar.sync without taking issue slots.  First version: an mbarrier they polled with try_wait -- four more spinning
+          // warps per SM, the epilogue warps sharing their schedulers lost 15 % (fc1 epilogue 8.8 k -> 10.3 k cycles per tile)
+          // and the MMA thread's accumulator waits rose from 5 % to 19 % of the fc1 phase, which ate the gain.
+          if (a_seq & 1) asm volatile("bar.arrive 5, 160;" ::: "memory");
+          else asm volatile("bar.arrive 4, 160;" ::: "memory");
           ++a_seq;
           a_job += step;
           if (a_job >= jobs) { ++a_s; a_job = first; }
@@ -507,7 +510,7 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
       }
       if (progressed) idle = 0;
       else {
-        __nanosleep(32);
+        __nanosleep(96);                              // this warp shares a scheduler with two epilogue warps
         if (++idle > (VPB_HANG_TRAP_SPINS >> 3)) __trap();
       }
     }
@@ -524,7 +527,9 @@ gemm_chain_tcgen05(const __grid_constant__ ChainMaps maps, const __grid_constant
         const int mt = (job * p.ln_job_rows) / GEMM_BM;
         const long long l0 = p.dbg ? clock64() : 0;
         if (ctl) {
-          mbar_wait(&ln_ready[seq & 1], (seq >> 1) & 1);             // the control warp has acquired the rows at gpu scope
+          // the control warp has acquired the rows at gpu scope and arrived on the slot's named barrier
+          if (seq & 1) asm volatile("bar.sync 5, 160;" ::: "memory");
+          else asm volatile("bar.sync 4, 160;" ::: "memory");
         } else {
           // one warp polls the counter, the other three sleep on a named barrier (bar.sync carries the acquired state over)
           if (lw == 0) wait_counter(L.src_done + mt, L.src_target);

@@ -54,7 +54,7 @@ struct GemmParams {
   __nv_bfloat16* ln_out;  // [M, N] or nullptr
   int* ln_counters;       // [ceil(M/128)] zero before the first launch; the last arriver resets its entry
   float ln_eps;
-  int rmw;                // EPI_F32_ADD: 1 = load + add + TMA store (epilogue_f32_rmw; needs out = the fp32 stream, ldc = N), 0 = TMA reduce-add
+  int rmw;                // EPI_F32_ADD: 1 = load + add + store in the generic proxy (epilogue_f32_rmw; needs out = the fp32 stream), 0 = TMA reduce-add
   int stages_limit;       // debug: use at most this many ring stages (0 = all)
   int dbg_flags;          // debug (results become wrong!): 1 = every pair loads the SAME A rows, 2 = the same W rows
                           //        (probes whether L2 reads or SM-side delivery bound the loop); 4 = m-fastest tile order
@@ -100,19 +100,23 @@ __device__ __forceinline__ float gelu_fast(float x) { return gelu_tanh_fit(x); }
 #endif
 
 // ---------------------------------------------------------------- fp32 residual epilogue as LOAD + ADD + STORE
-// x[tile] += acc + bias without the L2 reduction path.  A TMA reduce-add round of one epilogue warp (4 KB) takes ~3.1 k cycles
-// against ~1.9 k for a plain TMA store round of the same size, whatever the contention (tools/chain_diag.py: proj 12.4 k,
-// fc2 13.8 k cycles per tile for four rounds): cp.reduce.async.bulk is throttled per SM, not by the chip's L2 bandwidth, and
-// a K = 768 residual phase (patch embed, proj) is epilogue-bound at half the tensor rate.  Every element of the stream has
-// exactly ONE writer per phase (no split-K), so that writer can do the add itself: the warp reads its 32 x 32 fp32 box of x
-// out of L2 with COALESCED 16-byte loads (ld.global.cg; eight lanes per 128-byte row segment, four rows per instruction --
-// one lane per row was measured 2.6 times slower than the reduce-add: 256 partial-sector requests per box), parks the box in
-// its staging buffer in the tensor map's swizzled layout, each lane then adds its own row in place -- fl(x + fl(acc + bias)),
-// the very two roundings of the reduce-add form, hence bit-identical -- and the buffer leaves as a plain TMA store.  The loads
-// of box c + 1 are issued as soon as box c's registers are parked, so their latency runs under the adds, the store and the
-// next round's wait for the staging buffer.  Box 0 may be requested before the accumulator is ready whenever the rows were last
-// written by an EARLIER launch (proj, patch embed); inside a chained launch the rows of a later residual phase (fc2) are
-// complete once the tile's A operand is (proj -> LayerNorm -> fc1 -> this tile), so they are requested after acc_full.
+// x[tile] += acc + bias without TMA on the way out.  What a residual epilogue round costs is not the add but the staging
+// buffer's round trip through the TMA unit: one warp's 4 KB round takes ~3.4 k cycles as a TMA reduce-add, ~2.6 k as a plain
+// TMA store (tools/chain_diag.py: proj 13.7 k, fc2 14.2 k cycles per tile for four rounds, qkv 5.3 k for two), nearly all of
+// it cp.async.bulk.wait_group.read before the buffer may be overwritten.  A K = 768 residual phase (patch embed, proj) is
+// therefore epilogue-bound at half the tensor rate, and the epilogue of its last tiles heads the chain proj -> LayerNorm ->
+// first fc1 tile that every cluster waits on.  Every element of the stream has exactly ONE writer per phase (no split-K), so
+// that writer can do the add itself, in the generic proxy: the warp reads its 32 x 32 fp32 box of x out of L2 with coalesced
+// 16-byte loads (ld.global.cg; eight lanes per 128-byte row segment, four rows per instruction), transposes acc + bias from
+// the accumulator's row-per-lane layout into that same layout through its staging buffer (plain st.shared / ld.shared, the
+// buffer is free again after a __syncwarp), adds -- fl(x + fl(acc + bias)), the very two roundings of the reduce-add form,
+// hence bit-identical -- and stores the box with coalesced 16-byte st.global.cg.  The loads of box c + 1 are issued as soon as
+// box c is stored.  Box 0 may be requested before the accumulator is ready whenever the rows were last written by an EARLIER
+// launch (proj, patch embed); inside a chained launch the rows of a later residual phase (fc2) are complete once the tile's A
+// operand is (proj -> LayerNorm -> fc1 -> this tile), so they are requested after acc_full.  Measured and dropped on the
+// way: one lane per row for the loads (256 partial-sector requests per box: 2.6 times slower than the reduce-add), and
+// coalesced loads parked in the staging buffer with a TMA store at the end (19 k cycles per proj tile: the wait_group.read
+// stays on the critical path).
 //
 // xr[i]: lane l holds the 16-byte chunk (l & 7) of row 4 i + (l >> 3) of the box whose first row is row0, first column n.
 __device__ __forceinline__ void rmw_load_box(float4 (&xr)[8], const float* __restrict__ x, int ldx, int row0, int lane, int M, int n) {
@@ -121,50 +125,41 @@ __device__ __forceinline__ void rmw_load_box(float4 (&xr)[8], const float* __res
   for (int i = 0; i < 8; ++i) {
     // boxes are 32 columns wide and ldx % 32 == 0: a box lies inside or outside [0, ldx) as a whole
     if (row0 + 4 * i + (lane >> 3) < M && n < ldx) xr[i] = __ldcg(reinterpret_cast<const float4*>(src + static_cast<size_t>(4 * i) * ldx));
-    else xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);                             // clipped by the store
+    else xr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 // NCH boxes of 32 columns from column n_first / TMEM address t_col0 on; xr holds box 0.
 template <int NCH>
 __device__ __forceinline__ void epilogue_f32_rmw(uint32_t t_col0, int n_first, int row0, int M, const float* __restrict__ bias,
-                                                 const float* __restrict__ x, int ldx, float4 (&xr)[8], uint8_t* stile, int lane,
-                                                 const CUtensorMap* tmap) {
+                                                 float* __restrict__ x, int ldx, float4 (&xr)[8], uint8_t* stile, int lane) {
   const int sw = lane & 7;
-  uint8_t* srow = stile + lane * 128;               // staging row = lane, 16-byte chunk index XOR (row % 8): SWIZZLE_128B
+  uint8_t* srow = stile + lane * 128;               // row = lane, 16-byte chunk index XOR (row % 8): conflict-free both ways
+  if (elect_one()) tma_store_wait_read<0>();        // a TMA store of an earlier (bf16) tile may still be reading the buffer
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
     const int n = n_first + 32 * c;
     uint32_t r[32];
     tmem_ld32(t_col0 + 32 * c, r);
     tmem_ld_wait();
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + j));
-      v[j] = __uint_as_float(r[j]) + b4.x; v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
-      v[j + 2] = __uint_as_float(r[j + 2]) + b4.z; v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-    }
-    if (elect_one()) tma_store_wait_read<0>();      // previous store has finished reading the staging tile
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {                   // park the box: row 4 i + lane / 8, chunk lane % 8
-      const int row = 4 * i + (lane >> 3);
-      *reinterpret_cast<float4*>(stile + row * 128 + (((lane & 7) ^ (row & 7)) << 4)) = xr[i];
-    }
-    __syncwarp();
-    if (c + 1 < NCH) rmw_load_box(xr, x, ldx, row0, lane, M, n + 32);           // in flight until the next round parks it
+    __syncwarp();                                   // the previous round's reads of the staging buffer are done
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      float4* cell = reinterpret_cast<float4*>(srow + ((q ^ sw) << 4));
-      const float4 x4 = *cell;
-      *cell = make_float4(x4.x + v[4 * q], x4.y + v[4 * q + 1], x4.z + v[4 * q + 2], x4.w + v[4 * q + 3]);
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + 4 * q));
+      *reinterpret_cast<float4*>(srow + ((q ^ sw) << 4)) =
+          make_float4(__uint_as_float(r[4 * q]) + b4.x, __uint_as_float(r[4 * q + 1]) + b4.y, __uint_as_float(r[4 * q + 2]) + b4.z,
+                      __uint_as_float(r[4 * q + 3]) + b4.w);
     }
-    fence_proxy_async_smem();                       // staging writes -> visible to the TMA engine
     __syncwarp();
-    if (n < ldx && elect_one()) {                   // (a column tile may overhang N when N % BN != 0)
-      tma_store_2d(tmap, stile, n, row0);           // rows past M are clipped by the tensor map
-      tma_store_commit();
+    float* dst = x + static_cast<size_t>(row0 + (lane >> 3)) * ldx + n + 4 * (lane & 7);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = 4 * i + (lane >> 3);
+      const float4 t = *reinterpret_cast<const float4*>(stile + row * 128 + (((lane & 7) ^ (row & 7)) << 4));
+      if (row0 + row < M && n < ldx)
+        __stcg(reinterpret_cast<float4*>(dst + static_cast<size_t>(4 * i) * ldx),
+               make_float4(xr[i].x + t.x, xr[i].y + t.y, xr[i].z + t.z, xr[i].w + t.w));
     }
+    if (c + 1 < NCH) rmw_load_box(xr, x, ldx, row0, lane, M, n + 32);           // in flight under the next round's TMEM read
   }
 }
 
@@ -384,7 +379,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if constexpr (EPI == EPI_F32_ADD) {
         if (rmw)
           epilogue_f32_rmw<Cfg::HALF / 32>(t_row + half * Cfg::HALF, n0 + half * Cfg::HALF, m0 + quarter * 32, p.M, p.bias,
-                                           reinterpret_cast<const float*>(p.out), p.ldc, xr, stile, lane, &tmap_out);
+                                           reinterpret_cast<float*>(p.out), p.ldc, xr, stile, lane);
       }
       if constexpr (epi_uses_tma(EPI)) {
         if (!rmw) {

@@ -171,7 +171,13 @@ int vpb_submit_frame_host(vpb_engine* e, const uint8_t* h_frame, int32_t frame_h
 
 /* Introspection used by bench.py / tests. */
 int vpb_kernel_launches(const vpb_engine* e, int32_t batch);          /* kernels one vpb_infer enqueues */
-int vpb_set_option(vpb_engine* e, const char* name, int32_t value);   /* "stop_after", "profile", "pdl", "graph", "ln_fused" */
+/* Options (all keep the results bit-identical unless noted): "stop_after", "profile", "pdl", "graph", "ln_fused",
+ * "chain" (chained persistent launches, default 1), "chain_min_batch" (smallest batch that takes them, default 48),
+ * "ln_in_gemm" (LayerNorm + its consumer GEMM as one launch on the unchained path, default 0), "gelu_erf" (fc1 epilogue with
+ * erf instead of the fitted tanh form: rounding-level differences), "ln_ctl" (chained launches: counter polls / publishes of
+ * the LayerNorm jobs on a control warp, default 1; VPB_LN_CTL), "ln_job_rows" (8 | 16 rows per LayerNorm job, default 16),
+ * "resid_rmw" (residual epilogues as load + add + store instead of TMA reduce-add: measured slower, default 0; VPB_RESID_RMW). */
+int vpb_set_option(vpb_engine* e, const char* name, int32_t value);
 /* With option "profile"=1 every launch is bracketed by a CUDA-event pair on its stream; collect() synchronises,
  * sums elapsed ms and launch counts per kernel class (arrays of vpb_profile_classes() entries) and resets. */
 int vpb_profile_classes(void);
