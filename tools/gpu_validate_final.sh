@@ -2,8 +2,7 @@
 # Final validation of the round-2 build: the whole `-m gpu` suite, smoke(), the driver-length bench (N = 1)
 mkdir -p gpurun_out/r2z
 timeout 330 python -m pytest tests -m gpu -q -x > gpurun_out/r2z/pytest.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/r2z/pytest.log
-timeout 90 python __graft_entry__.py smoke > gpurun_out/r2z/smoke.log 2>&1; echo "smoke exit $?"; tail -1 gpurun_out/r2z/smoke.log
-timeout 150 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2z/bench_driver_len.json 2> gpurun_out/r2z/bench_driver_len.err; echo "bench exit $?"
+timeout 100 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-frame-path > gpurun_out/r2z/bench_driver_len.json 2> gpurun_out/r2z/bench_driver_len.err; echo "bench exit $?"
 python - <<'PY'
 import json
 try:
@@ -16,3 +15,4 @@ try:
 except Exception as e:
     print("bench parse failed", e)
 PY
+timeout 60 python __graft_entry__.py smoke > gpurun_out/r2z/smoke.log 2>&1; echo "smoke exit $?"; tail -1 gpurun_out/r2z/smoke.log
