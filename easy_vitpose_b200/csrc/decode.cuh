@@ -23,7 +23,8 @@ __device__ __constant__ float c_gauss11[6] = {0x1.20c256p-7f, 0x1.bcb86ap-6f, 0x
                                               0x1.f2464cp-4f, 0x1.6a7e1ep-3f, 0x1.9ac20ap-3f};
 
 // Modulation kernels other than 11 (keypoints_from_heatmaps' `kernel` argument, top_down_eval.py:499; 17 for sigma = 3): taps by
-// distance from the centre, filled on the host (engine.cu: gauss_taps) the way cv2.getGaussianKernel(k, 0) computes them.
+// distance from the centre, filled on the host (engine.cu: gauss_taps) the way cv2.getGaussianKernel(k, 0) returns them (the
+// formula from 11 taps on, fixed tables below).
 constexpr int MAX_RADIUS = 17;                              // kernel sizes up to 35
 struct GaussTaps {
   int radius = 5;
@@ -33,6 +34,30 @@ struct GaussTaps {
 __device__ __forceinline__ int reflect101(int i, int n) {
   i = i < 0 ? -i : i;
   return i >= n ? 2 * (n - 1) - i : i;
+}
+// Row pass of cv2's separable float32 filter at one output sample; at(j) = the input sample at offset j - R, t[d] = the tap at
+// distance d.  7 taps and more accumulate left to right (acc = 0; acc = fmaf(k[j], x[j], acc)); 3 and 5 taps take cv2's
+// small-kernel row filter, which starts with the inner pair: acc = (x[-1] + x[+1]) * k1; acc = fmaf(k0, x[0], acc);
+// acc = fmaf(k2, x[-2] + x[+2], acc)  (oracle/vitpose_oracle.py: row_pass, pinned on cv2 bit for bit).
+template <typename F>
+__device__ __forceinline__ float blur_row(const float* t, int R, F&& at) {
+  if (R == 1 || R == 2) {
+    float acc = __fmul_rn(__fadd_rn(at(R - 1), at(R + 1)), t[1]);
+    acc = __fmaf_rn(t[0], at(R), acc);
+    if (R == 2) acc = __fmaf_rn(t[2], __fadd_rn(at(0), at(4)), acc);
+    return acc;
+  }
+  float acc = 0.0f;
+  for (int j = 0; j <= 2 * R; ++j) acc = __fmaf_rn(t[j < R ? R - j : j - R], at(j), acc);
+  return acc;
+}
+// `_gaussian_blur` (top_down_eval.py:443-455) blurs the map inside a zero border of width R; cv2's column filter is vectorised
+// over x in steps of 8 and the columns of the (48 + 2R)-wide image past the last full step run through its scalar loop, whose
+// products are not fused.  First visible column handled that way (HM_W if none: only 5 and 7 taps reach visible columns).
+__host__ __device__ __forceinline__ int zero_padded_tail_start(int R) {
+  if (R < 2) return 48;
+  const int s = 8 * ((48 + 2 * R) / 8) - R;
+  return s < 48 ? s : 48;
 }
 __device__ __forceinline__ bool arg_better(float v, int i, float bv, int bi) {
   // np.argmax order: NaN beats everything, first index wins among equals
@@ -166,8 +191,12 @@ __global__ void __launch_bounds__(DECODE_WARPS * 32) decode_heatmaps(const Decod
       if (pt == i) { m = pmap[i]; cx = ptx[i]; cy = pty[i]; }
     const float* rowp = m + reflect101(cy - R + r, HM_H) * HM_W;
     float acc = 0.0f;
+    if constexpr (GENERIC) {
+      acc = blur_row(p.taps.t, R, [&](int j) { return __ldg(rowp + reflect101(cx - R + j, HM_W)); });
+    } else {
 #pragma unroll
-    for (int j = 0; j < KS; ++j) acc = __fmaf_rn(tap(j < R ? R - j : j - R), __ldg(rowp + reflect101(cx - R + j, HM_W)), acc);
+      for (int j = 0; j < KS; ++j) acc = __fmaf_rn(tap(j < R ? R - j : j - R), __ldg(rowp + reflect101(cx - R + j, HM_W)), acc);
+    }
     s_rowpass[wib][pt][r] = acc;
   }
   __syncwarp();
@@ -283,9 +312,7 @@ __device__ __forceinline__ float blur_point_reflect(const float* m, int cx, int 
   const int lane = threadIdx.x & 31, R = tp.radius;
   for (int r = lane; r <= 2 * R; r += 32) {
     const float* rowp = m + reflect101(cy - R + r, HM_H) * HM_W;
-    float acc = 0.0f;
-    for (int j = 0; j <= 2 * R; ++j) acc = __fmaf_rn(tp.t[j < R ? R - j : j - R], __ldg(rowp + reflect101(cx - R + j, HM_W)), acc);
-    s_rows[r] = acc;
+    s_rows[r] = blur_row(tp.t, R, [&](int j) { return __ldg(rowp + reflect101(cx - R + j, HM_W)); });
   }
   __syncwarp();
   float acc = __fmul_rn(tp.t[0], s_rows[R]);
@@ -306,10 +333,7 @@ __device__ __forceinline__ void decode_combined(const DecodeModesParams& p, floa
   const int R = p.taps_wide.radius;
   for (int i = tid; i < HM_PIX; i += 256) {
     const int y = i / HM_W, x = i % HM_W;
-    float acc = 0.0f;
-    for (int j = 0; j <= 2 * R; ++j)
-      acc = __fmaf_rn(p.taps_wide.t[j < R ? R - j : j - R], s_a[y * HM_W + reflect101(x - R + j, HM_W)], acc);
-    s_b[i] = acc;
+    s_b[i] = blur_row(p.taps_wide.t, R, [&](int j) { return s_a[y * HM_W + reflect101(x - R + j, HM_W)]; });
   }
   __syncthreads();
   for (int i = tid; i < HM_PIX; i += 256) {
@@ -366,20 +390,19 @@ __global__ void __launch_bounds__(256) decode_modes(const DecodeModesParams p) {
     const int R = p.taps.radius;
     for (int i = tid; i < HM_PIX; i += 256) {
       const int y = i / HM_W, x = i % HM_W;
-      float acc = 0.0f;
-      for (int j = 0; j <= 2 * R; ++j) {
+      s_b[i] = blur_row(p.taps.t, R, [&](int j) {
         const int xx = x - R + j;
-        acc = __fmaf_rn(p.taps.t[j < R ? R - j : j - R], (xx >= 0 && xx < HM_W) ? s_a[y * HM_W + xx] : 0.0f, acc);
-      }
-      s_b[i] = acc;
+        return (xx >= 0 && xx < HM_W) ? s_a[y * HM_W + xx] : 0.0f;
+      });
     }
     __syncthreads();
     for (int i = tid; i < HM_PIX; i += 256) {
       const int y = i / HM_W, x = i % HM_W;
       float acc = __fmul_rn(p.taps.t[0], s_b[i]);
+      const bool unfused = x >= zero_padded_tail_start(R);      // cv2's scalar tail (5 and 7 taps: the last visible columns)
       for (int d = 1; d <= R; ++d) {
         const float lo = y - d >= 0 ? s_b[(y - d) * HM_W + x] : 0.0f, hi = y + d < HM_H ? s_b[(y + d) * HM_W + x] : 0.0f;
-        acc = __fmaf_rn(p.taps.t[d], __fadd_rn(hi, lo), acc);
+        acc = unfused ? __fadd_rn(acc, __fmul_rn(p.taps.t[d], __fadd_rn(hi, lo))) : __fmaf_rn(p.taps.t[d], __fadd_rn(hi, lo), acc);
       }
       s_a[i] = acc;                                          // the raw map is no longer needed
     }

@@ -1150,11 +1150,21 @@ extern "C" int vpb_flip_back(const float* d_in, int32_t n, int32_t k, const int3
   return VPB_OK;
 }
 // cv2.getGaussianKernel(ksize, sigma <= 0) for a CV_32F image: sigma = 0.3 * ((ksize - 1) * 0.5 - 1) + 0.8, exp(-d^2 / (2 sigma^2))
-// normalised to sum 1 in double, stored as float; indexed by the distance from the centre.  ksize odd, 11..35 (cv2 switches to
-// fixed tables at 7 and below, and 9 does not come out bit-exact: oracle/make_golden_modes.py).
+// normalised to sum 1 in double, stored as float; indexed by the distance from the centre.  ksize odd, 1..35; for 9 taps and
+// fewer cv2 returns fixed tables instead (small_gaussian_tab; pinned against cv2 in oracle/make_golden_modes_small.py).
 static bool gauss_taps(int ksize, GaussTaps& tp) {
-  if (ksize < 11 || ksize > 2 * MAX_RADIUS + 1 || ksize % 2 == 0) return false;
+  if (ksize < 1 || ksize > 2 * MAX_RADIUS + 1 || ksize % 2 == 0) return false;
   const int r = ksize / 2;
+  if (ksize <= 9) {
+    static const float small[5][5] = {{1.0f},
+                                      {0.5f, 0.25f},
+                                      {0.375f, 0.25f, 0.0625f},
+                                      {0.28125f, 0.21875f, 0.109375f, 0.03125f},
+                                      {60.0f / 256, 51.0f / 256, 30.0f / 256, 13.0f / 256, 4.0f / 256}};
+    tp.radius = r;
+    for (int d = 0; d <= r; ++d) tp.t[d] = small[r][d];
+    return true;
+  }
   const double sigma = 0.3 * ((ksize - 1) * 0.5 - 1.0) + 0.8;
   double v[2 * MAX_RADIUS + 1], sum = 0.0;
   for (int i = 0; i < ksize; ++i) {
@@ -1174,7 +1184,9 @@ extern "C" int vpb_decode_modes_ex(const float* d_heatmaps, int32_t n, int32_t k
   if (n < 0 || k < 1 || mode < DECODE_NONE || mode > DECODE_COMBINED) return fail(VPB_ERR_ARG, "vpb_decode_modes: n=%d k=%d mode=%d", n, k, mode);
   const bool blurs = mode >= DECODE_UNBIASED;
   GaussTaps taps, wide;
-  if (blurs && !gauss_taps(kernel, taps)) return fail(VPB_ERR_ARG, "vpb_decode_modes: kernel=%d (odd, 11..%d)", kernel, 2 * MAX_RADIUS + 1);
+  if (blurs && !gauss_taps(kernel, taps)) return fail(VPB_ERR_ARG, "vpb_decode_modes: kernel=%d (odd, 1..%d)", kernel, 2 * MAX_RADIUS + 1);
+  if (kernel == 1 && (mode == DECODE_UNBIASED || mode == DECODE_MEGVII))     // the reference's _gaussian_blur raises (border = 0)
+    return fail(VPB_ERR_ARG, "vpb_decode_modes: kernel=1 has no zero-bordered blur (top_down_eval.py:443-455 raises)");
   if (mode == DECODE_COMBINED && !gauss_taps(2 * kernel + 1, wide))
     return fail(VPB_ERR_ARG, "vpb_decode_modes: CombinedTarget blurs with 2*kernel+1 = %d (limit %d)", 2 * kernel + 1, 2 * MAX_RADIUS + 1);
   if (n == 0) return VPB_OK;

@@ -4,7 +4,7 @@ reference function at easy_ViTPose/vit_utils/top_down_eval.py:493-641.
 `decode_heatmaps` is the fast form of the branch VitInference takes (unbiased=True, use_udp=True: DARK/UDP with
 centre = scale // 2, easy_ViTPose/inference.py:200-203).  `keypoints_from_heatmaps` covers every GaussianHeatmap
 branch of the reference function with general centre / scale; `decode_topdown` is
-TopdownHeatmapBaseHead.decode on top of it, including modulation kernels 11..35 and target_type='CombinedTarget'.
+TopdownHeatmapBaseHead.decode on top of it, including modulation kernels 1..35 and target_type='CombinedTarget'.
 """
 from __future__ import annotations
 
@@ -61,9 +61,11 @@ def keypoints_from_heatmaps(heatmaps, center, scale, unbiased=False, post_proces
 
     Every branch is built: post_process None / 'default' / 'unbiased' / 'megvii' with use_udp=False, the DARK/UDP branch
     (use_udp=True; the one VitInference.postprocess takes) and use_udp=True with target_type='CombinedTarget' (:580-593, heatmaps
-    [N,3K,64,48] -> K keypoints).  `kernel` is any odd size 11..35 (cv2 builds smaller kernels from fixed tables; not built);
-    CombinedTarget blurs the response maps with 2*kernel+1, so kernel <= 17 there.  Like the reference, CombinedTarget only
-    accepts N = 1: its index arithmetic (:589) does not broadcast for larger N."""
+    [N,3K,64,48] -> K keypoints).  `kernel` is any odd size 1..35 (cv2's fixed tables below 11, its small-kernel summation order
+    for 3 and 5 taps and the scalar tail of its column filter for 5 and 7 are reproduced bit for bit); CombinedTarget blurs the
+    response maps with 2*kernel+1, so kernel <= 17 there; kernel = 1 with post_process 'unbiased' / 'megvii' raises ValueError as
+    the reference's `_gaussian_blur` does (a zero-width border, :453).  Like the reference, CombinedTarget only accepts N = 1: its
+    index arithmetic (:589) does not broadcast for larger N."""
     # the reference's conflict checks (:548-553) and config normalisation (:556-579), deprecation warnings dropped
     if unbiased:
         assert post_process not in [False, None, "megvii"]
@@ -83,8 +85,10 @@ def keypoints_from_heatmaps(heatmaps, center, scale, unbiased=False, post_proces
     if post_process not in _MODES:
         raise ValueError(f"unknown post_process {post_process!r}")
     blurs = use_udp or post_process in ("unbiased", "megvii")
-    if blurs and (int(kernel) != kernel or kernel % 2 == 0 or not 11 <= kernel <= (17 if combined else 35)):
-        raise NotImplementedError(f"modulation kernel {kernel}: odd sizes 11..{17 if combined else 35} are built")
+    if blurs and (int(kernel) != kernel or kernel % 2 == 0 or not 1 <= kernel <= (17 if combined else 35)):
+        raise NotImplementedError(f"modulation kernel {kernel}: odd sizes 1..{17 if combined else 35} are built")
+    if kernel == 1 and not use_udp and post_process in ("unbiased", "megvii"):
+        raise ValueError("could not broadcast input array from shape (64,48) into shape (0,0)")       # the reference's :453 with border = 0
 
     if len(heatmaps.shape) != 4 or tuple(heatmaps.shape[2:]) != (64, 48):
         raise ValueError(f"expected [N,K,64,48], got {tuple(heatmaps.shape)}")

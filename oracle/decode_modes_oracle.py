@@ -11,7 +11,8 @@ easy_ViTPose/vit_utils/top_down_eval.py:493-641 and the general (float centre / 
   post_process='megvii'            :573-574 blur first, then argmax of the BLURRED maps, +-0.25, +0.5, scores / 255 + 0.5
   use_udp=True (GaussianHeatmap)   :576-579 DARK/UDP with any centre / scale (decode_maps restricts centre to scale // 2)
   use_udp=True (CombinedTarget)    :580-593 response maps blurred with 2*kernel+1, offset maps with kernel, offsets at the arg-max
-  kernel                           any odd modulation kernel 11..35 (cv2.getGaussianKernel computes those; <= 7 are fixed tables)
+  kernel                           any odd modulation kernel 1..35 (cv2.getGaussianKernel computes 11 and up; <= 9 are fixed tables,
+                                   3 and 5 taps take cv2's small-kernel row pass: vitpose_oracle.row_pass)
   transform_preds                  post_processing/post_transforms.py:150-194, both the /W (:186-187) and /(W-1) (:183-184) forms
 
 Parity: PINNED.  oracle/make_golden_modes.py runs the unmodified reference function on seeded maps for every mode and both
@@ -38,14 +39,31 @@ def blur_zero_padded(h: np.ndarray, taps: np.ndarray) -> np.ndarray:
     r = (len(taps) - 1) // 2
     p = np.zeros((H + 2 * r, W + 2 * r), np.float32)
     p[r:r + H, r:r + W] = h
-    rowpass = np.zeros((H + 2 * r, W), np.float32)
-    for j in range(2 * r + 1):
-        rowpass = O._fma32(np.broadcast_to(taps[j], rowpass.shape), p[:, j:j + W], rowpass)
+    rowpass = O.row_pass([p[:, j:j + W] for j in range(2 * r + 1)], taps)
     acc = (taps[r] * rowpass[r:r + H]).astype(np.float32)
     for d in range(1, r + 1):
         pair = (rowpass[r + d:r + d + H] + rowpass[r - d:r - d + H]).astype(np.float32)
         acc = O._fma32(np.broadcast_to(taps[r + d], acc.shape), pair, acc)
+    # cv2's column filter is vectorised over x in steps of 8; the columns of the (W + 2r)-wide bordered image past the last
+    # full step go through its scalar loop, whose products are NOT fused: acc += k[d] * (row[y+d] + row[y-d]) with two
+    # roundings.  With W = 48 that reaches visible columns only for 5 and 7 taps (bordered widths 52 / 54: visible columns 46.. /
+    # 45..; 3 taps go through cv2's small column filter, whose tail computes the same); found by matching cv2 bit for bit (oracle/make_golden_modes_small.py).
+    tail = zero_padded_tail_start(W, r)
+    if tail < W:
+        t = (taps[r] * rowpass[r:r + H, tail:]).astype(np.float32)
+        for d in range(1, r + 1):
+            pair = (rowpass[r + d:r + d + H, tail:] + rowpass[r - d:r - d + H, tail:]).astype(np.float32)
+            t = (t + (taps[r + d] * pair).astype(np.float32)).astype(np.float32)
+        acc[:, tail:] = t
     return acc
+
+
+def zero_padded_tail_start(W: int, r: int) -> int:
+    """First visible column that cv2's column filter handles in its scalar (unfused) loop when the map is blurred inside a zero
+    border of width r (`_gaussian_blur`, top_down_eval.py:443-455); W if none."""
+    if r < 2:
+        return W                                   # 3 taps: cv2's small column filter, the same arithmetic in its tail
+    return min(W, max(0, 8 * ((W + 2 * r) // 8) - r))
 
 
 def blur_reflect101(h: np.ndarray, taps: np.ndarray) -> np.ndarray:
@@ -54,9 +72,7 @@ def blur_reflect101(h: np.ndarray, taps: np.ndarray) -> np.ndarray:
     H, W = h.shape
     r = (len(taps) - 1) // 2
     p = np.pad(h.astype(np.float32), r, mode="reflect")
-    rowpass = np.zeros((H + 2 * r, W), np.float32)
-    for j in range(2 * r + 1):
-        rowpass = O._fma32(np.broadcast_to(taps[j], rowpass.shape), p[:, j:j + W], rowpass)
+    rowpass = O.row_pass([p[:, j:j + W] for j in range(2 * r + 1)], taps)
     acc = (taps[r] * rowpass[r:r + H]).astype(np.float32)
     for d in range(1, r + 1):
         pair = (rowpass[r + d:r + d + H] + rowpass[r - d:r - d + H]).astype(np.float32)

@@ -281,10 +281,23 @@ def forward_heatmaps(x: np.ndarray, sd: dict, depth: int, heads: int) -> np.ndar
 # --------------------------------------------------------------------------------------
 # decode: argmax + DARK/UDP Taylor refine + UDP map to crop pixels
 # --------------------------------------------------------------------------------------
+# cv2.getGaussianKernel(k, sigma <= 0) does not evaluate the formula for k <= 9: it returns fixed tables (OpenCV 4.13:
+# small_gaussian_tab).  Pinned against cv2 itself in oracle/make_golden_modes_small.py.
+_SMALL_GAUSSIAN_TAPS = {
+    1: [1.0],
+    3: [0.25, 0.5, 0.25],
+    5: [0.0625, 0.25, 0.375, 0.25, 0.0625],
+    7: [0.03125, 0.109375, 0.21875, 0.28125, 0.21875, 0.109375, 0.03125],
+    9: [4 / 256, 13 / 256, 30 / 256, 51 / 256, 60 / 256, 51 / 256, 30 / 256, 13 / 256, 4 / 256],
+}
+
+
 def gaussian_taps(ksize: int = 11) -> np.ndarray:
     """cv2.getGaussianKernel(ksize, sigma<=0): sigma = 0.3*((ksize-1)*0.5-1)+0.8 (=2.0 for 11),
     coefficients exp(-(i-c)^2/(2 sigma^2)) normalised to sum 1, held as float32 for a
-    CV_32F image.  Called from vit_utils/top_down_eval.py:385 with kernel=11."""
+    CV_32F image (fixed tables for ksize <= 9).  Called from vit_utils/top_down_eval.py:385 with kernel=11."""
+    if ksize in _SMALL_GAUSSIAN_TAPS:
+        return np.asarray(_SMALL_GAUSSIAN_TAPS[ksize], np.float32)
     sigma = 0.3 * ((ksize - 1) * 0.5 - 1.0) + 0.8
     i = np.arange(ksize, dtype=np.float64) - (ksize - 1) / 2.0
     k = np.exp(-(i * i) / (2.0 * sigma * sigma))
@@ -302,6 +315,26 @@ def _fma32(a: np.ndarray, b: np.ndarray, c: np.ndarray) -> np.ndarray:
     return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
 
 
+def row_pass(cols: "list[np.ndarray]", taps: np.ndarray) -> np.ndarray:
+    """Row pass of cv2's separable float32 filter over the 2r+1 shifted sample arrays `cols` (cols[j] = the samples at offset
+    j - r).  Kernels of 7 taps and more accumulate left to right, acc = 0; acc = fmaf(k[j], x[j], acc).  Kernels of 3 and 5
+    taps take cv2's small-kernel path, which sums symmetrically and starts with the inner pair:
+    acc = (x[-1] + x[+1]) * k1; acc = fmaf(k0, x[0], acc); acc = fmaf(k2, x[-2] + x[+2], acc)   (found by matching
+    cv2.GaussianBlur bit for bit; oracle/make_golden_modes_small.py re-checks it on whole maps)."""
+    n = len(taps)
+    r = (n - 1) // 2
+    if n in (3, 5):
+        acc = ((cols[r - 1] + cols[r + 1]).astype(np.float32) * taps[r + 1]).astype(np.float32)
+        acc = _fma32(np.broadcast_to(taps[r], acc.shape), cols[r], acc)
+        if n == 5:
+            acc = _fma32(np.broadcast_to(taps[r + 2], acc.shape), (cols[r - 2] + cols[r + 2]).astype(np.float32), acc)
+        return acc
+    acc = np.zeros(np.shape(cols[0]), np.float32)
+    for j in range(n):
+        acc = _fma32(np.broadcast_to(taps[j], acc.shape), cols[j], acc)
+    return acc
+
+
 def blur_at(h: np.ndarray, xs: np.ndarray, ys: np.ndarray, taps: np.ndarray) -> np.ndarray:
     """Value of cv2.GaussianBlur(h, (11,11), 0) (float32, BORDER_REFLECT_101 = cv2 default) at the
     integer points (xs, ys) of map h [H,W].  Only the points the Taylor stencil consumes are
@@ -309,7 +342,7 @@ def blur_at(h: np.ndarray, xs: np.ndarray, ys: np.ndarray, taps: np.ndarray) -> 
 
     Accumulation order is the one cv2 4.13's separable float filter uses, found by matching
     cv2.GaussianBlur bit for bit on random maps (oracle/make_golden.py re-checks it):
-      row pass    acc = 0; for j = 0..10 (left to right): acc = fmaf(k[j], x[c-5+j], acc)
+      row pass    acc = 0; for j = 0..10 (left to right): acc = fmaf(k[j], x[c-5+j], acc)     (3 / 5 taps: see row_pass)
       column pass acc = k[5]*r[y]; for d = 1..5: acc = fmaf(k[5+d], r[y+d] + r[y-d], acc)
     """
     H, W = h.shape
@@ -320,9 +353,7 @@ def blur_at(h: np.ndarray, xs: np.ndarray, ys: np.ndarray, taps: np.ndarray) -> 
         rows = _reflect101(y + off, H)
         cols = _reflect101(x + off, W)
         win = h[np.ix_(rows, cols)].astype(np.float32)          # [2r+1 rows, 2r+1 cols]
-        rowpass = np.zeros(len(off), np.float32)
-        for j in range(len(off)):
-            rowpass = _fma32(np.broadcast_to(taps[j], rowpass.shape), win[:, j], rowpass)
+        rowpass = row_pass([win[:, j] for j in range(len(off))], taps)
         acc = np.float32(taps[r] * rowpass[r])
         for d in range(1, r + 1):
             pair = np.float32(rowpass[r + d] + rowpass[r - d])

@@ -111,8 +111,12 @@ def test_decode_api_fails_loudly_without_cuda_and_checks_its_config():
                                 target_type="CombinedTarget")
     with pytest.raises(ValueError):
         keypoints_from_heatmaps(hm, c, s, use_udp=True, target_type="nonsense")
-    with pytest.raises(NotImplementedError):                          # cv2 builds kernels <= 7 from fixed tables: not built
-        keypoints_from_heatmaps(hm, c, s, post_process="unbiased", kernel=7)
+    with pytest.raises(NotImplementedError):                          # even / oversized modulation kernels
+        keypoints_from_heatmaps(hm, c, s, post_process="unbiased", kernel=8)
+    with pytest.raises(NotImplementedError):
+        keypoints_from_heatmaps(hm, c, s, post_process="megvii", kernel=37)
+    with pytest.raises(ValueError):                                   # kernel = 1: the reference's _gaussian_blur raises (zero-width border)
+        keypoints_from_heatmaps(hm, c, s, post_process="unbiased", kernel=1)
     with pytest.raises(NotImplementedError):                          # CombinedTarget blurs with 2 * kernel + 1 <= 35
         keypoints_from_heatmaps(hm[:, :15], c, s, use_udp=True, kernel=19, target_type="CombinedTarget")
     with pytest.raises(ValueError):

@@ -95,3 +95,34 @@ def test_flip_back_matches_reference_digest(golden):
         assert np.array_equal(np.frombuffer(hashlib.sha256(mine.tobytes()).digest(), np.uint8), g[f"flip_digest_shift{int(shift)}"])
     twice = M.flip_back(M.flip_back(maps, M.COCO_FLIP_PAIRS), M.COCO_FLIP_PAIRS)
     assert np.array_equal(twice, maps, equal_nan=True)                                 # an involution
+
+
+@pytest.mark.parametrize("kernel", [1, 3, 5, 7, 9])
+@pytest.mark.parametrize("tag", ["f32", "i64"])
+def test_small_kernels_match_reference(golden_dir, kernel, tag):
+    """Modulation kernels below 11 (tests/golden/decode_modes_small.npz, oracle/make_golden_modes_small.py): cv2 returns fixed tap
+    tables there, sums 3 and 5 taps in its small-kernel order and runs the last visible columns of the zero-bordered 5- / 7-tap
+    blur through the unfused tail of its column filter; the generating script pins all three on cv2 pixel by pixel."""
+    g = np.load(os.path.join(golden_dir, "decode_modes_small.npz"))
+    N, K, seed = (int(v) for v in g["meta"])
+    maps = O.make_decode_maps(N, K, seed)
+    c, s = (g["center32"], g["scale32"]) if tag == "f32" else (g["center64"], g["scale64"])
+    for pp, udp in (("unbiased", False), ("megvii", False), ("default", True)):
+        if kernel == 1 and not udp:
+            continue                                                # the reference's _gaussian_blur raises for kernel = 1
+        preds, maxvals, _ = M.keypoints_from_heatmaps(maps, c, s, post_process=pp, use_udp=udp, kernel=kernel)
+        key = f"k{kernel}_{pp}_{'udp' if udp else 'std'}_{tag}"
+        assert np.array_equal(maxvals, g[key + "_maxvals"], equal_nan=True)
+        ref = g[key + "_preds"]
+        if pp == "megvii":
+            assert np.array_equal(preds, ref, equal_nan=True)
+        else:
+            assert np.array_equal(np.isnan(preds), np.isnan(ref)) and np.nanmax(np.abs(preds - ref)) < 1e-3
+
+
+def test_small_kernel_taps_and_tail_rule():
+    assert np.array_equal(O.gaussian_taps(9) * 256, [4, 13, 30, 51, 60, 51, 30, 13, 4])
+    assert np.array_equal(O.gaussian_taps(5) * 16, [1, 4, 6, 4, 1]) and O.gaussian_taps(1).tolist() == [1.0]
+    assert abs(float(O.gaussian_taps(11).sum()) - 1.0) < 1e-6
+    # visible columns of a 48-wide map that cv2's column filter handles in its scalar tail when the map sits in a zero border
+    assert [M.zero_padded_tail_start(48, r) for r in (1, 2, 3, 4, 5, 8, 17)] == [48, 46, 45, 48, 48, 48, 48]

@@ -66,6 +66,56 @@ def test_kernel_17_vs_reference_fixture(golden_dir, pp, udp, tag):
     _check(preds, maxvals, g[key + "_preds"], g[key + "_maxvals"], exact=pp == "megvii")
 
 
+@pytest.mark.parametrize("kernel", [1, 3, 5, 7, 9])
+@pytest.mark.parametrize("tag", ["f32", "i64"])
+def test_small_kernels_vs_reference_fixture(golden_dir, kernel, tag):
+    """Modulation kernels below 11 against the unmodified reference (tests/golden/decode_modes_small.npz): cv2's fixed tap tables,
+    its small-kernel row order for 3 / 5 taps and the unfused tail of its column filter for 5 / 7 taps in the zero-bordered blur.
+    megvii (scores and quarter-pixel coordinates straight from the blurred map) is bit-exact; kernel = 1 only exists with use_udp."""
+    from easy_vitpose_b200 import keypoints_from_heatmaps
+    g = np.load(os.path.join(golden_dir, "decode_modes_small.npz"))
+    N, K, seed = (int(v) for v in g["meta"])
+    maps = O.make_decode_maps(N, K, seed)
+    c, s = (g["center32"], g["scale32"]) if tag == "f32" else (g["center64"], g["scale64"])
+    for pp, udp in (("unbiased", False), ("megvii", False), ("default", True)):
+        if kernel == 1 and not udp:
+            continue
+        preds, maxvals = keypoints_from_heatmaps(maps, c, s, post_process=pp, use_udp=udp, kernel=kernel)
+        key = f"k{kernel}_{pp}_{'udp' if udp else 'std'}_{tag}"
+        _check(preds, maxvals, g[key + "_preds"], g[key + "_maxvals"], exact=pp == "megvii")
+
+
+@pytest.mark.parametrize("kernel", [3, 5, 7, 9])
+def test_small_kernels_vs_oracle_on_more_maps(kernel):
+    """The whole blurred map is what megvii's arg-max runs over: index, score and coordinates bit-exact against the oracle (which
+    is pinned on cv2 pixel by pixel) on maps whose peaks sit in the last columns too (the scalar tail of cv2's column filter)."""
+    from easy_vitpose_b200 import keypoints_from_heatmaps
+    N, K = 4, 12
+    maps = O.make_decode_maps(N, K, 3100 + kernel)
+    maps[:, :, :, 40:] += maps[:, :, :, 8:0:-1] * 1.5                                 # mass near the right border
+    rs = np.random.RandomState(kernel)
+    c = rs.uniform(10, 800, (N, 2)).astype(np.float32); s = rs.uniform(40, 500, (N, 2)).astype(np.float32)
+    for pp, udp in (("megvii", False), ("unbiased", False), ("default", True)):
+        preds, maxvals, idx = keypoints_from_heatmaps(maps, c, s, post_process=pp, use_udp=udp, kernel=kernel, return_idx=True)
+        op, om, oi = M.keypoints_from_heatmaps(maps, c, s, post_process=pp, use_udp=udp, kernel=kernel)
+        assert np.array_equal(idx, oi)
+        _check(preds, maxvals, op, om, exact=pp == "megvii")
+
+
+@pytest.mark.parametrize("kernel", [3, 9])
+@pytest.mark.parametrize("tag", ["f32", "i64"])
+def test_combined_target_small_kernels_vs_reference_fixture(golden_dir, kernel, tag):
+    from easy_vitpose_b200 import keypoints_from_heatmaps
+    g = np.load(os.path.join(golden_dir, "decode_modes_small.npz"))
+    N, KC, seed = (int(v) for v in g["meta_combined"])
+    cmaps = M.make_combined_maps(N, KC, seed)
+    c, s = (g["center32"], g["scale32"]) if tag == "f32" else (g["center64"], g["scale64"])
+    for n in range(N):
+        preds, maxvals = keypoints_from_heatmaps(cmaps[n:n + 1], c[n:n + 1], s[n:n + 1], kernel=kernel, use_udp=True, target_type="CombinedTarget")
+        assert np.array_equal(maxvals[0], g[f"comb_k{kernel}_{tag}_maxvals"][n], equal_nan=True)
+        assert np.array_equal(preds[0], g[f"comb_k{kernel}_{tag}_preds"][n], equal_nan=True)
+
+
 @pytest.mark.parametrize("kernel", [13, 23, 35])
 def test_other_kernels_vs_oracle(kernel):
     """Blurred values are bit-exact for every kernel size: megvii's scores and quarter-pixel coordinates come straight from them."""
@@ -140,7 +190,9 @@ def test_config_normalisation_and_errors():
     with pytest.raises(ValueError):
         keypoints_from_heatmaps(maps, c, s, use_udp=True, target_type="CombinedTarget")   # N = 2, 17 maps: as in the reference
     with pytest.raises(NotImplementedError):
-        keypoints_from_heatmaps(maps, c, s, post_process="unbiased", kernel=9)
+        keypoints_from_heatmaps(maps, c, s, post_process="unbiased", kernel=10)
+    with pytest.raises(ValueError):                                                       # kernel = 1: the reference's _gaussian_blur raises
+        keypoints_from_heatmaps(maps, c, s, post_process="megvii", kernel=1)
     # TopdownHeatmapBaseHead.decode with the reference's test_cfg (configs/ViTPose_common.py:123-129)
     metas = [{"center": [96.5, 128.0], "scale": [192.0, 256.0], "image_file": "a.jpg", "bbox_score": 0.9, "bbox_id": 7},
              {"center": [50.0, 60.0], "scale": [120.0, 160.0], "image_file": "b.jpg", "bbox_id": 8}]
