@@ -101,7 +101,7 @@ int vpb_flip_back(const float* d_in, int32_t n, int32_t k, const int32_t* d_perm
  * (centre_x, centre_y, scale_x, scale_y) per crop: float32 arrays keep numpy's arithmetic in float32, int64 / float64 arrays
  * promote it to float64.  Output layout as vpb_decode: d_kpts f32 [n,k,3] (y, x, score), d_idx i32 [n,k] or NULL.
  * vpb_decode_modes is the kernel = 11 form (every reference config: modulate_kernel=11).  vpb_decode_modes_ex adds
- *   kernel        the `kernel` argument (:499): odd, 11..35 (17 for sigma = 3); used by modes 2-5;
+ *   kernel        the `kernel` argument (:499): odd, 1..35 (17 for sigma = 3; 1 only for modes 4-5); used by modes 2-5;
  *   mode 5        use_udp=True with target_type='CombinedTarget' (:580-593): d_heatmaps is f32 [n,3k,64,48], triples of
  *                 (response, offset x, offset y); 2*kernel+1 <= 35; valid_radius = (float)(valid_radius_factor * 64) (:586);
  *                 the (-1,-1) sentinel reads its offsets one row and one pixel before the keypoint's plane, wrapping to the
