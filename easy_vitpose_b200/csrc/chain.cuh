@@ -13,7 +13,9 @@
 //   * the TMA-producer warp of a consuming tile spins (acquire) on the counter of its A rows before its first load;
 //   * LayerNorm runs on four dedicated warps of every CTA, concurrently with that CTA's tensor-core tiles: 16-row jobs handed
 //     out statically (job j -> CTA j mod grid), each waiting for its row block's residual adds to complete; they read the fp32
-//     stream out of L2 (ld.global.cg) and write the bf16 operand rows, then bump the "normalised rows ready" counter.
+//     stream out of L2 (ld.global.cg) and write the bf16 operand rows; the gpu-scope part of a job -- polling the residual
+//     counter, the acquire, the cross-proxy fence and the release that bumps the "normalised rows ready" counter -- runs on a
+//     control warp (ln_ctl, default) so that the LayerNorm warps only load, normalise and store.
 //
 // Dependencies only point to tiles that come earlier in the list (and LN jobs only to tiles), all CTAs are resident (one per
 // SM, grid <= #SMs), every role walks its own list in order (see "Tile list" in the kernel for the order): the smallest unfinished tile can always run, so the waits cannot
