@@ -100,23 +100,24 @@ __device__ __forceinline__ float gelu_fast(float x) { return gelu_tanh_fit(x); }
 #endif
 
 // ---------------------------------------------------------------- fp32 residual epilogue as LOAD + ADD + STORE
-// x[tile] += acc + bias without TMA on the way out.  What a residual epilogue round costs is not the add but the staging
-// buffer's round trip through the TMA unit: one warp's 4 KB round takes ~3.4 k cycles as a TMA reduce-add, ~2.6 k as a plain
-// TMA store (tools/chain_diag.py: proj 13.7 k, fc2 14.2 k cycles per tile for four rounds, qkv 5.3 k for two), nearly all of
-// it cp.async.bulk.wait_group.read before the buffer may be overwritten.  A K = 768 residual phase (patch embed, proj) is
-// therefore epilogue-bound at half the tensor rate, and the epilogue of its last tiles heads the chain proj -> LayerNorm ->
-// first fc1 tile that every cluster waits on.  Every element of the stream has exactly ONE writer per phase (no split-K), so
-// that writer can do the add itself, in the generic proxy: the warp reads its 32 x 32 fp32 box of x out of L2 with coalesced
-// 16-byte loads (ld.global.cg; eight lanes per 128-byte row segment, four rows per instruction), transposes acc + bias from
-// the accumulator's row-per-lane layout into that same layout through its staging buffer (plain st.shared / ld.shared, the
-// buffer is free again after a __syncwarp), adds -- fl(x + fl(acc + bias)), the very two roundings of the reduce-add form,
-// hence bit-identical -- and stores the box with coalesced 16-byte st.global.cg.  The loads of box c + 1 are issued as soon as
-// box c is stored.  Box 0 may be requested before the accumulator is ready whenever the rows were last written by an EARLIER
-// launch (proj, patch embed); inside a chained launch the rows of a later residual phase (fc2) are complete once the tile's A
-// operand is (proj -> LayerNorm -> fc1 -> this tile), so they are requested after acc_full.  Measured and dropped on the
-// way: one lane per row for the loads (256 partial-sector requests per box: 2.6 times slower than the reduce-add), and
-// coalesced loads parked in the staging buffer with a TMA store at the end (19 k cycles per proj tile: the wait_group.read
-// stays on the critical path).
+// x[tile] += acc + bias without the L2 reduction path and without TMA on the way out (option "resid_rmw", OFF by default:
+// bit-identical, measured slower -- kept as the A/B switch and as the record of what does not bound these epilogues).
+// A residual epilogue round of one warp (4 KB) takes ~3.4 k cycles as a TMA reduce-add against ~2.6 k for a bf16 TMA store
+// (tools/chain_diag.py: proj 13.7 k, fc2 14.2 k cycles per tile for four rounds, qkv 5.3 k for two); a K = 768 residual phase
+// (patch embed, proj) is epilogue-bound and its last epilogues head the chain proj -> LayerNorm -> first fc1 tile that every
+// cluster waits on.  Every element of the stream has exactly ONE writer per phase (no split-K), so that writer can do the add
+// itself: the warp reads its 32 x 32 fp32 box of x out of L2 with coalesced 16-byte loads (ld.global.cg; eight lanes per
+// 128-byte row segment, four rows per instruction), transposes acc + bias from the accumulator's row-per-lane layout into
+// that same layout through its staging buffer (plain st.shared / ld.shared, free again after a __syncwarp), adds -- fl(x +
+// fl(acc + bias)), the very two roundings of the reduce-add form, hence bit-identical -- and stores the box with coalesced
+// 16-byte st.global.cg.  The loads of box c + 1 are issued as soon as box c is stored; box 0 may be requested before the
+// accumulator is ready whenever the rows were last written by an EARLIER launch (proj, patch embed); inside a chained launch
+// the rows of a later residual phase (fc2) are complete once the tile's A operand is (proj -> LayerNorm -> fc1 -> this tile),
+// so they are requested after acc_full.
+// Measured on B200 (ViT-B, 64 crops, profiles/r2_ab_resid_rmw.txt), per proj tile / per step against 13.7 k cycles / 2.30-2.37 ms
+// for the reduce-add: (1) one lane per row for the loads + TMA store: 35.6 k / 2.72 ms (256 partial-sector requests per box);
+// (2) coalesced loads parked in the staging buffer, add in place, TMA store: 19.3 k / 2.44 ms; (3) this form, no TMA at all:
+// 20.5 k / 2.37-2.40 ms.  Neither the reduction unit nor the staging buffer's hand-back explains the round time.
 //
 // xr[i]: lane l holds the 16-byte chunk (l & 7) of row 4 i + (l >> 3) of the box whose first row is row0, first column n.
 __device__ __forceinline__ void rmw_load_box(float4 (&xr)[8], const float* __restrict__ x, int ldx, int row0, int lane, int M, int n) {
@@ -363,8 +364,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = kDeconv ? (quarter * 32 + lane < up_pos && mt < num_m) : (row < p.M);
       const long long w0 = clock64();
-      // load + add + store form of the residual epilogue: the rows were completed by an earlier launch, so this lane's first
-      // 32 fp32 of x are requested before the accumulator is ready
+      // load + add + store form of the residual epilogue: the rows were completed by an earlier launch, so the warp's first
+      // 32 x 32 box of x is requested before the accumulator is ready
       [[maybe_unused]] float4 xr[8];
       [[maybe_unused]] bool rmw = false;
       if constexpr (EPI == EPI_F32_ADD) {
